@@ -1,0 +1,747 @@
+// abi.cu -- the C ABI of libtmgpu.so (include/tmgpu.h): vocabulary upload, workspaces, and the
+// host-buffer / device-buffer batch calls.  Host orchestration only; all per-byte work is in
+// kernels.cu.  There is no CPU compute path here: without a CUDA device every compute entry
+// fails with TMGPU_E_CUDA.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/tmgpu.h"
+#include "kernels.h"
+#include "vocab_tables.h"
+
+using namespace tmgpu;
+
+static thread_local std::string g_err;
+
+#define CU(expr)                                                                          \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      g_err = std::string(#expr) + ": " + cudaGetErrorString(e__);                        \
+      return TMGPU_E_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+struct tmgpu_vocab {
+  HostTables host;
+  int device = -1;  // -1: host tables only (parser / table self-tests without a GPU)
+  int sms = 0;
+  int group = 8;    // lanes per string
+  VocabDev dev{};
+  std::vector<void*> allocs;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  tmgpu_workspace* ws = nullptr;  // internal workspace of the host-buffer calls
+  uint8_t* d_in = nullptr;        // staging of host inputs
+  size_t d_in_cap = 0;
+  int64_t* d_off = nullptr;
+  size_t d_off_cap = 0;
+  int64_t* h_off = nullptr;       // pinned
+  size_t h_off_cap = 0;
+};
+
+struct tmgpu_workspace {
+  tmgpu_vocab* v = nullptr;
+  uint32_t max_strings = 0;
+  uint64_t max_bytes = 0;
+  uint32_t slab_pad = 16;
+  uint32_t* slab = nullptr;
+  uint64_t slab_ids = 0;
+  uint32_t* counts = nullptr;   // n + 1 (last = 0 for the scan)
+  uint32_t* need = nullptr;     // n + 1: uncapped counts (overflow re-run)
+  uint32_t* missing = nullptr;
+  uint8_t* status = nullptr;
+  uint64_t* tok_off = nullptr;  // n + 1
+  uint8_t* tokens = nullptr;    // dense serialized ids
+  uint32_t* work_counter = nullptr;
+  uint32_t* overflow = nullptr;
+  void* scan_temp = nullptr;
+  size_t scan_bytes = 0;
+  // decode
+  uint32_t* raw_len = nullptr;  // n + 1
+  uint64_t* raw_off = nullptr;  // n + 1
+  uint32_t* out_len = nullptr;  // n + 1
+  uint64_t* out_off = nullptr;  // n + 1
+  uint8_t* raw = nullptr;
+  uint8_t* dec = nullptr;
+  uint8_t* dense = nullptr;
+  uint64_t dec_cap = 0;
+  std::vector<void*> allocs;
+  int last_launches = 0;
+};
+
+extern "C" const char* tmgpu_last_error(void) { return g_err.c_str(); }
+extern "C" const char* tmgpu_version(void) { return "tokenmonster-b200 0.1 (sm_100a)"; }
+
+extern "C" int tmgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+template <class T>
+static int dev_alloc(std::vector<void*>& pool, T** out, size_t count) {
+  void* p = nullptr;
+  size_t bytes = count * sizeof(T);
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(&p, bytes + 16);
+  if (e != cudaSuccess) {
+    g_err = std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e);
+    return TMGPU_E_NOMEM;
+  }
+  pool.push_back(p);
+  *out = static_cast<T*>(p);
+  return TMGPU_OK;
+}
+
+template <class T>
+static int upload(tmgpu_vocab* v, const T* src, size_t count, const T** out) {
+  T* p = nullptr;
+  int rc = dev_alloc(v->allocs, &p, count);
+  if (rc) return rc;
+  if (count) CU(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+  *out = p;
+  return TMGPU_OK;
+}
+
+extern "C" int tmgpu_vocab_create(const uint8_t* file_bytes, size_t n, int device, tmgpu_vocab** out) {
+  if (!file_bytes || !out) {
+    g_err = "tmgpu_vocab_create: null argument";
+    return TMGPU_E_ARG;
+  }
+  *out = nullptr;
+  auto* v = new tmgpu_vocab();
+  std::string err;
+  int rc = parse_vocab(file_bytes, n, &v->host, &err);
+  if (rc) {
+    g_err = err;
+    delete v;
+    return rc;
+  }
+  const HostTables& h = v->host;
+  if (h.capcode == 1) {
+    g_err = "capcode level 1 (NoCapcodeEncode) has no specification in the reference; unsupported";
+    delete v;
+    return TMGPU_E_UNSUPPORTED;
+  }
+  if (h.capcode == 2 && h.charset == 2) {
+    g_err = "capcode with a UTF-16 vocabulary is unsupported";
+    delete v;
+    return TMGPU_E_UNSUPPORTED;
+  }
+  if (h.normflag & ~7u) {
+    g_err = "normalization flags other than nfd/lowercase/accents are unsupported on the device path";
+    delete v;
+    return TMGPU_E_UNSUPPORTED;
+  }
+  if (const char* g = getenv("TMGPU_GROUP")) {
+    int gi = atoi(g);
+    if (gi == 8 || gi == 16 || gi == 32) v->group = gi;
+  }
+  v->device = device;
+  if (device < 0) {  // host tables only
+    *out = v;
+    return TMGPU_OK;
+  }
+  if (device >= tmgpu_device_count()) {
+    g_err = "no CUDA device " + std::to_string(device) + " (this library has no CPU path)";
+    delete v;
+    return TMGPU_E_CUDA;
+  }
+  auto fail = [&](int code) {
+    tmgpu_vocab_destroy(v);
+    return code;
+  };
+  if (cudaSetDevice(device) != cudaSuccess) {
+    g_err = "cudaSetDevice failed";
+    return fail(TMGPU_E_CUDA);
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    g_err = "cudaGetDeviceProperties failed";
+    return fail(TMGPU_E_CUDA);
+  }
+  v->sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_err = "cudaStreamCreate failed";
+    return fail(TMGPU_E_CUDA);
+  }
+  VocabDev& d = v->dev;
+  std::vector<uint8_t> image(1280);
+  std::memcpy(image.data(), h.root_child, 1024);
+  std::memcpy(image.data() + 1024, h.begin_byte, 256);
+  const uint64_t* edges64 = nullptr;
+  if ((rc = upload(v, h.edges.data(), h.edges.size(), &edges64))) return fail(rc);
+  d.edges = reinterpret_cast<const uint2*>(edges64);
+  d.edge_mask = uint32_t(h.edges.size() - 1);
+  d.edge_shift = 32u - h.edge_bits;
+  const TokenRecord* recs = nullptr;
+  if ((rc = upload(v, h.rec.data(), h.rec.size(), &recs))) return fail(rc);
+  d.rec = reinterpret_cast<const uint4*>(recs);
+  if ((rc = upload(v, image.data(), image.size(), &d.smem_image))) return fail(rc);
+  if ((rc = upload(v, h.rev_off.data(), h.rev_off.size(), &d.rev_off))) return fail(rc);
+  if ((rc = upload(v, h.rev_len.data(), h.rev_len.size(), &d.rev_len))) return fail(rc);
+  if ((rc = upload(v, h.rev_blob.data(), h.rev_blob.size(), &d.rev_blob))) return fail(rc);
+  d.n_info = h.n_info;
+  d.n_reverse = h.n_reverse;
+  d.unk = h.unk;
+  d.delete_token = h.delete_token;
+  d.space_start = h.space_start;
+  d.max_len = h.max_len;
+  d.off = h.charset == 2 ? 2 : 1;
+  d.capcode = h.capcode;
+  d.normflag = h.normflag;
+  d.charset = h.charset;
+  *out = v;
+  return TMGPU_OK;
+}
+
+extern "C" int tmgpu_vocab_load_file(const char* path, int device, tmgpu_vocab** out) {
+  std::ifstream in(path ? path : "", std::ios::binary);
+  if (!in) {
+    g_err = std::string("cannot open vocabulary file: ") + (path ? path : "(null)");
+    return TMGPU_E_VOCAB_OPEN;
+  }
+  std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+  return tmgpu_vocab_create(bytes.data(), bytes.size(), device, out);
+}
+
+extern "C" void tmgpu_vocab_destroy(tmgpu_vocab* v) {
+  if (!v) return;
+  if (v->device >= 0) cudaSetDevice(v->device);
+  if (v->ws) tmgpu_workspace_destroy(v->ws);
+  for (void* p : v->allocs) cudaFree(p);
+  if (v->d_in) cudaFree(v->d_in);
+  if (v->d_off) cudaFree(v->d_off);
+  if (v->h_off) cudaFreeHost(v->h_off);
+  if (v->stream) cudaStreamDestroy(v->stream);
+  delete v;
+}
+
+extern "C" int tmgpu_vocab_info_get(const tmgpu_vocab* v, tmgpu_vocab_info* o) {
+  if (!v || !o) {
+    g_err = "tmgpu_vocab_info_get: null argument";
+    return TMGPU_E_ARG;
+  }
+  const HostTables& h = v->host;
+  std::memset(o, 0, sizeof(*o));
+  o->capcode = h.capcode;
+  o->charset = h.charset;
+  o->normflag = h.normflag;
+  o->level = h.level;
+  o->reserve = h.reserve;
+  o->max_token_length = uint8_t(h.max_len);
+  o->unk_token = h.unk;
+  o->delete_token = h.delete_token;
+  o->vocab_size = h.vocab_size;
+  o->n_reverse = h.n_reverse;
+  o->n_info = h.n_info;
+  o->n_trie_nodes = h.n_nodes;
+  return TMGPU_OK;
+}
+
+// Table self-check (host): walks the same prefix trie the kernels walk, for a single window.
+// Not a tokenizer and not a fallback -- it exists so that CPU-only CI can verify the table
+// builder against the oracle's dictionary.  Returns matched length in window bytes.
+extern "C" int tmgpu_selftest_trie_lookup(const tmgpu_vocab* v, const uint8_t* window, int n, int spaced,
+                                          uint32_t* index) {
+  return host_trie_lookup(v->host, window, n, spaced, index);
+}
+
+// ------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------
+extern "C" void tmgpu_workspace_destroy(tmgpu_workspace* ws) {
+  if (!ws) return;
+  if (ws->v && ws->v->device >= 0) cudaSetDevice(ws->v->device);
+  for (void* p : ws->allocs) cudaFree(p);
+  delete ws;
+}
+
+extern "C" int tmgpu_workspace_create(tmgpu_vocab* v, uint32_t max_strings, uint64_t max_bytes,
+                                      tmgpu_workspace** out) {
+  if (!v || !out) {
+    g_err = "tmgpu_workspace_create: null argument";
+    return TMGPU_E_ARG;
+  }
+  if (v->device < 0) {
+    g_err = "vocabulary was created without a device (this library has no CPU path)";
+    return TMGPU_E_CUDA;
+  }
+  CU(cudaSetDevice(v->device));
+  auto* ws = new tmgpu_workspace();
+  ws->v = v;
+  ws->max_strings = max_strings;
+  ws->max_bytes = max_bytes;
+  const size_t n1 = size_t(max_strings) + 1;
+  ws->slab_ids = max_bytes + uint64_t(ws->slab_pad) * max_strings + 64;
+  int rc = 0;
+  auto A = [&](auto** p, size_t count) {
+    if (!rc) rc = dev_alloc(ws->allocs, p, count);
+  };
+  A(&ws->slab, ws->slab_ids);
+  A(&ws->counts, n1);
+  A(&ws->need, n1);
+  A(&ws->missing, n1);
+  A(&ws->status, n1);
+  A(&ws->tok_off, n1);
+  A(&ws->tokens, ws->slab_ids * 4);
+  A(&ws->work_counter, 4);
+  A(&ws->overflow, 4);
+  ws->scan_bytes = scan_temp_bytes(uint32_t(n1)) + 256;
+  A(reinterpret_cast<uint8_t**>(&ws->scan_temp), ws->scan_bytes);
+  A(&ws->raw_len, n1);
+  A(&ws->raw_off, n1);
+  A(&ws->out_len, n1);
+  A(&ws->out_off, n1);
+  if (rc) {
+    tmgpu_workspace_destroy(ws);
+    return rc;
+  }
+  *out = ws;
+  return TMGPU_OK;
+}
+
+extern "C" int tmgpu_last_launch_count(const tmgpu_workspace* ws) { return ws ? ws->last_launches : 0; }
+
+static int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t* d_off, uint32_t n,
+                              uint8_t enc_len, int mode, cudaStream_t st, const uint64_t* slab_off,
+                              uint32_t* slab, uint8_t* dense) {
+  tmgpu_vocab* v = ws->v;
+  ws->last_launches = 0;
+  CU(cudaMemsetAsync(ws->work_counter, 0, 4, st));
+  CU(cudaMemsetAsync(ws->overflow, 0, 4, st));
+  CU(cudaMemsetAsync(ws->counts + n, 0, 4, st));
+  TokenizeArgs a{};
+  a.v = v->dev;
+  a.data = d_data;
+  a.off = d_off;
+  a.n = n;
+  a.slab = slab;
+  a.slab_pad = ws->slab_pad;
+  a.slab_off = slab_off;
+  a.counts = ws->counts;
+  a.need = ws->need;
+  a.missing = ws->missing;
+  a.status = ws->status;
+  a.work_counter = ws->work_counter;
+  a.overflow = ws->overflow;
+  if (v->host.max_len == 0) {  // empty vocabulary: empty result, not an error (go:960-962)
+    CU(cudaMemsetAsync(ws->counts, 0, (size_t(n) + 1) * 4, st));
+    CU(cudaMemsetAsync(ws->missing, 0, size_t(n) * 4, st));
+    CU(cudaMemsetAsync(ws->status, 0, n, st));
+  } else if (n > 0) {
+    CU(launch_tokenize(a, v->group, mode == 0, v->sms, st, nullptr));
+    ws->last_launches++;
+  }
+  if (mode == 0) {
+    CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, ws->counts, ws->tok_off, n + 1, st));
+    ws->last_launches++;
+    if (n > 0) {
+      CU(launch_pack(a.slab, d_off, ws->slab_pad, slab_off, ws->counts, ws->tok_off, dense, n, enc_len, v->sms, st));
+      ws->last_launches++;
+    }
+  }
+  return TMGPU_OK;
+}
+
+extern "C" int tmgpu_tokenize_device(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t* d_off, uint32_t n,
+                                     uint8_t enc_len, int mode, void* stream, tmgpu_device_view* view) {
+  if (!ws || !d_off || (!d_data && n) || !(mode == 0 || mode == 1)) {
+    g_err = "tmgpu_tokenize_device: bad argument";
+    return TMGPU_E_ARG;
+  }
+  if (enc_len == 0) enc_len = ws->v->host.n_reverse <= 65536 ? 2 : 3;  // go:990-996
+  if (mode == 0 && !(enc_len == 2 || enc_len == 3 || enc_len == 4)) {
+    g_err = "invalid encoding length";  // go:1012
+    return TMGPU_E_ARG;
+  }
+  if (n > ws->max_strings) {
+    g_err = "batch has more strings than the workspace was created for";
+    return TMGPU_E_ARG;
+  }
+  if (reinterpret_cast<uintptr_t>(d_data) & 15) {
+    g_err = "d_data must be 16-byte aligned";
+    return TMGPU_E_ARG;
+  }
+  CU(cudaSetDevice(ws->v->device));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ws->v->stream;
+  int rc = tokenize_on_stream(ws, d_data, d_off, n, enc_len, mode, st, nullptr, ws->slab, ws->tokens);
+  if (rc) return rc;
+  if (view) {
+    view->tokens = ws->tokens;
+    view->tok_off = ws->tok_off;
+    view->missing = ws->missing;
+    view->status = ws->status;
+    view->n_tokens = ws->tok_off + n;
+    view->counts = ws->counts;
+  }
+  return TMGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer calls
+// ------------------------------------------------------------------------------------------
+static int ensure_host_path(tmgpu_vocab* v, uint32_t n, uint64_t bytes) {
+  if (v->device < 0) {
+    g_err = "vocabulary was created without a device (this library has no CPU path)";
+    return TMGPU_E_CUDA;
+  }
+  CU(cudaSetDevice(v->device));
+  if (!v->ws || v->ws->max_strings < n || v->ws->max_bytes < bytes) {
+    if (v->ws) {
+      CU(cudaStreamSynchronize(v->stream));
+      tmgpu_workspace_destroy(v->ws);
+      v->ws = nullptr;
+    }
+    uint32_t ms = n < 1024 ? 1024 : n + n / 8;
+    uint64_t mb = bytes < (1u << 20) ? (1u << 20) : bytes + bytes / 8;
+    int rc = tmgpu_workspace_create(v, ms, mb, &v->ws);
+    if (rc) return rc;
+  }
+  if (v->d_in_cap < bytes + 64) {
+    if (v->d_in) cudaFree(v->d_in);
+    v->d_in = nullptr;
+    v->d_in_cap = bytes + bytes / 8 + 4096;
+    CU(cudaMalloc(&v->d_in, v->d_in_cap));
+  }
+  if (v->d_off_cap < size_t(n) + 1) {
+    if (v->d_off) cudaFree(v->d_off);
+    if (v->h_off) cudaFreeHost(v->h_off);
+    v->d_off = nullptr;
+    v->h_off = nullptr;
+    v->d_off_cap = size_t(n) + n / 8 + 1024;
+    CU(cudaMalloc(&v->d_off, v->d_off_cap * 8));
+    CU(cudaMallocHost(&v->h_off, v->d_off_cap * 8));
+  }
+  return TMGPU_OK;
+}
+
+struct ResultPriv {
+  std::vector<void*> pinned;
+};
+
+template <class T>
+static int pinned_alloc(ResultPriv* p, T** out, size_t count) {
+  void* q = nullptr;
+  size_t bytes = count * sizeof(T);
+  if (bytes == 0) bytes = 8;
+  cudaError_t e = cudaMallocHost(&q, bytes);
+  if (e != cudaSuccess) {
+    g_err = std::string("cudaMallocHost: ") + cudaGetErrorString(e);
+    return TMGPU_E_NOMEM;
+  }
+  p->pinned.push_back(q);
+  *out = static_cast<T*>(q);
+  return TMGPU_OK;
+}
+
+extern "C" void tmgpu_result_free(tmgpu_result* r) {
+  if (!r) return;
+  auto* p = static_cast<ResultPriv*>(r->priv);
+  if (p) {
+    for (void* q : p->pinned) cudaFreeHost(q);
+    delete p;
+  }
+  delete r;
+}
+
+extern "C" void tmgpu_bytes_free(tmgpu_bytes* b) {
+  if (!b) return;
+  auto* p = static_cast<ResultPriv*>(b->priv);
+  if (p) {
+    for (void* q : p->pinned) cudaFreeHost(q);
+    delete p;
+  }
+  delete b;
+}
+
+// stage host strings: device copy of data[off[0] .. off[n]) and offsets rebased to 0
+static int stage_input(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off, uint32_t n, uint64_t* total) {
+  const uint64_t base = off[0];
+  for (uint32_t i = 0; i <= n; i++) {
+    if (off[i] < base || (i && off[i] < off[i - 1])) {
+      g_err = "offsets must be non-decreasing";
+      return TMGPU_E_ARG;
+    }
+    v->h_off[i] = int64_t(off[i] - base);
+  }
+  *total = off[n] - base;
+  if (*total > 0x7FFFFFFFull * 1024) {
+    g_err = "batch too large";
+    return TMGPU_E_ARG;
+  }
+  for (uint32_t i = 0; i < n; i++) {
+    if (off[i + 1] - off[i] > 0x3FFFFFFFull) {
+      g_err = "a single string may not exceed 1 GiB";
+      return TMGPU_E_ARG;
+    }
+  }
+  if (*total) CU(cudaMemcpyAsync(v->d_in, data + base, *total, cudaMemcpyHostToDevice, v->stream));
+  CU(cudaMemcpyAsync(v->d_off, v->h_off, (size_t(n) + 1) * 8, cudaMemcpyHostToDevice, v->stream));
+  return TMGPU_OK;
+}
+
+// If a string produced more ids than its slab share (len + 16), run again with exact sizes.
+// On success *dense points at the serialized ids to copy out; temp holds what to cudaFree.
+static int rerun_if_overflow(tmgpu_vocab* v, uint32_t n, uint8_t enc_len, std::vector<void*>* temp,
+                             uint8_t** dense) {
+  tmgpu_workspace* ws = v->ws;
+  uint32_t flag = 0;
+  CU(cudaMemcpyAsync(&flag, ws->overflow, 4, cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaStreamSynchronize(v->stream));
+  if (!flag) return TMGPU_OK;
+  CU(cudaMemsetAsync(ws->need + n, 0, 4, v->stream));
+  uint64_t* slab_off = nullptr;
+  int rc = dev_alloc(*temp, &slab_off, size_t(n) + 1);
+  if (rc) return rc;
+  CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, ws->need, slab_off, n + 1, v->stream));
+  uint64_t total = 0;
+  CU(cudaMemcpyAsync(&total, slab_off + n, 8, cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaStreamSynchronize(v->stream));
+  uint32_t* big = nullptr;
+  if ((rc = dev_alloc(*temp, &big, total + 16))) return rc;
+  uint8_t* d = nullptr;
+  if ((rc = dev_alloc(*temp, &d, (total + 16) * 4))) return rc;
+  if ((rc = tokenize_on_stream(ws, v->d_in, v->d_off, n, enc_len, 0, v->stream, slab_off, big, d))) return rc;
+  *dense = d;
+  return TMGPU_OK;
+}
+
+extern "C" int tmgpu_tokenize_batch(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off, uint32_t n,
+                                    uint8_t enc_len, tmgpu_result** out) {
+  if (!v || !off || !out || (!data && n && off[n] != off[0])) {
+    g_err = "tmgpu_tokenize_batch: null argument";
+    return TMGPU_E_ARG;
+  }
+  if (enc_len == 0) enc_len = v->host.n_reverse <= 65536 ? 2 : 3;
+  if (!(enc_len == 2 || enc_len == 3 || enc_len == 4)) {
+    g_err = "invalid encoding length";
+    return TMGPU_E_ARG;
+  }
+  std::lock_guard<std::mutex> lock(v->mu);
+  int rc = ensure_host_path(v, n, off[n] - off[0]);
+  if (rc) return rc;
+  uint64_t total = 0;
+  if ((rc = stage_input(v, data, off, n, &total))) return rc;
+  tmgpu_workspace* ws = v->ws;
+  if ((rc = tokenize_on_stream(ws, v->d_in, v->d_off, n, enc_len, 0, v->stream, nullptr, ws->slab, ws->tokens)))
+    return rc;
+  std::vector<void*> temp;
+  uint8_t* dense = ws->tokens;
+  auto cleanup = [&]() {
+    for (void* p : temp) cudaFree(p);
+    temp.clear();
+  };
+  if ((rc = rerun_if_overflow(v, n, enc_len, &temp, &dense))) {
+    cleanup();
+    return rc;
+  }
+  auto* priv = new ResultPriv();
+  auto* r = new tmgpu_result();
+  std::memset(r, 0, sizeof(*r));
+  r->priv = priv;
+  r->n = n;
+  r->enc_len = enc_len;
+  auto bail = [&](int code) {
+    cleanup();
+    tmgpu_result_free(r);
+    return code;
+  };
+  if ((rc = pinned_alloc(priv, &r->tok_off, size_t(n) + 1))) return bail(rc);
+  if ((rc = pinned_alloc(priv, &r->missing, size_t(n) + 1))) return bail(rc);
+  if ((rc = pinned_alloc(priv, &r->status, size_t(n) + 1))) return bail(rc);
+  cudaError_t e;
+  e = cudaMemcpyAsync(r->tok_off, ws->tok_off, (size_t(n) + 1) * 8, cudaMemcpyDeviceToHost, v->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(r->missing, ws->missing, size_t(n) * 4, cudaMemcpyDeviceToHost, v->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(r->status, ws->status, size_t(n), cudaMemcpyDeviceToHost, v->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(v->stream);
+  if (e != cudaSuccess) {
+    g_err = std::string("tokenize: ") + cudaGetErrorString(e);
+    return bail(TMGPU_E_CUDA);
+  }
+  r->n_tokens = r->tok_off[n];
+  if ((rc = pinned_alloc(priv, &r->tokens, r->n_tokens * enc_len + 8))) return bail(rc);
+  if (r->n_tokens) {
+    e = cudaMemcpyAsync(r->tokens, dense, r->n_tokens * enc_len, cudaMemcpyDeviceToHost, v->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(v->stream);
+    if (e != cudaSuccess) {
+      g_err = std::string("tokenize D2H: ") + cudaGetErrorString(e);
+      return bail(TMGPU_E_CUDA);
+    }
+  }
+  cleanup();
+  *out = r;
+  return TMGPU_OK;
+}
+
+extern "C" int tmgpu_count_batch(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off, uint32_t n,
+                                 uint64_t* counts, uint32_t* missing, uint8_t* status) {
+  if (!v || !off || !counts) {
+    g_err = "tmgpu_count_batch: null argument";
+    return TMGPU_E_ARG;
+  }
+  std::lock_guard<std::mutex> lock(v->mu);
+  int rc = ensure_host_path(v, n, off[n] - off[0]);
+  if (rc) return rc;
+  uint64_t total = 0;
+  if ((rc = stage_input(v, data, off, n, &total))) return rc;
+  tmgpu_workspace* ws = v->ws;
+  if ((rc = tokenize_on_stream(ws, v->d_in, v->d_off, n, 0, 1, v->stream, nullptr, ws->slab, ws->tokens))) return rc;
+  std::vector<uint32_t> c(n + 1), m(n + 1);
+  std::vector<uint8_t> s(n + 1);
+  CU(cudaMemcpyAsync(c.data(), ws->counts, size_t(n) * 4, cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaMemcpyAsync(m.data(), ws->missing, size_t(n) * 4, cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaMemcpyAsync(s.data(), ws->status, size_t(n), cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaStreamSynchronize(v->stream));
+  for (uint32_t i = 0; i < n; i++) {
+    counts[i] = c[i];
+    if (missing) missing[i] = m[i];
+    if (status) status[i] = s[i];
+  }
+  return TMGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// decode
+// ------------------------------------------------------------------------------------------
+static int ensure_decode_cap(tmgpu_workspace* ws, uint64_t bytes) {
+  if (ws->dec_cap >= bytes + 64) return TMGPU_OK;
+  uint64_t cap = bytes + bytes / 8 + 4096;
+  int rc = dev_alloc(ws->allocs, &ws->raw, cap);
+  if (!rc) rc = dev_alloc(ws->allocs, &ws->dec, cap);
+  if (!rc) rc = dev_alloc(ws->allocs, &ws->dense, cap);
+  if (rc) return rc;
+  ws->dec_cap = cap;  // earlier (smaller) buffers stay in the pool until the workspace dies
+  return TMGPU_OK;
+}
+
+// Device decode.  Needs one host round trip for the byte total (output sizing).
+static int decode_on_stream(tmgpu_workspace* ws, const uint8_t* d_tokens, const int64_t* d_tok_off, uint32_t n,
+                            int enc, cudaStream_t st, const uint8_t** d_bytes, const uint64_t** d_off,
+                            uint64_t* total_out) {
+  tmgpu_vocab* v = ws->v;
+  ws->last_launches = 0;
+  CU(cudaMemsetAsync(ws->raw_len + n, 0, 4, st));
+  if (n) {
+    CU(launch_decode_size(v->dev, d_tokens, d_tok_off, n, enc, ws->raw_len, v->sms, st));
+    ws->last_launches++;
+  }
+  CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, ws->raw_len, ws->raw_off, n + 1, st));
+  ws->last_launches++;
+  uint64_t raw_total = 0;
+  CU(cudaMemcpyAsync(&raw_total, ws->raw_off + n, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  int rc = ensure_decode_cap(ws, raw_total);
+  if (rc) return rc;
+  if (n) {
+    CU(launch_decode_copy(v->dev, d_tokens, d_tok_off, n, enc, ws->raw_off, ws->raw, v->sms, st));
+    ws->last_launches++;
+  }
+  if (v->host.capcode != 2) {
+    *d_bytes = ws->raw;
+    *d_off = ws->raw_off;
+    *total_out = raw_total;
+    return TMGPU_OK;
+  }
+  CU(cudaMemsetAsync(ws->out_len + n, 0, 4, st));
+  if (n) {
+    CU(launch_capcode_decode(ws->raw, ws->raw_off, n, ws->dec, ws->out_len, v->sms, st));
+    ws->last_launches++;
+  }
+  CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, ws->out_len, ws->out_off, n + 1, st));
+  ws->last_launches++;
+  if (n) {
+    CU(launch_compact_bytes(ws->dec, ws->raw_off, ws->out_len, ws->out_off, n, ws->dense, v->sms, st));
+    ws->last_launches++;
+  }
+  uint64_t total = 0;
+  CU(cudaMemcpyAsync(&total, ws->out_off + n, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  *d_bytes = ws->dense;
+  *d_off = ws->out_off;
+  *total_out = total;
+  return TMGPU_OK;
+}
+
+extern "C" int tmgpu_decode_device(tmgpu_workspace* ws, const uint8_t* d_tokens, const int64_t* d_tok_off, uint32_t n,
+                                   uint8_t enc_len, void* stream, const uint8_t** d_bytes, const uint64_t** d_off,
+                                   const uint64_t** d_total) {
+  if (!ws || !d_tok_off || !d_bytes || !d_off) {
+    g_err = "tmgpu_decode_device: null argument";
+    return TMGPU_E_ARG;
+  }
+  if (enc_len == 0) enc_len = ws->v->host.n_reverse <= 65536 ? 2 : 3;
+  if (!(enc_len == 2 || enc_len == 3 || enc_len == 4) || n > ws->max_strings) {
+    g_err = "tmgpu_decode_device: bad enc_len or batch larger than the workspace";
+    return TMGPU_E_ARG;
+  }
+  CU(cudaSetDevice(ws->v->device));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ws->v->stream;
+  uint64_t total = 0;
+  int rc = decode_on_stream(ws, d_tokens, d_tok_off, n, enc_len, st, d_bytes, d_off, &total);
+  if (rc) return rc;
+  if (d_total) *d_total = *d_off + n;
+  return TMGPU_OK;
+}
+
+extern "C" int tmgpu_decode_batch(tmgpu_vocab* v, const uint8_t* tokens, const uint64_t* tok_off, uint32_t n,
+                                  uint8_t enc_len, tmgpu_bytes** out) {
+  if (!v || !tok_off || !out) {
+    g_err = "tmgpu_decode_batch: null argument";
+    return TMGPU_E_ARG;
+  }
+  if (enc_len == 0) enc_len = v->host.n_reverse <= 65536 ? 2 : 3;
+  if (!(enc_len == 2 || enc_len == 3 || enc_len == 4)) {
+    g_err = "invalid encoding length";
+    return TMGPU_E_ARG;
+  }
+  std::lock_guard<std::mutex> lock(v->mu);
+  const uint64_t n_ids = tok_off[n] - tok_off[0];
+  int rc = ensure_host_path(v, n, n_ids * enc_len + 64);
+  if (rc) return rc;
+  for (uint32_t i = 0; i <= n; i++) {
+    if (tok_off[i] < tok_off[0] || (i && tok_off[i] < tok_off[i - 1])) {
+      g_err = "token offsets must be non-decreasing";
+      return TMGPU_E_ARG;
+    }
+    v->h_off[i] = int64_t(tok_off[i] - tok_off[0]);
+  }
+  if (n_ids)
+    CU(cudaMemcpyAsync(v->d_in, tokens + tok_off[0] * enc_len, n_ids * enc_len, cudaMemcpyHostToDevice, v->stream));
+  CU(cudaMemcpyAsync(v->d_off, v->h_off, (size_t(n) + 1) * 8, cudaMemcpyHostToDevice, v->stream));
+  const uint8_t* d_bytes = nullptr;
+  const uint64_t* d_off = nullptr;
+  uint64_t total = 0;
+  if ((rc = decode_on_stream(v->ws, v->d_in, v->d_off, n, enc_len, v->stream, &d_bytes, &d_off, &total))) return rc;
+  auto* priv = new ResultPriv();
+  auto* b = new tmgpu_bytes();
+  std::memset(b, 0, sizeof(*b));
+  b->priv = priv;
+  b->n = n;
+  b->n_bytes = total;
+  if ((rc = pinned_alloc(priv, &b->off, size_t(n) + 1)) || (rc = pinned_alloc(priv, &b->bytes, total + 8))) {
+    tmgpu_bytes_free(b);
+    return rc;
+  }
+  cudaError_t e = cudaMemcpyAsync(b->off, d_off, (size_t(n) + 1) * 8, cudaMemcpyDeviceToHost, v->stream);
+  if (e == cudaSuccess && total) e = cudaMemcpyAsync(b->bytes, d_bytes, total, cudaMemcpyDeviceToHost, v->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(v->stream);
+  if (e != cudaSuccess) {
+    g_err = std::string("decode D2H: ") + cudaGetErrorString(e);
+    tmgpu_bytes_free(b);
+    return TMGPU_E_CUDA;
+  }
+  *out = b;
+  return TMGPU_OK;
+}

@@ -1,0 +1,96 @@
+// device_tables.h -- table layout shared by the host table builder and the sm_100a kernels,
+// plus the two pure functions both sides agree on: the trie walk and the pair score.
+#pragma once
+#include <cstdint>
+#include <vector_types.h>
+
+#if defined(__CUDACC__)
+#define TM_HD __host__ __device__ __forceinline__
+#else
+#define TM_HD inline
+#endif
+
+namespace tmgpu {
+
+constexpr uint32_t kNoVal = 0xFFFFFFFFu;   // "no child" / empty edge key
+constexpr uint32_t kRootStart = 0xFFFFFFFEu;  // walk starts at the trie root
+constexpr int kNegScore = -1000000;        // go/tokenmonster.go:1059-1065 sentinel
+
+// Everything a kernel needs about one vocabulary (device pointers + scalars).
+struct VocabDev {
+  const uint2* edges;          // hashed trie edges {key = parent<<8|byte, val = child|sig<<24}
+  uint32_t edge_mask;          // capacity - 1
+  uint32_t edge_shift;         // 32 - log2(capacity)
+  const uint4* rec;            // 2 x uint4 per dictionary index (TokenRecord)
+  const uint8_t* smem_image;   // 1280 B: root_child[256] (u32) then begin_byte[256]; staged by TMA
+  const uint32_t* rev_off;     // decode: reverse[id] offset into rev_blob
+  const uint8_t* rev_len;      // 0xFF = nil
+  const uint8_t* rev_blob;
+  uint32_t n_info, n_reverse;
+  uint32_t unk, delete_token;  // ids or 0xFFFFFF
+  uint32_t space_start;        // trie state after the virtual space prefix, or kNoVal
+  int max_len;                 // maxTokenLength
+  int off;                     // 1, or 2 for UTF-16 (lilbufOffset, go:1031-1034)
+  uint8_t capcode, normflag, charset, pad;
+};
+
+TM_HD uint32_t sig_bit_of(uint32_t b) { return (b ^ (b >> 3)) & 7u; }
+
+// Longest key that prefixes window[0 .. maxd): the semantics of pansearch.Fast.LongestSubstring
+// (call sites go/tokenmonster.go:1049,1068,1091,...; restated cpp:786-877).  `byte_at(d)` yields
+// window byte d, `root_child` is the 256-entry first-byte table, `load_edge(h)` reads edge slot h.
+// start = kRootStart for a plain window, or a trie state for the space-prefixed retry.
+// Returns the number of WINDOW bytes matched (0 = not found) and the dictionary index.
+template <class ByteAt, class RootChild, class LoadEdge>
+TM_HD int trie_longest(ByteAt byte_at, RootChild root_child, LoadEdge load_edge, uint32_t edge_mask,
+                       uint32_t edge_shift, uint32_t n_info, int maxd, uint32_t start,
+                       uint32_t* index_out) {
+  int best_len = 0;
+  uint32_t best = 0;
+  uint32_t node = 0, sig = 0;
+  bool at_root = (start == kRootStart);
+  if (!at_root) {
+    node = start & 0xFFFFFFu;
+    sig = start >> 24;
+  }
+  for (int d = 0; d < maxd; d++) {
+    uint32_t b = byte_at(d);
+    uint32_t val;
+    if (at_root) {
+      at_root = false;
+      val = root_child(b);
+    } else {
+      if (((sig >> sig_bit_of(b)) & 1u) == 0) break;  // no child can start with this byte
+      uint32_t key = (node << 8) | b;
+      uint32_t h = (key * 0x9E3779B1u) >> edge_shift;
+      for (;;) {
+        uint2 e = load_edge(h);
+        if (e.x == key) { val = e.y; break; }
+        if (e.x == kNoVal) { val = kNoVal; break; }
+        h = (h + 1) & edge_mask;
+      }
+    }
+    if (val == kNoVal) break;
+    node = val & 0xFFFFFFu;
+    sig = val >> 24;
+    if (node < n_info) {
+      best = node;
+      best_len = d + 1;
+    }
+  }
+  *index_out = best;
+  return best_len;
+}
+
+// Score of "first token a, then second token b" (go:1075-1084 plain,
+// :1096-1105 retry).  nw = a.nWords - forwardDelete, nb = beginByte of the byte after b.
+TM_HD int pair_score(int branch_len, uint32_t aflag, int nw, uint32_t bflag, int bnw, int nb, bool retry) {
+  int s = branch_len + int(aflag >> 7) + int(bflag >> 7) + (nw > 1 ? nw - 1 : 0) + (bnw > 1 ? bnw - 1 : 0) +
+          ((nb >> 2) & 1) + 100 * (nw + bnw + (nb >> 3));
+  s -= 100 * int((aflag >> 3) & 1u & (bflag >> 4)) + 3 * int(bflag & 1u & uint32_t(nb));
+  if (retry) s -= 103 * int(aflag & 1u) + 1;
+  else s += int((bflag >> 2) & 1u) - 103 * int(aflag & 1u & (bflag >> 1));
+  return s;
+}
+
+}  // namespace tmgpu

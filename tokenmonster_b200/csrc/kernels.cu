@@ -1,0 +1,271 @@
+// kernels.cu -- device code of libtmgpu.so (sm_100a only) and its launchers.
+//   K1/K3 tokenize_kernel        (tokenize_kernel.cuh)
+//   pack_tokens_kernel           slab of u32 ids -> dense 2/3/4-byte serialized ids
+//                                (the emit variants go/tokenmonster.go:1545/:1817/:2089)
+//   K2 decode_size / decode_copy reverse[id] gather (go/tokenmonster.go:813-948)
+//   capcode_decode_kernel        capcode level-2 decoder (javascript/tokenmonster.js:1007-1065)
+#include "kernels.h"
+
+#include <cub/device/device_scan.cuh>
+
+#include "tokenize_kernel.cuh"
+
+namespace tmgpu {
+
+// ------------------------------------------------------------------------------------------
+// pack: one warp per string copies its ids out of the slab into the dense serialized stream
+// ------------------------------------------------------------------------------------------
+template <int ENC>
+__global__ void __launch_bounds__(256) pack_tokens_kernel(const uint32_t* __restrict__ slab,
+                                                          const int64_t* __restrict__ off, uint32_t slab_pad,
+                                                          const uint64_t* __restrict__ slab_off,
+                                                          const uint32_t* __restrict__ counts,
+                                                          const uint64_t* __restrict__ tok_off,
+                                                          uint8_t* __restrict__ out, uint32_t n) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n; s += warps) {
+    const uint64_t base = slab_off ? slab_off[s] : uint64_t(off[s] - off[0]) + uint64_t(slab_pad) * s;
+    const uint32_t cnt = counts[s];
+    const uint64_t o = tok_off[s];
+    for (uint32_t k = lane; k < cnt; k += 32) {
+      const uint32_t id = slab[base + k];
+      if (ENC == 2) {
+        reinterpret_cast<uint16_t*>(out)[o + k] = uint16_t(id);
+      } else if (ENC == 4) {
+        reinterpret_cast<uint32_t*>(out)[o + k] = id;
+      } else {
+        uint8_t* p = out + (o + k) * 3;
+        p[0] = uint8_t(id);
+        p[1] = uint8_t(id >> 8);
+        p[2] = uint8_t(id >> 16);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// decode
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t load_id(const uint8_t* t, uint64_t k, int enc) {
+  if (enc == 2) return reinterpret_cast<const uint16_t*>(t)[k];
+  if (enc == 4) return reinterpret_cast<const uint32_t*>(t)[k];
+  const uint8_t* p = t + k * 3;
+  return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16);
+}
+
+// length of reverse[id], 0 for out-of-range / nil ids.  The 16-bit path compares against
+// uint16(len(reverse) - 1) like go/tokenmonster.go:861-864.
+__device__ __forceinline__ uint32_t rev_length(const VocabDev& V, uint32_t id, int enc) {
+  bool ok = (enc == 2) ? (V.n_reverse != 0 && id <= ((V.n_reverse - 1) & 0xFFFFu)) : (id < V.n_reverse);
+  if (!ok) return 0;
+  uint32_t l = V.rev_len[id];
+  return l == 0xFF ? 0 : l;
+}
+
+__global__ void __launch_bounds__(256) decode_size_kernel(VocabDev V, const uint8_t* __restrict__ tokens,
+                                                          const int64_t* __restrict__ tok_off, uint32_t n, int enc,
+                                                          uint32_t* __restrict__ raw_len) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n; s += warps) {
+    const uint64_t t0 = uint64_t(tok_off[s]), t1 = uint64_t(tok_off[s + 1]);
+    uint32_t sum = 0;
+    for (uint64_t k = t0 + lane; k < t1; k += 32) sum += rev_length(V, load_id(tokens, k, enc), enc);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+    if (lane == 0) raw_len[s] = sum;
+  }
+}
+
+__global__ void __launch_bounds__(256) decode_copy_kernel(VocabDev V, const uint8_t* __restrict__ tokens,
+                                                          const int64_t* __restrict__ tok_off, uint32_t n, int enc,
+                                                          const uint64_t* __restrict__ raw_off,
+                                                          uint8_t* __restrict__ out) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n; s += warps) {
+    const uint64_t t0 = uint64_t(tok_off[s]), t1 = uint64_t(tok_off[s + 1]);
+    uint64_t at = raw_off[s];
+    for (uint64_t kb = t0; kb < t1; kb += 32) {
+      const uint64_t k = kb + lane;
+      uint32_t id = 0, l = 0;
+      if (k < t1) {
+        id = load_id(tokens, k, enc);
+        l = rev_length(V, id, enc);
+      }
+      uint32_t incl = l;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      if (l) {
+        const uint8_t* src = V.rev_blob + V.rev_off[id];
+        uint8_t* dst = out + at + (incl - l);
+        for (uint32_t b = 0; b < l; b++) dst[b] = src[b];
+      }
+      at += total;
+    }
+  }
+}
+
+// capcode level-2 decoder, one thread per string (javascript/tokenmonster.js:1007-1065; the
+// stateless form used by Vocab.Decode, go/tokenmonster.go:788-796).  ASCII classes; non-ASCII
+// code points pass through unchanged and a pending delete swallows a whole UTF-8 sequence.
+// Decoding never grows the text, so the result is written at the same offsets of `dst`.
+__global__ void __launch_bounds__(256) capcode_decode_kernel(const uint8_t* __restrict__ src,
+                                                             const uint64_t* __restrict__ raw_off, uint32_t n,
+                                                             uint8_t* __restrict__ dst,
+                                                             uint32_t* __restrict__ out_len) {
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    const uint8_t* in = src + raw_off[s];
+    uint8_t* out = dst + raw_off[s];
+    const uint32_t len = uint32_t(raw_off[s + 1] - raw_off[s]);
+    bool in_word = false, in_char = false, del = false, ignore = false;
+    uint32_t o = 0;
+    for (uint32_t i = 0; i < len; i++) {
+      uint32_t r = in[i];
+      if (r == 'C') { in_char = true; in_word = false; continue; }
+      if (r == 'W') { in_word = true; in_char = false; ignore = true; continue; }
+      if (r == 'D') { del = true; continue; }
+      if (r == ' ') {
+        if (del) del = false;
+        else { out[o++] = ' '; if (!ignore) in_word = false; }
+      } else if (r >= 0x80) {
+        if (del) {
+          while (i + 1 < len && (in[i + 1] & 0xC0) == 0x80) i++;
+          del = false;
+        } else {
+          in_char = false;
+          out[o++] = uint8_t(r);
+          while (i + 1 < len && (in[i + 1] & 0xC0) == 0x80) out[o++] = in[++i];
+        }
+      } else if (del) {
+        del = false;
+      } else if (in_char) {
+        in_char = false;
+        out[o++] = uint8_t((r - 'a' < 26u) ? r - 32 : r);
+      } else if (in_word) {
+        if (r - 'a' < 26u) out[o++] = uint8_t(r - 32);
+        else if (r - 'A' < 26u) out[o++] = uint8_t(r);
+        else {
+          out[o++] = uint8_t(r);
+          if (!((r - '0' < 10u) || r == '\'')) in_word = false;
+        }
+      } else {
+        out[o++] = uint8_t(r);
+      }
+      ignore = false;
+    }
+    out_len[s] = o;
+  }
+}
+
+// dense copy of variable-length segments: src segments at src_off[s] (length len[s]) -> dst_off[s]
+__global__ void __launch_bounds__(256) compact_bytes_kernel(const uint8_t* __restrict__ src,
+                                                            const uint64_t* __restrict__ src_off,
+                                                            const uint32_t* __restrict__ len,
+                                                            const uint64_t* __restrict__ dst_off, uint32_t n,
+                                                            uint8_t* __restrict__ dst) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n; s += warps) {
+    const uint8_t* a = src + src_off[s];
+    uint8_t* b = dst + dst_off[s];
+    const uint32_t l = len[s];
+    for (uint32_t k = lane; k < l; k += 32) b[k] = a[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+// exclusive sum of u32 counts into u64 offsets (the accumulator type follows the u64 init value)
+size_t scan_temp_bytes(uint32_t n_items) {
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveScan(nullptr, bytes, (const uint32_t*)nullptr, (uint64_t*)nullptr, ::cuda::std::plus<>{},
+                                 uint64_t(0), int(n_items));
+  return bytes;
+}
+
+cudaError_t exclusive_scan_u32_to_u64(void* temp, size_t temp_bytes, const uint32_t* in, uint64_t* out,
+                                      uint32_t n_items, cudaStream_t st) {
+  return cub::DeviceScan::ExclusiveScan(temp, temp_bytes, in, out, ::cuda::std::plus<>{}, uint64_t(0), int(n_items), st);
+}
+
+template <int G, int CAP, bool STORE>
+static cudaError_t launch_tok(const TokenizeArgs& a, int sms, cudaStream_t st, int* grid_out) {
+  auto k = tokenize_kernel<G, CAP, STORE>;
+  constexpr int smem = GroupCfg<G>::SMEM;
+  static bool configured = false;
+  static int per_sm = 0;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kBlockThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    configured = true;
+  }
+  // persistent grid: every SM gets its resident share of CTAs; strings are pulled from a counter
+  long long want = (static_cast<long long>(a.n) + GroupCfg<G>::GROUPS - 1) / GroupCfg<G>::GROUPS;
+  long long full = static_cast<long long>(sms) * per_sm;
+  int grid = int(want < full ? (want < 1 ? 1 : want) : full);
+  if (grid_out) *grid_out = grid;
+  k<<<grid, kBlockThreads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tokenize(const TokenizeArgs& a, int group, bool store, int sms, cudaStream_t st, int* grid_out) {
+  const int cap = a.v.capcode;
+#define TM_CASE(G_)                                                                      \
+  if (group == G_) {                                                                     \
+    if (cap == 0) return store ? launch_tok<G_, 0, true>(a, sms, st, grid_out)           \
+                               : launch_tok<G_, 0, false>(a, sms, st, grid_out);         \
+    return store ? launch_tok<G_, 2, true>(a, sms, st, grid_out)                         \
+                 : launch_tok<G_, 2, false>(a, sms, st, grid_out);                       \
+  }
+  TM_CASE(32)
+  TM_CASE(16)
+  TM_CASE(8)
+#undef TM_CASE
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_pack(const uint32_t* slab, const int64_t* off, uint32_t slab_pad, const uint64_t* slab_off,
+                        const uint32_t* counts, const uint64_t* tok_off, uint8_t* out, uint32_t n, int enc,
+                        int sms, cudaStream_t st) {
+  int grid = sms * 8;
+  if (enc == 2) pack_tokens_kernel<2><<<grid, 256, 0, st>>>(slab, off, slab_pad, slab_off, counts, tok_off, out, n);
+  else if (enc == 3) pack_tokens_kernel<3><<<grid, 256, 0, st>>>(slab, off, slab_pad, slab_off, counts, tok_off, out, n);
+  else pack_tokens_kernel<4><<<grid, 256, 0, st>>>(slab, off, slab_pad, slab_off, counts, tok_off, out, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_decode_size(const VocabDev& v, const uint8_t* tokens, const int64_t* tok_off, uint32_t n, int enc,
+                               uint32_t* raw_len, int sms, cudaStream_t st) {
+  decode_size_kernel<<<sms * 8, 256, 0, st>>>(v, tokens, tok_off, n, enc, raw_len);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_decode_copy(const VocabDev& v, const uint8_t* tokens, const int64_t* tok_off, uint32_t n, int enc,
+                               const uint64_t* raw_off, uint8_t* out, int sms, cudaStream_t st) {
+  decode_copy_kernel<<<sms * 8, 256, 0, st>>>(v, tokens, tok_off, n, enc, raw_off, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_capcode_decode(const uint8_t* src, const uint64_t* raw_off, uint32_t n, uint8_t* dst,
+                                  uint32_t* out_len, int sms, cudaStream_t st) {
+  capcode_decode_kernel<<<sms * 8, 256, 0, st>>>(src, raw_off, n, dst, out_len);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_compact_bytes(const uint8_t* src, const uint64_t* src_off, const uint32_t* len,
+                                 const uint64_t* dst_off, uint32_t n, uint8_t* dst, int sms, cudaStream_t st) {
+  compact_bytes_kernel<<<sms * 8, 256, 0, st>>>(src, src_off, len, dst_off, n, dst);
+  return cudaGetLastError();
+}
+
+}  // namespace tmgpu

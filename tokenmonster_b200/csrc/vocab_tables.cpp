@@ -1,0 +1,218 @@
+// vocab_tables.cpp -- .vocab parser and device-table builder (host side, no CUDA).
+// Format: /root/reference go/tokenmonster.go:2602-2653 (writer), :2656-2736 (reader);
+// worked example tokenmonster-cpp/tests/unit.cpp:12-79.
+#include "vocab_tables.h"
+
+#include <cstring>
+#include <string_view>
+#include <unordered_map>
+
+#include "../../include/tmgpu.h"
+#include "device_tables.h"
+
+namespace tmgpu {
+
+namespace {
+struct Cursor {
+  const uint8_t* p;
+  size_t n, at = 0;
+  bool ok = true;
+  bool need(size_t k) {
+    if (at + k > n) ok = false;
+    return ok;
+  }
+  uint32_t u8() { return need(1) ? p[at++] : 0; }
+  uint32_t u24() {
+    if (!need(3)) return 0;
+    uint32_t v = p[at] | (p[at + 1] << 8) | (uint32_t(p[at + 2]) << 16);
+    at += 3;
+    return v;
+  }
+};
+}  // namespace
+
+int parse_vocab(const uint8_t* file, size_t n, HostTables* t, std::string* err) {
+  Cursor c{file, n};
+  if (n < 24) {
+    *err = "not a valid TokenMonster vocabulary (truncated header)";
+    return TMGPU_E_VOCAB_FORMAT;
+  }
+  t->capcode = (uint8_t)c.u8();
+  t->charset = (uint8_t)c.u8();
+  t->normflag = (uint8_t)c.u8();
+  t->level = (uint8_t)c.u8();
+  t->reserve = (uint8_t)c.u8();
+  c.at = 8;
+  if (t->charset > 2 || t->capcode > 2) {  // go:2675
+    *err = "not a valid TokenMonster vocabulary (charset/capcode byte)";
+    return TMGPU_E_VOCAB_FORMAT;
+  }
+  t->unk = c.u24();
+  t->vocab_size = c.u24();
+  t->n_reverse = c.u24();
+  t->n_info = c.u24();
+  t->delete_token = c.u24();
+  t->max_len = (int)c.u8();
+
+  struct Key {
+    uint32_t off;
+    uint8_t len;
+  };
+  std::vector<Key> keys(t->n_info);
+  std::vector<uint8_t> blob;
+  blob.reserve(size_t(t->n_info) * 8);
+  std::vector<uint8_t> flag(t->n_info), nwords(t->n_info);
+  std::vector<uint32_t> alt(t->n_info), alt2(t->n_info), id(t->n_info);
+  t->rev_off.assign(t->n_reverse, 0);
+  t->rev_len.assign(t->n_reverse, 0xFF);
+
+  for (uint32_t i = 0; i < t->n_info; i++) {
+    uint32_t kl = c.u8();
+    if (!c.ok || kl == 0 || kl > 40 || !c.need(kl + 15)) {  // go:2695
+      *err = "not a valid TokenMonster vocabulary (token record)";
+      return TMGPU_E_VOCAB_FORMAT;
+    }
+    keys[i] = {uint32_t(blob.size()), uint8_t(kl)};
+    blob.insert(blob.end(), file + c.at, file + c.at + kl);
+    c.at += kl;
+    flag[i] = (uint8_t)c.u8();
+    nwords[i] = (uint8_t)c.u8();
+    alt[i] = c.u24();
+    alt2[i] = c.u24();
+    id[i] = c.u24();
+    c.at += 4;  // float32 score: not used on the hot path
+    // alternatives always point at EARLIER records (go:2636 enforces it at save time,
+    // go:2703-2711 resolves them against what has been read so far)
+    if ((alt[i] != kDNE && alt[i] >= i) || (alt2[i] != kDNE && alt2[i] >= i) || id[i] >= t->n_reverse) {
+      *err = "not a valid TokenMonster vocabulary (alternative index / id out of range)";
+      return TMGPU_E_VOCAB_FORMAT;
+    }
+    if (i > 0) {  // the dictionary index IS the record order: cpp:1352-1357
+      const Key& a = keys[i - 1];
+      const Key& b = keys[i];
+      bool bad = a.len > b.len || (a.len == b.len && std::memcmp(&blob[a.off], &blob[b.off], b.len) >= 0);
+      if (bad) {
+        *err = "dictionary order does not match vocabulary info order";
+        return TMGPU_E_VOCAB_ORDER;
+      }
+    }
+  }
+  if (!c.need(256 + 3)) {
+    *err = "not a valid TokenMonster vocabulary (beginByte table)";
+    return TMGPU_E_VOCAB_FORMAT;
+  }
+  std::memcpy(t->begin_byte, file + c.at, 256);
+  c.at += 256;
+  uint32_t n_deleted = c.u24();
+  for (uint32_t i = 0; i < n_deleted && c.ok; i++) {
+    uint32_t kl = c.u8();
+    if (c.need(kl + 7)) c.at += kl + 7;
+  }
+  if (!c.ok || c.at != n) {  // go:2731
+    *err = "not a valid TokenMonster vocabulary (trailing bytes)";
+    return TMGPU_E_VOCAB_FORMAT;
+  }
+
+  // ---- token records -------------------------------------------------------------------
+  t->rec.resize(t->n_info);
+  for (uint32_t i = 0; i < t->n_info; i++) {
+    TokenRecord& r = t->rec[i];
+    uint32_t al = alt[i] != kDNE ? keys[alt[i]].len : 0;
+    uint32_t al2 = alt2[i] != kDNE ? keys[alt2[i]].len : 0;
+    uint32_t f1 = alt[i] != kDNE ? flag[alt[i]] : 0, n1 = alt[i] != kDNE ? nwords[alt[i]] : 0;
+    uint32_t f2 = alt2[i] != kDNE ? flag[alt2[i]] : 0, n2 = alt2[i] != kDNE ? nwords[alt2[i]] : 0;
+    r.w[0] = flag[i] | (uint32_t(nwords[i]) << 8) | (uint32_t(keys[i].len) << 16) | (al << 24);
+    r.w[1] = id[i];
+    r.w[2] = alt[i] != kDNE ? id[alt[i]] : 0;
+    r.w[3] = alt2[i] != kDNE ? id[alt2[i]] : 0;
+    r.w[4] = al2 | (f1 << 8) | (n1 << 16) | (f2 << 24);
+    r.w[5] = n2;
+    r.w[6] = alt[i];
+    r.w[7] = alt2[i];
+    t->rev_off[id[i]] = keys[i].off;  // later records overwrite earlier ones (go:2715)
+    t->rev_len[id[i]] = keys[i].len;
+  }
+  t->rev_blob = blob;
+
+  // ---- prefix trie ---------------------------------------------------------------------
+  std::unordered_map<std::string_view, uint32_t> node_of;
+  node_of.reserve(size_t(t->n_info) * 4);
+  for (uint32_t i = 0; i < t->n_info; i++)
+    node_of.emplace(std::string_view((const char*)&blob[keys[i].off], keys[i].len), i);
+  struct Edge {
+    uint32_t parent, child;
+    uint8_t byte;
+  };
+  std::vector<Edge> edge_list;
+  edge_list.reserve(size_t(t->n_info) * 3);
+  uint32_t next_id = t->n_info;
+  constexpr uint32_t kRoot = 0xFFFFFFu;
+  // every proper prefix of every key becomes an interior node unless it is itself a key
+  for (uint32_t i = 0; i < t->n_info; i++) {
+    const char* k = (const char*)&blob[keys[i].off];
+    for (uint32_t l = 1; l < keys[i].len; l++) {
+      auto ins = node_of.emplace(std::string_view(k, l), next_id);
+      if (ins.second) next_id++;
+    }
+  }
+  // one edge per node: (node of the prefix minus its last byte, last byte) -> node
+  for (const auto& kv : node_of) {
+    std::string_view p = kv.first;
+    uint32_t parent = p.size() == 1 ? kRoot : node_of.find(p.substr(0, p.size() - 1))->second;
+    edge_list.push_back({parent, kv.second, (uint8_t)p.back()});
+  }
+  t->n_nodes = next_id;
+  if (next_id >= 0xFFFFF0u) {
+    *err = "vocabulary too large for the 24-bit trie node space";
+    return TMGPU_E_UNSUPPORTED;
+  }
+  std::vector<uint8_t> sig(next_id, 0);
+  for (const Edge& e : edge_list)
+    if (e.parent != kRoot) sig[e.parent] |= uint8_t(1u << sig_bit(e.byte));
+  uint32_t bits = 4;
+  while ((1ull << bits) < edge_list.size() * 2 + 2) bits++;
+  t->edge_bits = bits;
+  t->edges.assign(size_t(1) << bits, ~0ull);
+  for (int b = 0; b < 256; b++) t->root_child[b] = kNone;
+  uint32_t mask = (1u << bits) - 1;
+  for (const Edge& e : edge_list) {
+    uint32_t val = e.child | (uint32_t(sig[e.child]) << 24);
+    if (e.parent == kRoot) {
+      t->root_child[e.byte] = val;
+      continue;
+    }
+    uint32_t key = (e.parent << 8) | e.byte;
+    uint32_t h = edge_hash(key, bits);
+    while (t->edges[h] != ~0ull) h = (h + 1) & mask;
+    t->edges[h] = uint64_t(key) | (uint64_t(val) << 32);
+  }
+  // start state of the space-prefixed retry (go:1029-1036 lilbuf): after " " (+0x00 in UTF-16)
+  t->space_start = t->root_child[0x20];
+  if (t->charset == 2 && t->space_start != kNone) {
+    uint32_t node = t->space_start & 0xFFFFFFu;
+    uint32_t key = (node << 8) | 0u, h = edge_hash(key, bits);
+    t->space_start = kNone;
+    while (t->edges[h] != ~0ull) {
+      if (uint32_t(t->edges[h]) == key) {
+        t->space_start = uint32_t(t->edges[h] >> 32);
+        break;
+      }
+      h = (h + 1) & mask;
+    }
+  }
+  return TMGPU_OK;
+}
+
+int host_trie_lookup(const HostTables& h, const uint8_t* window, int n, int spaced, uint32_t* index) {
+  uint32_t start = spaced ? h.space_start : kRootStart;
+  if (spaced && start == kNoVal) return 0;
+  const uint2* edges = reinterpret_cast<const uint2*>(h.edges.data());
+  uint32_t idx = 0;
+  int l = trie_longest([&](int d) { return uint32_t(window[d]); }, [&](uint32_t b) { return h.root_child[b]; },
+                       [&](uint32_t s) { return edges[s]; }, uint32_t(h.edges.size() - 1), 32u - h.edge_bits,
+                       h.n_info, n, start, &idx);
+  if (index) *index = idx;
+  return l;
+}
+
+}  // namespace tmgpu

@@ -1,0 +1,60 @@
+// vocab_tables.h -- host-side: parse a TokenMonster .vocab file and flatten it into the
+// tables the sm_100a kernels consume.  Replaces the products of Load
+// (/root/reference go/tokenmonster.go:2656-2736): info[], reverse[][], beginByte[256] and the
+// pansearch dictionary.  The dictionary is NOT pansearch's bloom/bucket cascade
+// (tokenmonster-cpp/src/tokenmonster.cpp:491-1280, a CPU-cache design) but a prefix trie with
+// hashed edges: the path to a node is the key, so a walk proves the longest key that prefixes a
+// window exactly, with no key-byte compares, and the " "-prefixed retry of go:1088-1107 is just a
+// different start node.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace tmgpu {
+
+constexpr uint32_t kDNE = 0xFFFFFFu;
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+// 32-byte token record (one L2 sector), indexed by dictionary index.
+//  w0: flag | nWords<<8 | key_len<<16 | alt_len<<24      (alt_len 0 = no alternative 1)
+//  w1: id   w2: id1 (alternative 1)   w3: id2 (alternative 2)
+//  w4: alt_len2 | alt1.flag<<8 | alt1.nWords<<16 | alt2.flag<<24
+//  w5: alt2.nWords | (spare)
+//  w6: alt index  w7: alt2 index (diagnostics)
+struct TokenRecord {
+  uint32_t w[8];
+};
+
+struct HostTables {
+  // header
+  uint8_t capcode = 0, charset = 0, normflag = 0, level = 0, reserve = 0;
+  uint32_t unk = kDNE, vocab_size = 0, n_reverse = 0, n_info = 0, delete_token = kDNE;
+  int max_len = 0;
+  uint8_t begin_byte[256] = {};
+
+  std::vector<TokenRecord> rec;  // n_info
+  // trie: node ids < n_info are terminal (id == dictionary index); others are interior.
+  // edge table: open addressing, key = parent<<8 | byte, val = child | sig(child)<<24
+  std::vector<uint64_t> edges;   // lo 32 = key, hi 32 = val; empty = all ones
+  uint32_t edge_bits = 0;        // log2(capacity)
+  uint32_t root_child[256];      // val or kNone
+  uint32_t space_start = kNone;  // trie state after the virtual " " (0x20 0x00 in UTF-16) prefix
+  uint32_t n_nodes = 0;
+
+  // reverse table for decode: reverse[id] = LAST record with that id (go:2715)
+  std::vector<uint32_t> rev_off; // n_reverse, offset into rev_blob
+  std::vector<uint8_t> rev_len;  // n_reverse, 0xFF = nil
+  std::vector<uint8_t> rev_blob;
+};
+
+// returns 0 or a TMGPU_E_* code; err receives a message
+int parse_vocab(const uint8_t* file, size_t n, HostTables* out, std::string* err);
+
+// host walk of the device trie for one window (table self-check; see tmgpu_selftest_trie_lookup)
+int host_trie_lookup(const HostTables& h, const uint8_t* window, int n, int spaced, uint32_t* index);
+
+inline uint32_t sig_bit(uint32_t b) { return (b ^ (b >> 3)) & 7u; }
+inline uint32_t edge_hash(uint32_t key, uint32_t bits) { return (key * 0x9E3779B1u) >> (32u - bits); }
+
+}  // namespace tmgpu
