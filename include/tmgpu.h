@@ -8,7 +8,7 @@
  *
  * Conventions
  *   - plain pointers and sizes only; no CUDA / torch types in any signature
- *     (streams are passed as void* = cudaStream_t, 0 = the library's own stream)
+ *     (streams are passed as void* = cudaStream_t; NULL = the CUDA default stream)
  *   - every function returns an int status: 0 = OK, otherwise a TMGPU_E_* code;
  *     tmgpu_last_error() gives the message for the calling thread
  *   - per-string failures do not fail the batch: see status[] (the reference server only
@@ -144,13 +144,16 @@ typedef struct tmgpu_device_view {
 int tmgpu_workspace_create(tmgpu_vocab* v, uint32_t max_strings, uint64_t max_bytes,
                            tmgpu_workspace** out);
 void tmgpu_workspace_destroy(tmgpu_workspace* ws);
-/* Launches the tokenize kernels on `stream` (void* = cudaStream_t; NULL = vocab stream) and
+/* Launches the tokenize kernels on `stream` (void* = cudaStream_t; NULL = default stream) and
  * returns without synchronising.  mode: 0 = ids (enc_len 2/3/4), 1 = count only. */
 int tmgpu_tokenize_device(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t* d_off,
                           uint32_t n, uint8_t enc_len, int mode, void* stream,
                           tmgpu_device_view* view);
 /* Number of kernels the last tmgpu_tokenize_device / decode call launched (bench accounting). */
 int tmgpu_last_launch_count(const tmgpu_workspace* ws);
+/* Device durations (ms, CUDA events on the launching stream) of the tokenize kernel for the
+ * launches since the previous call, oldest first (ring of 64).  Synchronises on the last one. */
+int tmgpu_workspace_kernel_times(tmgpu_workspace* ws, float* ms_out, int max_out);
 /* Device decode: d_tokens packed enc_len bytes per id, d_tok_off[n+1] in ids.  Output bytes and
  * offsets are workspace-owned device buffers. */
 int tmgpu_decode_device(tmgpu_workspace* ws, const uint8_t* d_tokens, const int64_t* d_tok_off,

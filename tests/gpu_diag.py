@@ -74,7 +74,8 @@ def main():
     data = np.frombuffer(b"".join(texts), np.uint8)
     off = np.zeros(len(texts) + 1, np.uint64)
     off[1:] = np.cumsum([len(t) for t in texts])
-    for g in (32, 16, 8):
+    groups = [int(x) for x in os.environ.get('DIAG_GROUPS', '1,8,32').split(',')]
+    for g in groups:
         total += run("unit.cpp", vb, data, off, g)
     for name in ("c3", "c4", "c2", "c1"):
         vb = configs.vocab_bytes(name)
@@ -82,8 +83,8 @@ def main():
         n = 300 if quick else 3000
         d, o = corpus.make_batch(base, n, 0, 900, 11, "cpu")
         d, o = d.numpy(), o.numpy().astype(np.uint64)
-        for g in (32, 16, 8):
-            total += run(name, vb, d, o, g, enc=4 if g != 16 else 2 if configs.CONFIGS[name]["ids"] <= 65536 else 3)
+        for g in groups:
+            total += run(name, vb, d, o, g, enc=4 if g != 8 else 2 if configs.CONFIGS[name]["ids"] <= 65536 else 3)
     print("TOTAL BAD", total)
     return 1 if total else 0
 

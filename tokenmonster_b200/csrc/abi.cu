@@ -33,7 +33,7 @@ struct tmgpu_vocab {
   HostTables host;
   int device = -1;  // -1: host tables only (parser / table self-tests without a GPU)
   int sms = 0;
-  int group = 8;    // lanes per string
+  int group = 1;    // lanes per string: 1 = thread-per-string kernel, 8/16/32 = lanes-over-branches kernel
   VocabDev dev{};
   std::vector<void*> allocs;
   cudaStream_t stream = nullptr;
@@ -75,6 +75,10 @@ struct tmgpu_workspace {
   uint64_t dec_cap = 0;
   std::vector<void*> allocs;
   int last_launches = 0;
+  // CUDA events around the dominant kernel (tokenize) of the most recent launches
+  static constexpr int kEv = 64;
+  cudaEvent_t ev0[kEv] = {}, ev1[kEv] = {};
+  int ev_head = 0, ev_count = 0;
 };
 
 extern "C" const char* tmgpu_last_error(void) { return g_err.c_str(); }
@@ -146,7 +150,7 @@ extern "C" int tmgpu_vocab_create(const uint8_t* file_bytes, size_t n, int devic
   }
   if (const char* g = getenv("TMGPU_GROUP")) {
     int gi = atoi(g);
-    if (gi == 8 || gi == 16 || gi == 32) v->group = gi;
+    if (gi == 1 || gi == 8 || gi == 16 || gi == 32) v->group = gi;
   }
   v->device = device;
   if (device < 0) {  // host tables only
@@ -265,6 +269,10 @@ extern "C" void tmgpu_workspace_destroy(tmgpu_workspace* ws) {
   if (!ws) return;
   if (ws->v && ws->v->device >= 0) cudaSetDevice(ws->v->device);
   for (void* p : ws->allocs) cudaFree(p);
+  for (int i = 0; i < tmgpu_workspace::kEv; i++) {
+    if (ws->ev0[i]) cudaEventDestroy(ws->ev0[i]);
+    if (ws->ev1[i]) cudaEventDestroy(ws->ev1[i]);
+  }
   delete ws;
 }
 
@@ -308,8 +316,31 @@ extern "C" int tmgpu_workspace_create(tmgpu_vocab* v, uint32_t max_strings, uint
     tmgpu_workspace_destroy(ws);
     return rc;
   }
+  for (int i = 0; i < tmgpu_workspace::kEv; i++) {
+    CU(cudaEventCreate(&ws->ev0[i]));
+    CU(cudaEventCreate(&ws->ev1[i]));
+  }
   *out = ws;
   return TMGPU_OK;
+}
+
+// Durations (ms) of the tokenize kernel in the launches since the previous call, oldest first.
+// Synchronises on the last recorded event.  Returns the number of values written.
+extern "C" int tmgpu_workspace_kernel_times(tmgpu_workspace* ws, float* ms_out, int max_out) {
+  if (!ws || !ms_out) return 0;
+  int n = ws->ev_count < max_out ? ws->ev_count : max_out;
+  int first = (ws->ev_head - ws->ev_count + 2 * tmgpu_workspace::kEv) % tmgpu_workspace::kEv;
+  int skip = ws->ev_count - n;
+  for (int k = 0; k < n; k++) {
+    int i = (first + skip + k) % tmgpu_workspace::kEv;
+    if (cudaEventSynchronize(ws->ev1[i]) != cudaSuccess ||
+        cudaEventElapsedTime(&ms_out[k], ws->ev0[i], ws->ev1[i]) != cudaSuccess) {
+      cudaGetLastError();
+      ms_out[k] = -1.f;
+    }
+  }
+  ws->ev_count = 0;
+  return n;
 }
 
 extern "C" int tmgpu_last_launch_count(const tmgpu_workspace* ws) { return ws ? ws->last_launches : 0; }
@@ -341,12 +372,17 @@ static int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const 
     CU(cudaMemsetAsync(ws->missing, 0, size_t(n) * 4, st));
     CU(cudaMemsetAsync(ws->status, 0, n, st));
   } else if (n > 0) {
+    const int e = ws->ev_head;
+    CU(cudaEventRecord(ws->ev0[e], st));
     CU(launch_tokenize(a, v->group, mode == 0, v->sms, st, nullptr));
+    CU(cudaEventRecord(ws->ev1[e], st));
+    ws->ev_head = (e + 1) % tmgpu_workspace::kEv;
+    if (ws->ev_count < tmgpu_workspace::kEv) ws->ev_count++;
     ws->last_launches++;
   }
   if (mode == 0) {
     CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, ws->counts, ws->tok_off, n + 1, st));
-    ws->last_launches++;
+    ws->last_launches += 2;  // cub::DeviceScan = init kernel + scan kernel
     if (n > 0) {
       CU(launch_pack(a.slab, d_off, ws->slab_pad, slab_off, ws->counts, ws->tok_off, dense, n, enc_len, v->sms, st));
       ws->last_launches++;
@@ -375,7 +411,7 @@ extern "C" int tmgpu_tokenize_device(tmgpu_workspace* ws, const uint8_t* d_data,
     return TMGPU_E_ARG;
   }
   CU(cudaSetDevice(ws->v->device));
-  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ws->v->stream;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);  // NULL = the CUDA default stream
   int rc = tokenize_on_stream(ws, d_data, d_off, n, enc_len, mode, st, nullptr, ws->slab, ws->tokens);
   if (rc) return rc;
   if (view) {
@@ -687,7 +723,7 @@ extern "C" int tmgpu_decode_device(tmgpu_workspace* ws, const uint8_t* d_tokens,
     return TMGPU_E_ARG;
   }
   CU(cudaSetDevice(ws->v->device));
-  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ws->v->stream;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);  // NULL = the CUDA default stream
   uint64_t total = 0;
   int rc = decode_on_stream(ws, d_tokens, d_tok_off, n, enc_len, st, d_bytes, d_off, &total);
   if (rc) return rc;

@@ -6,9 +6,11 @@
 //   capcode_decode_kernel        capcode level-2 decoder (javascript/tokenmonster.js:1007-1065)
 #include "kernels.h"
 
+#include <cstdlib>
 #include <cub/device/device_scan.cuh>
 
 #include "tokenize_kernel.cuh"
+#include "tokenize_thread_kernel.cuh"
 
 namespace tmgpu {
 
@@ -218,8 +220,42 @@ static cudaError_t launch_tok(const TokenizeArgs& a, int sms, cudaStream_t st, i
   return cudaGetLastError();
 }
 
+template <int BLOCK, int CAP, bool STORE>
+static cudaError_t launch_thr(const TokenizeArgs& a, int sms, cudaStream_t st, int* grid_out) {
+  auto k = tokenize_thread_kernel<BLOCK, CAP, STORE>;
+  constexpr int smem = ThreadCfg<BLOCK>::SMEM;
+  static bool configured = false;
+  static int per_sm = 0;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, BLOCK, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    configured = true;
+  }
+  long long want = (static_cast<long long>(a.n) + BLOCK - 1) / BLOCK;
+  long long full = static_cast<long long>(sms) * per_sm;
+  int grid = int(want < full ? (want < 1 ? 1 : want) : full);
+  if (grid_out) *grid_out = grid;
+  k<<<grid, BLOCK, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_tokenize(const TokenizeArgs& a, int group, bool store, int sms, cudaStream_t st, int* grid_out) {
   const int cap = a.v.capcode;
+  if (group == 1) {  // one thread per string; big CTAs share a big edge cache when the batch fills them
+    static const bool force_big = getenv("TMGPU_BIG_CTA") != nullptr;  // test hook
+    const bool big = force_big || a.n >= uint32_t(sms) * 768u;
+#define TM_THR(B_)                                                                         \
+    if (cap == 0) return store ? launch_thr<B_, 0, true>(a, sms, st, grid_out)             \
+                               : launch_thr<B_, 0, false>(a, sms, st, grid_out);           \
+    return store ? launch_thr<B_, 2, true>(a, sms, st, grid_out)                           \
+                 : launch_thr<B_, 2, false>(a, sms, st, grid_out);
+    if (big) { TM_THR(1024) }
+    TM_THR(256)
+#undef TM_THR
+  }
 #define TM_CASE(G_)                                                                      \
   if (group == G_) {                                                                     \
     if (cap == 0) return store ? launch_tok<G_, 0, true>(a, sms, st, grid_out)           \

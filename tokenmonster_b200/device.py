@@ -26,7 +26,7 @@ class _CAI:
 
 def _view(ptr, count: int, typestr: str, device):
     if count == 0 or not ptr:
-        dt = {"|u1": torch.uint8, "<u2": torch.uint16, "<u4": torch.uint32, "<u8": torch.uint64}[typestr]
+        dt = {"|u1": torch.uint8, "<i4": torch.int32, "<i8": torch.int64}[typestr]
         return torch.empty(0, dtype=dt, device=device)
     return torch.as_tensor(_CAI(ptr, (count,), typestr), device=device)
 
@@ -66,19 +66,25 @@ class DeviceWorkspace:
     def launches(self) -> int:
         return lib().tmgpu_last_launch_count(self._h)
 
+    def kernel_times_ms(self):
+        """CUDA-event durations of the tokenize kernel for the launches since the last call."""
+        buf = (C.c_float * 64)()
+        k = lib().tmgpu_workspace_kernel_times(self._h, buf, 64)
+        return [float(buf[i]) for i in range(k)]
+
     def results(self):
         """Synchronise and wrap the outputs of the last launch_tokenize (mode 0) as torch tensors."""
         torch.cuda.current_stream(self.device).synchronize()
         n = self._n
-        tok_off = _view(self.view.tok_off, n + 1, "<u8", self.device)
+        tok_off = _view(self.view.tok_off, n + 1, "<i8", self.device)
         total = int(tok_off[-1].item()) if n >= 0 else 0
         tokens = _view(self.view.tokens, total * self._enc, "|u1", self.device)
         return {
             "tokens_u8": tokens,
             "tok_off": tok_off,
-            "missing": _view(self.view.missing, n, "<u4", self.device),
+            "missing": _view(self.view.missing, n, "<i4", self.device),
             "status": _view(self.view.status, n, "|u1", self.device),
-            "counts": _view(self.view.counts, n, "<u4", self.device),
+            "counts": _view(self.view.counts, n, "<i4", self.device),
             "n_tokens": total,
             "enc_len": self._enc,
         }
@@ -91,6 +97,6 @@ class DeviceWorkspace:
         off64 = tok_off.to(torch.int64) if tok_off.dtype != torch.int64 else tok_off
         check(lib().tmgpu_decode_device(self._h, tokens_u8.data_ptr(), off64.data_ptr(), n, enc_len, st,
                                         C.byref(d_bytes), C.byref(d_off), C.byref(d_total)))
-        off = _view(d_off.value, n + 1, "<u8", self.device)
+        off = _view(d_off.value, n + 1, "<i8", self.device)
         total = int(off[-1].item())
         return _view(d_bytes.value, total, "|u1", self.device), off
