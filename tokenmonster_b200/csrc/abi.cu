@@ -33,7 +33,7 @@ struct tmgpu_vocab {
   HostTables host;
   int device = -1;  // -1: host tables only (parser / table self-tests without a GPU)
   int sms = 0;
-  int group = 1;    // lanes per string: 1 = thread-per-string kernel, 8/16/32 = lanes-over-branches kernel
+  int group = 8;    // lanes per string: 8/16/32 = lanes-over-branches kernel, 1 = thread-per-string kernel
   VocabDev dev{};
   std::vector<void*> allocs;
   cudaStream_t stream = nullptr;
@@ -45,6 +45,12 @@ struct tmgpu_vocab {
   size_t d_off_cap = 0;
   int64_t* h_off = nullptr;       // pinned
   size_t h_off_cap = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t chunk_ev[32] = {};
+  // pinned host blocks handed out as results and taken back by tmgpu_result_free / bytes_free
+  struct PinnedBlock { void* p; size_t bytes; bool used; };
+  std::vector<PinnedBlock> pinned;
+  std::mutex pin_mu;
 };
 
 struct tmgpu_workspace {
@@ -76,6 +82,7 @@ struct tmgpu_workspace {
   std::vector<void*> allocs;
   int last_launches = 0;
   // CUDA events around the dominant kernel (tokenize) of the most recent launches
+  static constexpr int kMaxChunks = 32;
   static constexpr int kEv = 64;
   cudaEvent_t ev0[kEv] = {}, ev1[kEv] = {};
   int ev_head = 0, ev_count = 0;
@@ -176,9 +183,16 @@ extern "C" int tmgpu_vocab_create(const uint8_t* file_bytes, size_t n, int devic
     return fail(TMGPU_E_CUDA);
   }
   v->sms = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
     g_err = "cudaStreamCreate failed";
     return fail(TMGPU_E_CUDA);
+  }
+  for (auto& e : v->chunk_ev) {
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+      g_err = "cudaEventCreate failed";
+      return fail(TMGPU_E_CUDA);
+    }
   }
   VocabDev& d = v->dev;
   std::vector<uint8_t> image(1280);
@@ -229,6 +243,10 @@ extern "C" void tmgpu_vocab_destroy(tmgpu_vocab* v) {
   if (v->d_off) cudaFree(v->d_off);
   if (v->h_off) cudaFreeHost(v->h_off);
   if (v->stream) cudaStreamDestroy(v->stream);
+  if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
+  for (auto& e : v->chunk_ev)
+    if (e) cudaEventDestroy(e);
+  for (auto& b : v->pinned) cudaFreeHost(b.p);
   delete v;
 }
 
@@ -304,7 +322,7 @@ extern "C" int tmgpu_workspace_create(tmgpu_vocab* v, uint32_t max_strings, uint
   A(&ws->status, n1);
   A(&ws->tok_off, n1);
   A(&ws->tokens, ws->slab_ids * 4);
-  A(&ws->work_counter, 4);
+  A(&ws->work_counter, tmgpu_workspace::kMaxChunks);
   A(&ws->overflow, 4);
   ws->scan_bytes = scan_temp_bytes(uint32_t(n1)) + 256;
   A(reinterpret_cast<uint8_t**>(&ws->scan_temp), ws->scan_bytes);
@@ -345,12 +363,20 @@ extern "C" int tmgpu_workspace_kernel_times(tmgpu_workspace* ws, float* ms_out, 
 
 extern "C" int tmgpu_last_launch_count(const tmgpu_workspace* ws) { return ws ? ws->last_launches : 0; }
 
+// A host-buffer batch is tokenized in chunks of strings so that the H2D copy of chunk k+1 overlaps
+// the kernel of chunk k: `ready` is recorded on the copy stream after the chunk's bytes landed.
+struct ChunkPlan {
+  uint32_t s0, s1;       // strings [s0, s1)
+  uint64_t slab_base;    // (off[s0] - off[0]) + slab_pad * s0
+  cudaEvent_t ready;     // may be null
+};
+
 static int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t* d_off, uint32_t n,
                               uint8_t enc_len, int mode, cudaStream_t st, const uint64_t* slab_off,
-                              uint32_t* slab, uint8_t* dense) {
+                              uint32_t* slab, uint8_t* dense, const std::vector<ChunkPlan>* chunks = nullptr) {
   tmgpu_vocab* v = ws->v;
   ws->last_launches = 0;
-  CU(cudaMemsetAsync(ws->work_counter, 0, 4, st));
+  CU(cudaMemsetAsync(ws->work_counter, 0, 4 * tmgpu_workspace::kMaxChunks, st));
   CU(cudaMemsetAsync(ws->overflow, 0, 4, st));
   CU(cudaMemsetAsync(ws->counts + n, 0, 4, st));
   TokenizeArgs a{};
@@ -371,6 +397,23 @@ static int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const 
     CU(cudaMemsetAsync(ws->counts, 0, (size_t(n) + 1) * 4, st));
     CU(cudaMemsetAsync(ws->missing, 0, size_t(n) * 4, st));
     CU(cudaMemsetAsync(ws->status, 0, n, st));
+  } else if (n > 0 && chunks && !slab_off) {
+    int ci = 0;
+    for (const ChunkPlan& c : *chunks) {
+      if (c.s1 <= c.s0) continue;
+      if (c.ready) CU(cudaStreamWaitEvent(st, c.ready, 0));
+      TokenizeArgs b = a;
+      b.off = d_off + c.s0;
+      b.n = c.s1 - c.s0;
+      b.slab = slab + c.slab_base;
+      b.counts = ws->counts + c.s0;
+      b.need = ws->need + c.s0;
+      b.missing = ws->missing + c.s0;
+      b.status = ws->status + c.s0;
+      b.work_counter = ws->work_counter + (ci++ % tmgpu_workspace::kMaxChunks);
+      CU(launch_tokenize(b, v->group, mode == 0, v->sms, st, nullptr));
+      ws->last_launches++;
+    }
   } else if (n > 0) {
     const int e = ws->ev_head;
     CU(cudaEventRecord(ws->ev0[e], st));
@@ -464,67 +507,104 @@ static int ensure_host_path(tmgpu_vocab* v, uint32_t n, uint64_t bytes) {
 }
 
 struct ResultPriv {
-  std::vector<void*> pinned;
+  tmgpu_vocab* v = nullptr;
+  std::vector<void*> blocks;
 };
 
+// pinned host memory from the vocabulary's pool (cudaMallocHost is far too slow to pay per call)
 template <class T>
 static int pinned_alloc(ResultPriv* p, T** out, size_t count) {
-  void* q = nullptr;
   size_t bytes = count * sizeof(T);
-  if (bytes == 0) bytes = 8;
-  cudaError_t e = cudaMallocHost(&q, bytes);
-  if (e != cudaSuccess) {
-    g_err = std::string("cudaMallocHost: ") + cudaGetErrorString(e);
-    return TMGPU_E_NOMEM;
+  if (bytes < 64) bytes = 64;
+  tmgpu_vocab* v = p->v;
+  std::lock_guard<std::mutex> lock(v->pin_mu);
+  int best = -1;
+  for (size_t i = 0; i < v->pinned.size(); i++) {
+    auto& b = v->pinned[i];
+    if (!b.used && b.bytes >= bytes && (best < 0 || b.bytes < v->pinned[best].bytes)) best = int(i);
   }
-  p->pinned.push_back(q);
-  *out = static_cast<T*>(q);
+  if (best < 0) {
+    void* q = nullptr;
+    size_t cap = bytes + bytes / 4 + 4096;
+    cudaError_t e = cudaMallocHost(&q, cap);
+    if (e != cudaSuccess) {
+      g_err = std::string("cudaMallocHost: ") + cudaGetErrorString(e);
+      return TMGPU_E_NOMEM;
+    }
+    v->pinned.push_back({q, cap, false});
+    best = int(v->pinned.size()) - 1;
+  }
+  v->pinned[best].used = true;
+  p->blocks.push_back(v->pinned[best].p);
+  *out = static_cast<T*>(v->pinned[best].p);
   return TMGPU_OK;
+}
+
+static void release_priv(ResultPriv* p) {
+  if (!p) return;
+  if (p->v) {
+    std::lock_guard<std::mutex> lock(p->v->pin_mu);
+    for (void* q : p->blocks)
+      for (auto& b : p->v->pinned)
+        if (b.p == q) b.used = false;
+  }
+  delete p;
 }
 
 extern "C" void tmgpu_result_free(tmgpu_result* r) {
   if (!r) return;
-  auto* p = static_cast<ResultPriv*>(r->priv);
-  if (p) {
-    for (void* q : p->pinned) cudaFreeHost(q);
-    delete p;
-  }
+  release_priv(static_cast<ResultPriv*>(r->priv));
   delete r;
 }
 
 extern "C" void tmgpu_bytes_free(tmgpu_bytes* b) {
   if (!b) return;
-  auto* p = static_cast<ResultPriv*>(b->priv);
-  if (p) {
-    for (void* q : p->pinned) cudaFreeHost(q);
-    delete p;
-  }
+  release_priv(static_cast<ResultPriv*>(b->priv));
   delete b;
 }
 
-// stage host strings: device copy of data[off[0] .. off[n]) and offsets rebased to 0
-static int stage_input(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off, uint32_t n, uint64_t* total) {
+// stage host strings: offsets rebased to 0 go first, then the bytes in chunks on the copy stream;
+// each chunk records an event the compute stream waits on, so copy k+1 overlaps kernel k.
+static int stage_input(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off, uint32_t n, uint64_t* total,
+                       std::vector<ChunkPlan>* plan) {
   const uint64_t base = off[0];
   for (uint32_t i = 0; i <= n; i++) {
     if (off[i] < base || (i && off[i] < off[i - 1])) {
       g_err = "offsets must be non-decreasing";
       return TMGPU_E_ARG;
     }
-    v->h_off[i] = int64_t(off[i] - base);
-  }
-  *total = off[n] - base;
-  if (*total > 0x7FFFFFFFull * 1024) {
-    g_err = "batch too large";
-    return TMGPU_E_ARG;
-  }
-  for (uint32_t i = 0; i < n; i++) {
-    if (off[i + 1] - off[i] > 0x3FFFFFFFull) {
+    if (i && off[i] - off[i - 1] > 0x3FFFFFFFull) {
       g_err = "a single string may not exceed 1 GiB";
       return TMGPU_E_ARG;
     }
+    v->h_off[i] = int64_t(off[i] - base);
   }
-  if (*total) CU(cudaMemcpyAsync(v->d_in, data + base, *total, cudaMemcpyHostToDevice, v->stream));
-  CU(cudaMemcpyAsync(v->d_off, v->h_off, (size_t(n) + 1) * 8, cudaMemcpyHostToDevice, v->stream));
+  *total = off[n] - base;
+  CU(cudaMemcpyAsync(v->d_off, v->h_off, (size_t(n) + 1) * 8, cudaMemcpyHostToDevice, v->copy_stream));
+  // chunks of ~equal bytes; few enough that every launch still fills the GPU
+  int want = int(*total / (24ull << 20)) + 1;
+  if (want > 16) want = 16;
+  if (plan) plan->clear();
+  uint32_t s0 = 0;
+  const uint32_t pad = v->ws->slab_pad;
+  for (int c = 0; c < want && s0 < n; c++) {
+    uint32_t s1 = n;
+    if (c + 1 < want) {
+      const uint64_t target = *total * uint64_t(c + 1) / uint64_t(want);
+      uint32_t lo = s0, hi = n;  // first string whose end offset passes the target
+      while (lo < hi) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (uint64_t(v->h_off[mid + 1]) < target) lo = mid + 1; else hi = mid;
+      }
+      s1 = lo + 1 > n ? n : lo + 1;
+    }
+    const uint64_t b0 = uint64_t(v->h_off[s0]), b1 = uint64_t(v->h_off[s1]);
+    if (b1 > b0) CU(cudaMemcpyAsync(v->d_in + b0, data + base + b0, b1 - b0, cudaMemcpyHostToDevice, v->copy_stream));
+    CU(cudaEventRecord(v->chunk_ev[c], v->copy_stream));
+    if (plan) plan->push_back({s0, s1, b0 + uint64_t(pad) * s0, v->chunk_ev[c]});
+    s0 = s1;
+  }
+  if (!plan) CU(cudaStreamSynchronize(v->copy_stream));
   return TMGPU_OK;
 }
 
@@ -569,9 +649,10 @@ extern "C" int tmgpu_tokenize_batch(tmgpu_vocab* v, const uint8_t* data, const u
   int rc = ensure_host_path(v, n, off[n] - off[0]);
   if (rc) return rc;
   uint64_t total = 0;
-  if ((rc = stage_input(v, data, off, n, &total))) return rc;
+  std::vector<ChunkPlan> plan;
+  if ((rc = stage_input(v, data, off, n, &total, &plan))) return rc;
   tmgpu_workspace* ws = v->ws;
-  if ((rc = tokenize_on_stream(ws, v->d_in, v->d_off, n, enc_len, 0, v->stream, nullptr, ws->slab, ws->tokens)))
+  if ((rc = tokenize_on_stream(ws, v->d_in, v->d_off, n, enc_len, 0, v->stream, nullptr, ws->slab, ws->tokens, &plan)))
     return rc;
   std::vector<void*> temp;
   uint8_t* dense = ws->tokens;
@@ -584,6 +665,7 @@ extern "C" int tmgpu_tokenize_batch(tmgpu_vocab* v, const uint8_t* data, const u
     return rc;
   }
   auto* priv = new ResultPriv();
+  priv->v = v;
   auto* r = new tmgpu_result();
   std::memset(r, 0, sizeof(*r));
   r->priv = priv;
@@ -631,9 +713,11 @@ extern "C" int tmgpu_count_batch(tmgpu_vocab* v, const uint8_t* data, const uint
   int rc = ensure_host_path(v, n, off[n] - off[0]);
   if (rc) return rc;
   uint64_t total = 0;
-  if ((rc = stage_input(v, data, off, n, &total))) return rc;
+  std::vector<ChunkPlan> plan;
+  if ((rc = stage_input(v, data, off, n, &total, &plan))) return rc;
   tmgpu_workspace* ws = v->ws;
-  if ((rc = tokenize_on_stream(ws, v->d_in, v->d_off, n, 0, 1, v->stream, nullptr, ws->slab, ws->tokens))) return rc;
+  if ((rc = tokenize_on_stream(ws, v->d_in, v->d_off, n, 0, 1, v->stream, nullptr, ws->slab, ws->tokens, &plan)))
+    return rc;
   std::vector<uint32_t> c(n + 1), m(n + 1);
   std::vector<uint8_t> s(n + 1);
   CU(cudaMemcpyAsync(c.data(), ws->counts, size_t(n) * 4, cudaMemcpyDeviceToHost, v->stream));
@@ -761,6 +845,7 @@ extern "C" int tmgpu_decode_batch(tmgpu_vocab* v, const uint8_t* tokens, const u
   uint64_t total = 0;
   if ((rc = decode_on_stream(v->ws, v->d_in, v->d_off, n, enc_len, v->stream, &d_bytes, &d_off, &total))) return rc;
   auto* priv = new ResultPriv();
+  priv->v = v;
   auto* b = new tmgpu_bytes();
   std::memset(b, 0, sizeof(*b));
   b->priv = priv;

@@ -128,42 +128,58 @@ __global__ void __launch_bounds__(kBlockThreads) tokenize_kernel(const TokenizeA
   const bool spaced = (gl >= 3);
   const bool is_branch_lane = (gl < 6);
 
+  // ---- per-group string state (lives across iterations of the warp-synchronous loop) --------
+  bool running = false, no_more = false;
+  uint32_t s = 0;
+  int slen = 0, cshift = 0, total_c = 0;
+  const uint8_t* g0 = nullptr;
+  const uint8_t* ga = nullptr;
+  uint64_t slab_base = 0;
+  uint32_t cap = 0;
+  int filled = 0;                           // ring coordinates [0, filled) are valid
+  int rpos = 0;                             // CAP 2: raw characters consumed
+  bool in_word = false, run_mixed = false;  // CAP 2 encoder carry
+  uint32_t rl1 = '.', rl2 = '.';            // CAP 2: previous two raw characters
+  bool bad = false;                         // non-ASCII where ASCII is required
+  int i = 0, fd = 0, len = 0;
+  uint32_t idx = 0;
+  bool have = false;
+  uint32_t cnt = 0, miss = 0;
+
+  auto ring_at = [&](int p) -> uint32_t { return ring[(p + cshift) & (RB - 1)]; };
+  auto emit = [&](uint32_t id) {
+    if (STORE && gl == 0 && cnt < cap) A.slab[slab_base + cnt] = id;
+    cnt++;
+  };
+
+  // One iteration = at most one token step for every group of the warp.  The full-warp
+  // __syncwarp() keeps the 32/G strings of a warp in lock-step; without it the groups drift
+  // apart for good and every instruction issues for one group only (measured: 8.1 of 32 lanes
+  // active at G = 8, profiles/r01_v1_group8_details.txt).
   for (;;) {
-    uint32_t s = 0;
-    if (gl == 0) s = atomicAdd(A.work_counter, 1u);
-    s = __shfl_sync(gmask, s, 0, G);
-    if (s >= A.n) break;
-
-    const int64_t o0 = A.off[s];
-    const int slen = int(A.off[s + 1] - o0);
-    const uint8_t* g0 = A.data + o0;
-    const uint64_t slab_base = A.slab_off ? A.slab_off[s] : uint64_t(o0 - A.off[0]) + uint64_t(A.slab_pad) * s;
-    const uint32_t cap = A.slab_off ? uint32_t(A.slab_off[s + 1] - A.slab_off[s]) : uint32_t(slen) + A.slab_pad;
-
-    // ---- producer state ------------------------------------------------------------
-    const int cshift = (CAP == 0) ? int(reinterpret_cast<uintptr_t>(g0) & 15) : 0;
-    const uint8_t* ga = g0 - cshift;          // 16-byte aligned
-    int filled = 0;                           // ring coordinates [0, filled) are valid
-    const int total_c = cshift + slen;        // CAP 0: end coordinate of the data
-    int rpos = 0;                             // CAP 2: raw characters consumed
-    bool in_word = false, run_mixed = false;  // CAP 2 encoder carry
-    uint32_t rl1 = '.', rl2 = '.';            // CAP 2: previous two raw characters
-    bool bad = false;                         // non-ASCII where ASCII is required
-
-    // ---- consumer state ------------------------------------------------------------
-    int i = 0, fd = 0, len = 0;
-    uint32_t idx = 0;
-    bool have = false;
-    uint32_t cnt = 0, miss = 0;
-
-    auto ring_at = [&](int p) -> uint32_t { return ring[(p + cshift) & (RB - 1)]; };
-    auto emit = [&](uint32_t id) {
-      if (STORE && gl == 0 && cnt < cap) A.slab[slab_base + cnt] = id;
-      cnt++;
-    };
-
-    for (;;) {
-      __syncwarp(gmask);  // ring reads of the previous step are done before it is refilled
+    __syncwarp();
+    if (!running && !no_more) {
+      if (gl == 0) s = atomicAdd(A.work_counter, 1u);
+      s = __shfl_sync(gmask, s, 0, G);
+      if (s >= A.n) {
+        no_more = true;
+      } else {
+        const int64_t o0 = A.off[s];
+        slen = int(A.off[s + 1] - o0);
+        g0 = A.data + o0;
+        slab_base = A.slab_off ? A.slab_off[s] : uint64_t(o0 - A.off[0]) + uint64_t(A.slab_pad) * s;
+        cap = A.slab_off ? uint32_t(A.slab_off[s + 1] - A.slab_off[s]) : uint32_t(slen) + A.slab_pad;
+        cshift = (CAP == 0) ? int(reinterpret_cast<uintptr_t>(g0) & 15) : 0;
+        ga = g0 - cshift;                       // 16-byte aligned
+        filled = 0;
+        total_c = cshift + slen;                // CAP 0: end coordinate of the data
+        rpos = 0; in_word = false; run_mixed = false; rl1 = '.'; rl2 = '.'; bad = false;
+        i = 0; fd = 0; len = 0; idx = 0; have = false; cnt = 0; miss = 0;
+        running = true;
+      }
+    }
+    if (__all_sync(0xFFFFFFFFu, !running)) break;
+    if (running) {
       // =========================== producer: keep LA bytes ahead of i ================
       if (CAP == 0) {
         while (filled < total_c && filled < i + cshift + LA) {
@@ -304,13 +320,12 @@ __global__ void __launch_bounds__(kBlockThreads) tokenize_kernel(const TokenizeA
         bad = __any_sync(gmask, bad);
       }
       __syncwarp(gmask);
-      if (bad) break;
-
       const int len_data = (CAP == 0) ? slen : ((rpos >= slen) ? filled : 0x3FFFFFFF);
-      if (i >= len_data) break;
+      const bool finished = bad || (i >= len_data);
+      bool skip = finished;
 
       // =========================== consumer: one token step ==========================
-      if (!have) {
+      if (!skip && !have) {
         // LongestSubstring(data[i : i + min(lenData - i, M)])  (go:1049)
         uint32_t x = 0;
         int l = 0;
@@ -327,12 +342,14 @@ __global__ void __launch_bounds__(kBlockThreads) tokenize_kernel(const TokenizeA
           i++;
           miss++;
           fd = 0;
-          continue;
+          skip = true;
+        } else {
+          idx = x;
+          len = l;
+          have = true;
         }
-        idx = x;
-        len = l;
-        have = true;
       }
+      if (!skip) {
 
       // ---- "checkpoint": current token = (idx, len) at i (go:1051-1054) ----------------
       const uint4 r0 = __ldg(&V.rec[2 * idx]);
@@ -421,16 +438,19 @@ __global__ void __launch_bounds__(kBlockThreads) tokenize_kernel(const TokenizeA
         fd = (w >= 3) ? 1 : 0;
         have = true;
       }
-    }
-
-    if (gl == 0) {
-      if (bad) { cnt = 0; miss = 0; }
-      A.counts[s] = STORE ? min(cnt, cap) : cnt;
-      A.need[s] = cnt;
-      A.missing[s] = miss;
-      A.status[s] = bad ? 13 : 0;
-      if (STORE && cnt > cap) atomicExch(A.overflow, 1u);
-    }
+      }  // !skip
+      if (finished) {
+        if (gl == 0) {
+          if (bad) { cnt = 0; miss = 0; }
+          A.counts[s] = STORE ? min(cnt, cap) : cnt;
+          A.need[s] = cnt;
+          A.missing[s] = miss;
+          A.status[s] = bad ? 13 : 0;
+          if (STORE && cnt > cap) atomicExch(A.overflow, 1u);
+        }
+        running = false;
+      }
+    }  // running
   }
 }
 

@@ -121,58 +121,77 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
     return best_len;
   };
 
+  // ---- per-lane string state (lives across iterations of the warp-synchronous loop below) ----
+  bool running = false, no_more = false;
+  uint32_t s = 0;
+  int slen = 0, galign = 0, cshift = 0, total_c = 0;
+  const uint8_t* ga = nullptr;
+  uint64_t slab_base = 0;
+  uint32_t cap = 0;
+  int filled = 0;                                // ring coordinates [0, filled) are valid
+  bool bad = false;
+  // CAP 2 encoder: raw cursor + a 64-bit byte window refilled from 16-byte loads
+  int rc = 0;                                    // aligned coordinate of the next raw byte
+  uint4 q = make_uint4(0, 0, 0, 0);              // the 16-byte chunk at aligned coordinate qbase
+  int qbase = -16;
+  uint64_t win = 0;
+  int avail = 0;                                 // bytes in win, starting at coordinate rc
+  bool in_word = false, mixed = false;
+  uint32_t rl1 = '.', rl2 = '.';
+  uint32_t ow = 0;                               // partially assembled output word
+  // consumer
+  int i = 0, fd = 0, len = 0;
+  uint32_t idx = 0;
+  bool have = false;
+  uint32_t cnt = 0, miss = 0;
+
+  auto load16 = [&](int c0) -> uint4 {           // raw bytes [c0, c0+16) of the aligned stream
+    if (c0 + 16 <= total_c) return __ldg(reinterpret_cast<const uint4*>(ga + c0));
+    uint32_t t[4] = {0, 0, 0, 0};                // ragged tail: never read past the string
+    for (int k = 0; c0 + k < total_c; k++) t[k >> 2] |= uint32_t(ga[c0 + k]) << (8 * (k & 3));
+    return make_uint4(t[0], t[1], t[2], t[3]);
+  };
+  auto put = [&](uint32_t b) {                   // append one normalized byte (CAP 2)
+    ow |= b << ((filled & 3) * 8);
+    filled++;
+    if ((filled & 3) == 0) {
+      ring[(((filled - 1) >> 2) & (kRingWords - 1)) * 32] = ow;
+      ow = 0;
+    }
+  };
+  auto emit = [&](uint32_t id) {
+    if (STORE && cnt < cap) A.slab[slab_base + cnt] = id;
+    cnt++;
+  };
+
+  // One iteration = at most one token step for every lane.  The explicit __syncwarp() is what
+  // keeps the 32 strings of a warp in lock-step: without it the lanes drift apart for good the
+  // first time two strings end at different moments (measured: 2.0 of 32 lanes active).
   for (;;) {
-    const uint32_t s = atomicAdd(A.work_counter, 1u);
-    if (s >= A.n) break;
-    const int64_t o0 = A.off[s];
-    const int slen = int(A.off[s + 1] - o0);
-    const uint8_t* g0 = A.data + o0;
-    const uint64_t slab_base = A.slab_off ? A.slab_off[s] : uint64_t(o0 - A.off[0]) + uint64_t(A.slab_pad) * s;
-    const uint32_t cap = A.slab_off ? uint32_t(A.slab_off[s + 1] - A.slab_off[s]) : uint32_t(slen) + A.slab_pad;
-
-    // ---- producer state -------------------------------------------------------------------
-    const int galign = int(reinterpret_cast<uintptr_t>(g0) & 15);
-    const uint8_t* ga = g0 - galign;               // 16-byte aligned
-    const int cshift = (CAP == 0) ? galign : 0;    // ring coordinate of normalized byte 0
-    int filled = 0;                                // ring coordinates [0, filled) are valid
-    const int total_c = galign + slen;             // end of the raw data in aligned coordinates
-    bool bad = false;
-    // CAP 2 encoder: raw cursor + a 64-bit byte window refilled from 16-byte loads
-    int rc = galign;                               // aligned coordinate of the next raw byte
-    uint4 q = make_uint4(0, 0, 0, 0);              // the 16-byte chunk at aligned coordinate qbase
-    int qbase = -16;
-    uint64_t win = 0;
-    int avail = 0;                                 // bytes in win, starting at coordinate rc
-    bool in_word = false, mixed = false;
-    uint32_t rl1 = '.', rl2 = '.';
-    uint32_t ow = 0;                               // partially assembled output word
-
-    auto load16 = [&](int c0) -> uint4 {           // raw bytes [c0, c0+16) of the aligned stream
-      if (c0 + 16 <= total_c) return __ldg(reinterpret_cast<const uint4*>(ga + c0));
-      uint32_t t[4] = {0, 0, 0, 0};                // ragged tail: never read past the string
-      for (int k = 0; c0 + k < total_c; k++) t[k >> 2] |= uint32_t(ga[c0 + k]) << (8 * (k & 3));
-      return make_uint4(t[0], t[1], t[2], t[3]);
-    };
-    auto put = [&](uint32_t b) {                   // append one normalized byte (CAP 2)
-      ow |= b << ((filled & 3) * 8);
-      filled++;
-      if ((filled & 3) == 0) {
-        ring[(((filled - 1) >> 2) & (kRingWords - 1)) * 32] = ow;
-        ow = 0;
+    __syncwarp();
+    if (!running && !no_more) {
+      s = atomicAdd(A.work_counter, 1u);
+      if (s >= A.n) {
+        no_more = true;
+      } else {
+        const int64_t o0 = A.off[s];
+        slen = int(A.off[s + 1] - o0);
+        const uint8_t* g0 = A.data + o0;
+        slab_base = A.slab_off ? A.slab_off[s] : uint64_t(o0 - A.off[0]) + uint64_t(A.slab_pad) * s;
+        cap = A.slab_off ? uint32_t(A.slab_off[s + 1] - A.slab_off[s]) : uint32_t(slen) + A.slab_pad;
+        galign = int(reinterpret_cast<uintptr_t>(g0) & 15);
+        ga = g0 - galign;                        // 16-byte aligned
+        cshift = (CAP == 0) ? galign : 0;        // ring coordinate of normalized byte 0
+        total_c = galign + slen;                 // end of the raw data in aligned coordinates
+        filled = 0; bad = false;
+        rc = galign; qbase = -16; win = 0; avail = 0;
+        in_word = false; mixed = false; rl1 = '.'; rl2 = '.'; ow = 0;
+        i = 0; fd = 0; len = 0; idx = 0; have = false; cnt = 0; miss = 0;
+        running = true;
       }
-    };
-
-    // ---- consumer state -------------------------------------------------------------------
-    int i = 0, fd = 0, len = 0;
-    uint32_t idx = 0;
-    bool have = false;
-    uint32_t cnt = 0, miss = 0;
-    auto emit = [&](uint32_t id) {
-      if (STORE && cnt < cap) A.slab[slab_base + cnt] = id;
-      cnt++;
-    };
-
-    for (;;) {
+    }
+    if (__all_sync(0xFFFFFFFFu, !running)) break;
+    if (running) {
       // =========================== producer ==================================================
       if (CAP == 0) {
         while (filled < total_c && filled < i + cshift + LA) {
@@ -281,13 +300,13 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
         }
         if (filled & 3) ring[((filled >> 2) & (kRingWords - 1)) * 32] = ow;   // publish the partial word
       }
-      if (bad) break;
       const bool exhausted = (CAP == 0) ? true : (rc >= total_c);
       const int len_data = (CAP == 0) ? slen : (exhausted ? filled : 0x3FFFFFFF);
-      if (i >= len_data) break;
+      bool finished = bad || (i >= len_data);
+      bool skip = finished;
 
       // =========================== consumer: one token step ==================================
-      if (!have) {
+      if (!skip && !have) {
         uint32_t x;
         const int l = longest(i + cshift, min(len_data - i, M), kRootStart, x);   // go:1049
         if (l == 0) {                                                             // go:1269-1276
@@ -295,12 +314,14 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
           i++;
           miss++;
           fd = 0;
-          continue;
+          skip = true;
+        } else {
+          idx = x;
+          len = l;
+          have = true;
         }
-        idx = x;
-        len = l;
-        have = true;
       }
+      if (!skip) {
       const uint4 r0 = __ldg(&V.rec[2 * idx]);
       const uint4 r1 = __ldg(&V.rec[2 * idx + 1]);
       const uint32_t oflag = r0.x & 0xFFu;
@@ -382,14 +403,17 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
         fd = 1;
         have = true;
       }
-    }
-
-    if (bad) { cnt = 0; miss = 0; }
-    A.counts[s] = STORE ? min(cnt, cap) : cnt;
-    A.need[s] = cnt;
-    A.missing[s] = miss;
-    A.status[s] = bad ? 13 : 0;
-    if (STORE && cnt > cap) atomicExch(A.overflow, 1u);
+      }  // !skip
+      if (finished) {
+        if (bad) { cnt = 0; miss = 0; }
+        A.counts[s] = STORE ? min(cnt, cap) : cnt;
+        A.need[s] = cnt;
+        A.missing[s] = miss;
+        A.status[s] = bad ? 13 : 0;
+        if (STORE && cnt > cap) atomicExch(A.overflow, 1u);
+        running = false;
+      }
+    }  // running
   }
 }
 

@@ -12,7 +12,6 @@ the CPU.  torch is used only to hand device buffers to the device-resident entry
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass
 from typing import List, Sequence, Union
 
 import numpy as np
@@ -23,21 +22,52 @@ from ._lib import TmgpuError, check, lib
 Text = Union[str, bytes, bytearray, memoryview]
 
 
-@dataclass
 class TokenizeResult:
-    """Batch result: ids of string s are tokens[tok_off[s]:tok_off[s+1]]."""
-    tokens: np.ndarray      # uint16 / uint32 ids (enc_len 3 is widened to uint32)
-    tok_off: np.ndarray     # uint64 [n+1]
-    missing: np.ndarray     # uint32 [n]
-    status: np.ndarray      # uint8  [n]   0 ok, 13 normalization failed
-    enc_len: int
-    serialized: bytes       # the raw little-endian enc_len-byte stream (TokenizeToSerialized)
+    """Batch result: ids of string s are tokens[tok_off[s]:tok_off[s+1]].
+
+    The arrays are zero-copy views of the pinned host buffers the library returned; they stay
+    valid for the lifetime of this object (the buffers go back to the library's pool on __del__).
+    """
+
+    def __init__(self, res, n: int):
+        self._res = res
+        r = res.contents
+        nt, enc = int(r.n_tokens), int(r.enc_len)
+        self.enc_len = enc
+        self.n_tokens = nt
+        raw = np.ctypeslib.as_array(r.tokens, shape=(nt * enc,)) if nt else np.zeros(0, np.uint8)
+        self.raw = raw                                   # little-endian enc_len-byte stream
+        self.tok_off = np.ctypeslib.as_array(r.tok_off, shape=(n + 1,))
+        self.missing = np.ctypeslib.as_array(r.missing, shape=(n,)) if n else np.zeros(0, np.uint32)
+        self.status = np.ctypeslib.as_array(r.status, shape=(n,)) if n else np.zeros(0, np.uint8)
+        if enc == 2:
+            self.tokens = raw.view(np.uint16)
+        elif enc == 4:
+            self.tokens = raw.view(np.uint32)
+        else:
+            self.tokens = _widen24(raw)                  # 24-bit ids are widened (one copy)
+
+    @property
+    def serialized(self) -> bytes:
+        """The TokenizeToSerialized byte stream (go/tokenmonster.go:986)."""
+        return self.raw.tobytes()
 
     def __len__(self):
         return len(self.tok_off) - 1
 
     def __getitem__(self, s: int) -> np.ndarray:
         return self.tokens[int(self.tok_off[s]):int(self.tok_off[s + 1])]
+
+    def close(self):
+        if getattr(self, "_res", None) is not None:
+            lib().tmgpu_result_free(self._res)
+            self._res = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _flatten(texts: Sequence[Text]):
@@ -132,22 +162,7 @@ class Vocab:
         res = C.POINTER(_lib.Result)()
         check(lib().tmgpu_tokenize_batch(self._h, data.ctypes.data if data.size else None, off.ctypes.data, n,
                                          enc_len, C.byref(res)))
-        try:
-            r = res.contents
-            nt, enc = int(r.n_tokens), int(r.enc_len)
-            raw = np.ctypeslib.as_array(r.tokens, shape=(nt * enc,)).copy() if nt else np.zeros(0, np.uint8)
-            tok_off = np.ctypeslib.as_array(r.tok_off, shape=(n + 1,)).copy()
-            missing = np.ctypeslib.as_array(r.missing, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
-            status = np.ctypeslib.as_array(r.status, shape=(n,)).copy() if n else np.zeros(0, np.uint8)
-        finally:
-            lib().tmgpu_result_free(res)
-        if enc == 2:
-            toks = raw.view(np.uint16)
-        elif enc == 4:
-            toks = raw.view(np.uint32)
-        else:
-            toks = _widen24(raw)
-        return TokenizeResult(toks, tok_off, missing, status, enc, raw.tobytes())
+        return TokenizeResult(res, n)
 
     def tokenize(self, text):
         """python/tokenmonster.py:410 -- a string -> ids; a list of strings -> list of id arrays."""
