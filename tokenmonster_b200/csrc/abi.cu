@@ -33,7 +33,7 @@ struct tmgpu_vocab {
   HostTables host;
   int device = -1;  // -1: host tables only (parser / table self-tests without a GPU)
   int sms = 0;
-  int group = 8;    // lanes per string: 8/16/32 = lanes-over-branches kernel, 1 = thread-per-string kernel
+  int group = 1;    // 1 = lane-per-string kernel (default); 4/8/16/32 = lanes-over-branches kernel
   VocabDev dev{};
   std::vector<void*> allocs;
   cudaStream_t stream = nullptr;
@@ -157,7 +157,7 @@ extern "C" int tmgpu_vocab_create(const uint8_t* file_bytes, size_t n, int devic
   }
   if (const char* g = getenv("TMGPU_GROUP")) {
     int gi = atoi(g);
-    if (gi == 1 || gi == 8 || gi == 16 || gi == 32) v->group = gi;
+    if (gi == 1 || gi == 4 || gi == 8 || gi == 16 || gi == 32) v->group = gi;
   }
   v->device = device;
   if (device < 0) {  // host tables only
@@ -583,7 +583,9 @@ static int stage_input(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off,
   CU(cudaMemcpyAsync(v->d_off, v->h_off, (size_t(n) + 1) * 8, cudaMemcpyHostToDevice, v->copy_stream));
   // chunks of ~equal bytes; few enough that every launch still fills the GPU
   int want = int(*total / (24ull << 20)) + 1;
-  if (want > 16) want = 16;
+  if (want > 8) want = 8;
+  const int by_strings = int(n / (uint32_t(v->sms) * 800u));  // keep every launch big enough for full CTAs
+  if (want > by_strings) want = by_strings < 1 ? 1 : by_strings;
   if (plan) plan->clear();
   uint32_t s0 = 0;
   const uint32_t pad = v->ws->slab_pad;

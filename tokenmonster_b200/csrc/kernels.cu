@@ -245,14 +245,16 @@ static cudaError_t launch_thr(const TokenizeArgs& a, int sms, cudaStream_t st, i
 cudaError_t launch_tokenize(const TokenizeArgs& a, int group, bool store, int sms, cudaStream_t st, int* grid_out) {
   const int cap = a.v.capcode;
   if (group == 1) {  // one thread per string; big CTAs share a big edge cache when the batch fills them
-    static const bool force_big = getenv("TMGPU_BIG_CTA") != nullptr;  // test hook
-    const bool big = force_big || a.n >= uint32_t(sms) * 768u;
+    static const int forced = getenv("TMGPU_CTA") ? atoi(getenv("TMGPU_CTA")) : 0;  // experiment hook
+    int cta = forced ? forced : (a.n >= uint32_t(sms) * 768u ? 1024 : 256);
 #define TM_THR(B_)                                                                         \
     if (cap == 0) return store ? launch_thr<B_, 0, true>(a, sms, st, grid_out)             \
                                : launch_thr<B_, 0, false>(a, sms, st, grid_out);           \
     return store ? launch_thr<B_, 2, true>(a, sms, st, grid_out)                           \
                  : launch_thr<B_, 2, false>(a, sms, st, grid_out);
-    if (big) { TM_THR(1024) }
+    if (cta >= 1024) { TM_THR(1024) }
+    if (cta >= 768) { TM_THR(768) }
+    if (cta >= 512) { TM_THR(512) }
     TM_THR(256)
 #undef TM_THR
   }
@@ -266,6 +268,7 @@ cudaError_t launch_tokenize(const TokenizeArgs& a, int group, bool store, int sm
   TM_CASE(32)
   TM_CASE(16)
   TM_CASE(8)
+  TM_CASE(4)
 #undef TM_CASE
   return cudaErrorInvalidValue;
 }

@@ -13,11 +13,12 @@
 //     shared-memory ring.  Producer = fill_*: coalesced 16-byte loads (capcode 0) or the
 //     data-parallel capcode encoder (capcode 2: one input character per lane, emission offsets
 //     by a group prefix sum).  Consumer = the match loop below.
-//   * all six candidate continuations of a step (look-ahead after the longest token, after
-//     each of its two alternatives, and the three " "-prefixed retries: go:1068-1210) are
-//     independent once (i, index, length, forwardDelete) is known, so lanes 0..5 walk the
-//     prefix trie for them at the same time; scores live in registers and the winner is
-//     picked with a group max + ballot in the reference's tie order (go:1217-1262).
+//   * the three look-ahead positions of a step (after the longest token and after each of its two
+//     alternatives: go:1068,1113,1165) are independent once (i, index, length, forwardDelete) is
+//     known, so lanes 0..2 of the group walk the prefix trie for them at the same time; the
+//     " "-prefixed retries (go:1088-1107) run as a second pass on the same lanes, only where the
+//     plain result asks for one; the six scores live in registers and the winner is picked with
+//     a group max + two ballots in the reference's tie order (go:1217-1262).
 //   * the look-ahead token that wins becomes the next step's current token (the reference's
 //     `goto checkpoint`), and so does the plain look-ahead after a step that takes no branch,
 //     which is exactly the LongestSubstring the reference would recompute at the loop top.
@@ -122,11 +123,11 @@ __global__ void __launch_bounds__(kBlockThreads) tokenize_kernel(const TokenizeA
   const bool want_ascii = (V.normflag != 0) || (CAP != 0);
   const bool to_lower = (V.normflag & 2) != 0;
 
-  // per-lane branch role: lanes 0..2 plain look-ahead (primary, alt1, alt2), 3..5 the
-  // space-prefixed retries of the same three positions
-  const int br = gl % 3;
-  const bool spaced = (gl >= 3);
-  const bool is_branch_lane = (gl < 6);
+  // per-lane branch role: lanes 0..2 of a group own the three look-ahead positions (after the
+  // longest token, after alternative 1, after alternative 2); the same lane also does that
+  // position's space-prefixed retry when it is needed
+  const int br = gl;
+  const bool is_branch_lane = (gl < 3);
 
   // ---- per-group string state (lives across iterations of the warp-synchronous loop) --------
   bool running = false, no_more = false;
@@ -360,7 +361,8 @@ __global__ void __launch_bounds__(kBlockThreads) tokenize_kernel(const TokenizeA
       // skip the look-ahead for a whole word followed by a space (go:1057)
       const bool look = (i1 < len_data) && (((oflag & 32u) == 0) || s_begin[ring_at(i1)] != 12);
 
-      // this lane's candidate: first token a (flag, nWords), bytes it consumes, where b starts
+      // this lane's candidate: first token a (flag, nWords), bytes it consumes, where b starts.
+      // lanes 0,1,2 of the group = look-ahead after the longest token / alternative 1 / alternative 2
       int base = len;
       uint32_t aflag = oflag;
       int anw = int(onw);
@@ -369,52 +371,58 @@ __global__ void __launch_bounds__(kBlockThreads) tokenize_kernel(const TokenizeA
       if (br == 2) { base = alen2 - fd; aflag = (r1.x >> 24) & 0xFFu; anw = int(r1.y & 0xFFu); exists = exists && alen1 != 0 && alen2 != 0; }
       const int nw = anw - fd;
       const int p = i + base;
+      const int room = len_data - p;
       // lane 0's plain walk is always wanted: it is the next current token when no branch wins
-      bool walk = exists && (look || gl == 0) && (p <= len_data);
-      if (spaced) walk = walk && look && (V.delete_token != 0xFFFFFFu) && (V.space_start != kNoVal);
+      const bool walk = exists && (look || gl == 0) && (room >= 0);
+      // ---- phase 1: plain look-ahead (go:1068, :1113, :1165) ------------------------------
       uint32_t x = 0;
       int l = 0;
       if (walk) {
-        const int room = len_data - p;
-        const int maxd = spaced ? min(room, M - V.off) : min(room, M);
         l = trie_longest([&](int d) { return ring_at(p + d); }, [&](uint32_t b) { return s_root[b]; },
-                         [&](uint32_t h) { return __ldg(&V.edges[h]); }, V.edge_mask, V.edge_shift, V.n_info, maxd,
-                         spaced ? V.space_start : kRootStart, &x);
+                         [&](uint32_t h) { return __ldg(&V.edges[h]); }, V.edge_mask, V.edge_shift, V.n_info,
+                         min(room, M), kRootStart, &x);
       }
-      // second token's flag / nWords and the byte class after it
       uint32_t bflag = 0;
       int bnw = 0, nb = 0;
-      if (l > 0) {
+      int score = kNegScore;
+      if (look && l > 0) {
         const uint32_t w0 = __ldg(&V.rec[2 * x]).x;
         bflag = w0 & 0xFFu;
         bnw = int((w0 >> 8) & 0xFFu);
         const int q = p + l;  // q <= len_data; the byte AT len_data reads as 0 (cpp:1726)
         nb = s_begin[(q < len_data) ? ring_at(q) : 0u];
+        score = pair_score(base + l, aflag, nw, bflag, bnw, nb, false);
+        if (br != 0) score -= 100 * int(base + l < len) + 10000 * int(base + l == len);  // go:1132-1133
       }
-      // a retry lane needs the plain result of the same position (3 lanes below it)
-      const int pl_l = __shfl_up_sync(gmask, l, 3, G);
-      const uint32_t pl_flag = __shfl_up_sync(gmask, bflag, 3, G);
-      const int pl_nw = __shfl_up_sync(gmask, bnw, 3, G);
-      const int pl_nb = __shfl_up_sync(gmask, nb, 3, G);
-      int score = kNegScore;
-      if (look && l > 0) {
-        if (!spaced) {
-          score = pair_score(base + l, aflag, nw, bflag, bnw, nb, false);
-        } else if (pl_l > 0 && (pl_flag & 2u) && pl_nb == 1 && pl_nw == 0 && (l + V.off) > pl_l + 1) {
-          score = pair_score(base + l, aflag, nw, bflag, bnw, nb, true);  // go:1088-1107
-        }
-        if (score != kNegScore && br != 0) {  // go:1132-1133
-          const int bl = base + l;
-          score -= 100 * int(bl < len) + 10000 * int(bl == len);
+      // ---- phase 2: the " "-prefixed retry, only where the second token starts inside a word
+      //      (go:1088-1107); same lane, same position, trie walk started behind the virtual space
+      const bool need = (score != kNegScore) && (V.delete_token != 0xFFFFFFu) && (V.space_start != kNoVal) &&
+                        (bflag & 2u) && nb == 1 && bnw == 0;
+      int score_b = kNegScore, lb = 0;
+      uint32_t xb = 0;
+      if (__any_sync(gmask, need)) {
+        if (need) {
+          lb = trie_longest([&](int d) { return ring_at(p + d); }, [&](uint32_t b) { return s_root[b]; },
+                            [&](uint32_t h) { return __ldg(&V.edges[h]); }, V.edge_mask, V.edge_shift, V.n_info,
+                            min(room, M - V.off), V.space_start, &xb);
+          if (lb + V.off > l + 1) {
+            const uint32_t w0 = __ldg(&V.rec[2 * xb]).x;
+            const uint32_t bflag2 = w0 & 0xFFu;
+            const int bnw2 = int((w0 >> 8) & 0xFFu);
+            const int q = p + lb;
+            const int nb2 = s_begin[(q < len_data) ? ring_at(q) : 0u];
+            score_b = pair_score(base + lb, aflag, nw, bflag2, bnw2, nb2, true);
+            if (br != 0) score_b -= 100 * int(base + lb < len) + 10000 * int(base + lb == len);
+          }
         }
       }
-      if (!is_branch_lane) score = kNegScore;
-      // group max, then the first lane holding it: tie order s1,s2,s3,s1b,s2b,s3b (go:1217-1262)
-      int best = score;
+      // group max, then the first holder in the tie order s1,s2,s3,s1b,s2b,s3b (go:1217-1262)
+      int best = max(score, score_b);
 #pragma unroll
-      for (int d = 1; d < 8 && d < G; d <<= 1) best = max(best, __shfl_xor_sync(gmask, best, d, G));
-      best = __shfl_sync(gmask, best, 0, G);  // lanes 0..7 hold the max; make it group-uniform
-      const uint32_t win_mask = (__ballot_sync(gmask, score == best && is_branch_lane) & gmask) >> gbase;
+      for (int d = 1; d < 4 && d < G; d <<= 1) best = max(best, __shfl_xor_sync(gmask, best, d, G));
+      best = __shfl_sync(gmask, best, 0, G);  // lanes 0..3 hold the max; make it group-uniform
+      const uint32_t plain_mask = (__ballot_sync(gmask, score == best && is_branch_lane) & gmask) >> gbase;
+      const uint32_t retry_mask = (__ballot_sync(gmask, score_b == best && is_branch_lane) & gmask) >> gbase;
       const uint32_t id0 = r0.y, id1 = r0.z, id2 = r0.w;
       if (best == kNegScore) {
         emit(id0);                       // go:1265-1267
@@ -426,16 +434,14 @@ __global__ void __launch_bounds__(kBlockThreads) tokenize_kernel(const TokenizeA
         idx = nx;
         len = nl;
       } else {
-        const int w = __ffs(win_mask) - 1;
-        const int wbr = w % 3;
-        emit(wbr == 0 ? id0 : (wbr == 1 ? id1 : id2));
-        if (w >= 3) {
-          if (STORE) emit(V.delete_token);   // Count() adds only 1 here (go:1281-1543, quirk Q2)
-        }
+        const bool retry = (plain_mask == 0);
+        const int w = __ffs(retry ? retry_mask : plain_mask) - 1;
+        emit(w == 0 ? id0 : (w == 1 ? id1 : id2));
+        if (retry && STORE) emit(V.delete_token);   // Count() adds only 1 here (go:1281-1543, quirk Q2)
         i += __shfl_sync(gmask, base, w, G);
-        idx = __shfl_sync(gmask, x, w, G);
-        len = __shfl_sync(gmask, l, w, G);
-        fd = (w >= 3) ? 1 : 0;
+        idx = __shfl_sync(gmask, retry ? xb : x, w, G);
+        len = __shfl_sync(gmask, retry ? lb : l, w, G);
+        fd = retry ? 1 : 0;
         have = true;
       }
       }  // !skip

@@ -1,29 +1,34 @@
-// tokenize_thread_kernel.cuh -- K1/K3, second mapping: ONE THREAD PER STRING.
+// tokenize_thread_kernel.cuh -- K1/K3, mapping 2: ONE LANE PER STRING, warp-synchronous phases.
 //
-// Why a second mapping: the lanes-over-branches kernel (tokenize_kernel.cuh) was measured on a
-// B200 with ncu (profiles/r01_v1_group8_details.txt): 440 warp instructions per emitted id with
-// 8.1 of 32 lanes active on average -- the per-string control flow keeps the groups of a warp
-// from running in lock-step, so cooperative lanes buy nothing and the kernel is issue bound at
-// 0.13 % of the HBM roofline.  Tokenising a string is a strict dependency chain (the branch
-// chosen at step k fixes the position of step k+1, go/tokenmonster.go:1217-1262); the only
-// parallelism that keeps all 32 lanes busy is ACROSS strings.  So here every lane runs the whole
-// chain for its own string and the warp-level machinery is spent on what the memory system
-// needs instead:
-//   * normalized text lives in a shared-memory ring per string, interleaved word-by-word across
-//     the lanes of a warp (word w of lane t at ring[w*32 + t]) so that 32 different strings read
-//     their own bytes with zero bank conflicts, whatever their positions;
-//   * capcode level 2 is encoded on the fly into that ring by a forward-looking restatement of
-//     javascript/tokenmonster.js:900-1005: the marker of a capitalised run (W or C) and the
-//     "D C ␠" respelling of a mixed-case run are decided when the run starts, by peeking at the
-//     first lower-case / non-letter character after it, so nothing already emitted is rewritten;
-//   * the hashed trie edges (8 bytes each) are read through a direct-mapped software cache in
-//     shared memory shared by the whole CTA (hot edges hit there; misses fall through to the
-//     L2-resident table and refill the slot), and the first-byte table + beginByte are staged
-//     once per CTA by a TMA bulk copy;
-//   * strings are pulled from a global work counter by each lane as it finishes, so ragged
-//     batches keep the lanes of a warp occupied.
-// Same reference semantics as tokenize_kernel.cuh: go/tokenmonster.go:242-253 + :1017-1279
-// (ids) / :1281-1543 (count).
+// Why a second mapping.  ncu on the lanes-over-branches kernel (tokenize_kernel.cuh, profiles/
+// r01_v5_g4_*) shows ~330 warp instructions per emitted id with 8.6 of 32 lanes active: every
+// trie walk of a step runs until the LONGEST of the concurrent walks ends, and the tail of that
+// distribution (a 15-byte word) sets the pace while most lanes finished after 3 bytes.  The walks
+// of one string cannot be overlapped with its own next step (the branch chosen at step k fixes
+// the position of step k+1: go/tokenmonster.go:1217-1262), so the only way to keep lanes busy is
+// to give every lane its OWN string and its own little queue of walks, and to let all 32 lanes
+// drain their queues in one shared loop:
+//
+//   per warp iteration (= one token step for each of 32 strings)
+//     FILL   each lane tops up its normalized-text ring (capcode level 2 encoded on the fly by a
+//            branch-free, forward-looking restatement of javascript/tokenmonster.js:900-1005)
+//     WALK 1 one loop, one copy of the trie-step code: a lane pops its next look-ahead position
+//            (after the longest token / alternative 1 / alternative 2: go:1068,1113,1165) the
+//            moment its previous walk ends, so the loop runs for max(sum of a lane's depths), not
+//            for 3 x max(depth)
+//     SCORE  uniform straight-line code for the three plain candidates (go:1075-1133)
+//     WALK 2 same loop for the " "-prefixed retries that the plain results ask for (go:1088-1107)
+//     PICK   first maximum in the order s1,s2,s3,s1b,s2b,s3b (go:1217-1262), emit, advance
+//
+// Memory system: normalized text lives in shared-memory rings interleaved word-by-word across the
+// lanes of a warp (word w of lane t at ring[w*32+t]: 32 strings read their own bytes with zero
+// bank conflicts); trie edges (8 bytes each, L2-resident table at load factor <= 1/4) are read
+// through the read-only path behind an 8-bit child-byte filter kept in the parent's value, which
+// answers most "no such child" steps without a load (a CTA-shared software cache in shared
+// memory was measured slower: its miss path diverges, profiles/r01_v6_*); first-byte table,
+// beginByte and the character-class table are staged once per CTA by a TMA bulk copy; strings
+// are pulled from a global work counter by each lane.
+// Reference semantics: go/tokenmonster.go:242-253 + :1017-1279 (ids) / :1281-1543 (count).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -31,7 +36,7 @@
 
 #include "device_tables.h"
 #include "kernels.h"
-#include "tokenize_kernel.cuh"  // stage_tables_tma, char_class, lower4, smem layout constants
+#include "tokenize_kernel.cuh"  // stage_tables_tma, lower4, smem layout constants
 
 namespace tmgpu {
 
@@ -42,104 +47,57 @@ template <int BLOCK>
 struct ThreadCfg {
   static constexpr int WARPS = BLOCK / 32;
   static constexpr int RING_BYTES = WARPS * kRingWords * 32 * 4;   // interleaved rings
-  static constexpr int CACHE_ENTRIES = (BLOCK >= 1024) ? 8192 : (BLOCK >= 512 ? 4096 : 2048);
-  static constexpr int CACHE_BYTES = CACHE_ENTRIES * 8;
-  static constexpr int CACHE_BASE = kSmemRingBase;
-  static constexpr int RING_BASE = CACHE_BASE + CACHE_BYTES;
+  static constexpr int RING_BASE = kSmemRingBase;
   static constexpr int SMEM = RING_BASE + RING_BYTES;
 };
 
 template <int BLOCK, int CAP, bool STORE>
 __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const TokenizeArgs A) {
   using Cfg = ThreadCfg<BLOCK>;
+  constexpr unsigned FULL = 0xFFFFFFFFu;
   extern __shared__ __align__(128) uint8_t smem[];
-  // one 64-bit word per slot (key in the low half, value in the high half): read and written with
-  // single 8-byte shared accesses so a concurrent refill can never be observed half-way
-  volatile unsigned long long* s_cache = reinterpret_cast<volatile unsigned long long*>(smem + Cfg::CACHE_BASE);
-  for (int k = threadIdx.x; k < Cfg::CACHE_ENTRIES; k += BLOCK) s_cache[k] = ~0ull;
-  stage_tables_tma(smem, A.v.smem_image);   // contains a __syncthreads()
+  stage_tables_tma(smem, A.v.smem_image);   // root_child[256], begin_byte[256] (+ barrier inside)
+  uint8_t* s_cls = smem + kSmemTableBytes + 16;   // 240 bytes are free behind the mbarrier: classes of 0..127
+  if (threadIdx.x < 128) {
+    const uint32_t c = threadIdx.x;
+    s_cls[c] = uint8_t((c - 'a' < 26u) ? CL_L : (c - 'A' < 26u) ? CL_U : (c - '0' < 10u) ? CL_N : (c == '\'') ? CL_A : CL_O);
+  }
   __syncthreads();
   const uint32_t* s_root = reinterpret_cast<const uint32_t*>(smem);
   const uint8_t* s_begin = smem + 1024;
   const int lane = threadIdx.x & 31;
   uint32_t* ring = reinterpret_cast<uint32_t*>(smem + Cfg::RING_BASE) + (threadIdx.x >> 5) * (kRingWords * 32) + lane;
-  // word w of this string: ring[(w & 31) * 32]
 
   const VocabDev& V = A.v;
   const int M = V.max_len;
   const int LA = 2 * M + 2;
   const bool want_ascii = (V.normflag != 0) || (CAP != 0);
   const bool to_lower = (V.normflag & 2) != 0;
-  constexpr uint32_t kCacheShift = 32 - (Cfg::CACHE_ENTRIES == 8192 ? 13 : (Cfg::CACHE_ENTRIES == 4096 ? 12 : 11));
+  const bool can_retry = (V.delete_token != 0xFFFFFFu) && (V.space_start != kNoVal);
 
   auto ring_byte = [&](int c) -> uint32_t {
     return (ring[((c >> 2) & (kRingWords - 1)) * 32] >> ((c & 3) * 8)) & 0xFFu;
   };
+  auto cls_of = [&](uint32_t c) -> uint32_t { return s_cls[c & 127u]; };
 
-  // trie edge: CTA-shared direct-mapped cache in shared memory in front of the global table
-  auto find_edge = [&](uint32_t key) -> uint32_t {
-    const uint32_t slot = (key * 0x85EBCA6Bu) >> kCacheShift;
-    const unsigned long long c = s_cache[slot];
-    if (uint32_t(c) == key) return uint32_t(c >> 32);
-    uint32_t h = (key * 0x9E3779B1u) >> V.edge_shift;
-    uint32_t val;
-    for (;;) {
-      const uint2 e = __ldg(&V.edges[h]);
-      if (e.x == key) { val = e.y; break; }
-      if (e.x == kNoVal) { val = kNoVal; break; }
-      h = (h + 1) & V.edge_mask;
-    }
-    s_cache[slot] = (static_cast<unsigned long long>(val) << 32) | key;
-    return val;
-  };
-
-  // longest key prefixing normalized[c .. c+maxd) (ring coordinates); returns window bytes matched
-  auto longest = [&](int c, int maxd, uint32_t start, uint32_t& index) -> int {
-    int best_len = 0;
-    uint32_t best = 0, node = 0, sig = 0;
-    bool at_root = (start == kRootStart);
-    if (!at_root) { node = start & 0xFFFFFFu; sig = start >> 24; }
-    uint32_t w = ring[((c >> 2) & (kRingWords - 1)) * 32] >> ((c & 3) * 8);
-    for (int d = 0; d < maxd; d++) {
-      const uint32_t b = w & 0xFFu;
-      const int cn = c + d + 1;
-      w = (cn & 3) ? (w >> 8) : ring[((cn >> 2) & (kRingWords - 1)) * 32];
-      uint32_t val;
-      if (at_root) {
-        at_root = false;
-        val = s_root[b];
-      } else {
-        if (((sig >> sig_bit_of(b)) & 1u) == 0) break;
-        val = find_edge((node << 8) | b);
-      }
-      if (val == kNoVal) break;
-      node = val & 0xFFFFFFu;
-      sig = val >> 24;
-      if (node < V.n_info) { best = node; best_len = d + 1; }
-    }
-    index = best;
-    return best_len;
-  };
-
-  // ---- per-lane string state (lives across iterations of the warp-synchronous loop below) ----
+  // ---- per-lane string state ------------------------------------------------------------------
   bool running = false, no_more = false;
   uint32_t s = 0;
   int slen = 0, galign = 0, cshift = 0, total_c = 0;
   const uint8_t* ga = nullptr;
   uint64_t slab_base = 0;
   uint32_t cap = 0;
-  int filled = 0;                                // ring coordinates [0, filled) are valid
+  int filled = 0;                  // ring coordinates [0, filled) hold normalized text
   bool bad = false;
-  // CAP 2 encoder: raw cursor + a 64-bit byte window refilled from 16-byte loads
-  int rc = 0;                                    // aligned coordinate of the next raw byte
-  uint4 q = make_uint4(0, 0, 0, 0);              // the 16-byte chunk at aligned coordinate qbase
-  int qbase = -16;
-  uint64_t win = 0;
-  int avail = 0;                                 // bytes in win, starting at coordinate rc
+  int rc = 0;                      // CAP 2: aligned coordinate of the next raw character
+  uint4 q = make_uint4(0, 0, 0, 0);
+  int qbase = -16;                 // CAP 2: q holds raw bytes [qbase, qbase+16)
+  uint64_t win = 0;                // CAP 2: the next `avail` raw bytes, starting at rc
+  int avail = 0;
   bool in_word = false, mixed = false;
-  uint32_t rl1 = '.', rl2 = '.';
-  uint32_t ow = 0;                               // partially assembled output word
-  // consumer
+  uint32_t cl1 = CL_O, cl2 = CL_O; // classes of the previous two raw characters
+  bool sp1 = false;                // previous raw character was a space
+  uint32_t ow = 0;                 // CAP 2: partially assembled ring word
   int i = 0, fd = 0, len = 0;
   uint32_t idx = 0;
   bool have = false;
@@ -151,24 +109,24 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
     for (int k = 0; c0 + k < total_c; k++) t[k >> 2] |= uint32_t(ga[c0 + k]) << (8 * (k & 3));
     return make_uint4(t[0], t[1], t[2], t[3]);
   };
-  auto put = [&](uint32_t b) {                   // append one normalized byte (CAP 2)
-    ow |= b << ((filled & 3) * 8);
-    filled++;
-    if ((filled & 3) == 0) {
-      ring[(((filled - 1) >> 2) & (kRingWords - 1)) * 32] = ow;
-      ow = 0;
+  auto check16 = [&](uint4& w, int c0) {         // non-ASCII detection + optional lower-casing
+    uint32_t m0 = w.x, m1 = w.y, m2 = w.z, m3 = w.w;
+    if (c0 == 0 && galign) {                     // bytes before the string start are foreign
+      uint32_t t[4] = {m0, m1, m2, m3};
+      for (int k = 0; k < galign; k++) t[k >> 2] &= ~(0xFFu << (8 * (k & 3)));
+      m0 = t[0]; m1 = t[1]; m2 = t[2]; m3 = t[3];
     }
+    if ((m0 | m1 | m2 | m3) & 0x80808080u) bad = true;
+    if (to_lower) { w.x = lower4(w.x); w.y = lower4(w.y); w.z = lower4(w.z); w.w = lower4(w.w); }
   };
   auto emit = [&](uint32_t id) {
     if (STORE && cnt < cap) A.slab[slab_base + cnt] = id;
     cnt++;
   };
 
-  // One iteration = at most one token step for every lane.  The explicit __syncwarp() is what
-  // keeps the 32 strings of a warp in lock-step: without it the lanes drift apart for good the
-  // first time two strings end at different moments (measured: 2.0 of 32 lanes active).
   for (;;) {
     __syncwarp();
+    // ============================ take a new string ============================================
     if (!running && !no_more) {
       s = atomicAdd(A.work_counter, 1u);
       if (s >= A.n) {
@@ -180,32 +138,28 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
         slab_base = A.slab_off ? A.slab_off[s] : uint64_t(o0 - A.off[0]) + uint64_t(A.slab_pad) * s;
         cap = A.slab_off ? uint32_t(A.slab_off[s + 1] - A.slab_off[s]) : uint32_t(slen) + A.slab_pad;
         galign = int(reinterpret_cast<uintptr_t>(g0) & 15);
-        ga = g0 - galign;                        // 16-byte aligned
-        cshift = (CAP == 0) ? galign : 0;        // ring coordinate of normalized byte 0
-        total_c = galign + slen;                 // end of the raw data in aligned coordinates
+        ga = g0 - galign;
+        cshift = (CAP == 0) ? galign : 0;
+        total_c = galign + slen;
         filled = 0; bad = false;
         rc = galign; qbase = -16; win = 0; avail = 0;
-        in_word = false; mixed = false; rl1 = '.'; rl2 = '.'; ow = 0;
+        in_word = false; mixed = false; cl1 = CL_O; cl2 = CL_O; sp1 = false; ow = 0;
         i = 0; fd = 0; len = 0; idx = 0; have = false; cnt = 0; miss = 0;
         running = true;
       }
     }
-    if (__all_sync(0xFFFFFFFFu, !running)) break;
-    if (running) {
-      // =========================== producer ==================================================
-      if (CAP == 0) {
-        while (filled < total_c && filled < i + cshift + LA) {
+    if (__all_sync(FULL, !running)) break;
+
+    // ============================ FILL =========================================================
+    if (CAP == 0) {
+      for (;;) {
+        // the loop runs while some lane NEEDS bytes; every lane with ring space joins in
+        const bool must = running && filled < total_c && filled < i + cshift + LA;
+        if (!__any_sync(FULL, must)) break;
+        const bool want = running && filled < total_c && filled + 16 <= i + cshift + (kRingBytes - 16);
+        if (want) {
           uint4 w = load16(filled);
-          if (want_ascii) {
-            uint32_t m0 = w.x, m1 = w.y, m2 = w.z, m3 = w.w;
-            if (filled < cshift) {                 // leading bytes of the first block are foreign
-              uint32_t t[4] = {m0, m1, m2, m3};
-              for (int k = 0; k < cshift; k++) t[k >> 2] &= ~(0xFFu << (8 * (k & 3)));
-              m0 = t[0]; m1 = t[1]; m2 = t[2]; m3 = t[3];
-            }
-            if ((m0 | m1 | m2 | m3) & 0x80808080u) bad = true;
-            if (to_lower) { w.x = lower4(w.x); w.y = lower4(w.y); w.z = lower4(w.z); w.w = lower4(w.w); }
-          }
+          if (want_ascii) check16(w, filled);
           const int w0 = filled >> 2;
           ring[((w0 + 0) & (kRingWords - 1)) * 32] = w.x;
           ring[((w0 + 1) & (kRingWords - 1)) * 32] = w.y;
@@ -213,207 +167,290 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
           ring[((w0 + 3) & (kRingWords - 1)) * 32] = w.w;
           filled += 16;
         }
-      } else {
-        // capcode level 2 (javascript/tokenmonster.js:900-1005), one character at a time
-        while (rc < total_c && filled < i + LA) {
-          // keep >= 2 bytes in the window so the next character can be peeked
-          while (avail < 2) {
+      }
+    } else {
+      for (;;) {
+        const bool must = running && rc < total_c && filled < i + LA;
+        if (!__any_sync(FULL, must)) break;
+        const bool want = running && rc < total_c && filled + 4 <= i + (kRingBytes - 4);
+        if (want) {
+          // keep >= 2 raw bytes in the window so the next character can be peeked
+          while (avail < 2 && rc + avail < total_c) {
             const int nwc = rc + avail;            // first coordinate not yet in the window
-            if (nwc >= total_c) break;
-            const int wc = nwc & ~3;
-            const int cb = wc & ~15;
-            if (cb != qbase) {
-              q = load16(cb);
-              qbase = cb;
-              if (want_ascii) {
-                uint32_t m0 = q.x, m1 = q.y, m2 = q.z, m3 = q.w;
-                if (cb == 0 && galign) {           // bytes before the string start are foreign
-                  uint32_t t[4] = {m0, m1, m2, m3};
-                  for (int k = 0; k < galign; k++) t[k >> 2] &= ~(0xFFu << (8 * (k & 3)));
-                  m0 = t[0]; m1 = t[1]; m2 = t[2]; m3 = t[3];
-                }
-                if ((m0 | m1 | m2 | m3) & 0x80808080u) bad = true;
-                if (to_lower) { q.x = lower4(q.x); q.y = lower4(q.y); q.z = lower4(q.z); q.w = lower4(q.w); }
+            {
+              const int wc = nwc & ~3;
+              const int cb = wc & ~15;
+              if (cb != qbase) {
+                q = load16(cb);
+                qbase = cb;
+                check16(q, cb);
               }
+              const int wi = (wc >> 2) & 3;
+              const uint32_t wq = (wi == 0) ? q.x : (wi == 1) ? q.y : (wi == 2) ? q.z : q.w;
+              const int skip = nwc - wc;           // non-zero only for the first, unaligned word
+              win |= uint64_t(wq >> (8 * skip)) << (8 * avail);
+              avail += 4 - skip;
             }
-            const int wi = (wc >> 2) & 3;
-            const uint32_t wq = (wi == 0) ? q.x : (wi == 1) ? q.y : (wi == 2) ? q.z : q.w;
-            const int skip = nwc - wc;             // non-zero only for the first, unaligned word
-            win |= uint64_t(wq >> (8 * skip)) << (8 * avail);
-            avail += 4 - skip;
           }
           const uint32_t c = uint32_t(win) & 0xFFu;
           const bool has_next = (rc + 1 < total_c);
-          const uint32_t cn = has_next ? (uint32_t(win >> 8) & 0xFFu) : 0u;
+          const uint32_t cn = has_next ? (uint32_t(win >> 8) & 0xFFu) : uint32_t('.');
           win >>= 8;
           avail--;
           rc++;
-          const uint32_t cl = char_class(c);
-          const uint32_t cl_last = char_class(rl1);
-          const bool last_letter = (cl_last == CL_U || cl_last == CL_L);
-          const bool last_glue = last_letter || cl_last == CL_A;
-          if (cl == CL_U) {
-            if (!in_word) {
-              // decide W (word stays capital) or C (mixed case) from the first L/O char after the run
-              uint32_t k_cl = has_next ? char_class(cn) : CL_O;
-              if (has_next && !(k_cl == CL_L || k_cl == CL_O)) {
-                k_cl = CL_O;
-                for (int j = rc + 1; j < total_c; j++) {   // rare: runs of 3+ capitals / digits
-                  uint32_t cj = ga[j];
-                  if (to_lower && cj - 'A' < 26u) cj += 32;
-                  const uint32_t x = char_class(cj);
-                  if (x == CL_L || x == CL_O) { k_cl = x; break; }
-                }
+          const uint32_t cl = cls_of(c), cln = cls_of(cn);
+          const bool letter1 = (cl1 == CL_U) || (cl1 == CL_L);
+          const bool glue1 = letter1 || (cl1 == CL_A);
+          const bool start = (cl == CL_U) && !in_word;
+          if (start) {
+            // W (the word stays capital) or C (mixed case): class of the first L/O character
+            // after the run of capitals / digits / apostrophes that starts here
+            uint32_t k_cl = cln;
+            if (!(k_cl == CL_L || k_cl == CL_O)) {     // rare: a run of 2+ such characters
+              k_cl = CL_O;
+              for (int jj = rc + 1; jj < total_c; jj++) {
+                uint32_t cj = ga[jj];
+                if (to_lower && cj - 'A' < 26u) cj += 32;
+                const uint32_t x = cls_of(cj);
+                if (x == CL_L || x == CL_O) { k_cl = x; break; }
               }
-              mixed = (k_cl == CL_L);
-              if (rl1 != ' ') put('D');
-              put(mixed ? 'C' : 'W');
-              put(' ');
-              put(c | 0x20u);
-              in_word = true;
-            } else {
-              if (mixed) { put('D'); put('C'); put(' '); }
-              else if (!last_glue) { put('D'); put(' '); }
-              put(c | 0x20u);
             }
-          } else if (cl == CL_L) {
-            const uint32_t cl_last2 = char_class(rl2);
-            const bool joined = in_word ? last_glue
-                                        : (rl1 == ' ' || last_letter ||
-                                           ((cl_last2 == CL_U || cl_last2 == CL_L) && cl_last == CL_A));
-            if (!joined) { put('D'); put(' '); }
-            put(c);
-            in_word = false;
-          } else if (cl == CL_N) {
-            const bool joined = in_word ? (cl_last == CL_N) : (rl1 == ' ' || cl_last == CL_N);
-            if (!joined) { put('D'); put(' '); }
-            put(c);
+            mixed = (k_cl == CL_L);
+          }
+          // what goes in front of the character
+          const bool joined_l = in_word ? glue1 : (sp1 || letter1 || (((cl2 == CL_U) || (cl2 == CL_L)) && cl1 == CL_A));
+          const bool joined_n = in_word ? (cl1 == CL_N) : (sp1 || cl1 == CL_N);
+          const bool k_dspace = (cl == CL_L && !joined_l) || (cl == CL_N && !joined_n) ||
+                                (cl == CL_U && in_word && !mixed && !glue1);
+          const bool k_dcs = (cl == CL_U) && in_word && mixed;
+          const uint32_t marker = mixed ? 'C' : 'W';
+          uint32_t pre = 0, np = 0;
+          if (k_dspace) { pre = 'D' | (' ' << 8); np = 2; }
+          if (k_dcs) { pre = 'D' | ('C' << 8) | (' ' << 16); np = 3; }
+          if (start) {
+            pre = sp1 ? (marker | (' ' << 8)) : ('D' | (marker << 8) | (' ' << 16));
+            np = sp1 ? 2 : 3;
+          }
+          // a space right before the first letter of a capitalised word is replaced by the marker
+          // (js:976-979): the capital emits "<marker> x" and the space emits nothing
+          const bool eaten = (c == ' ') && has_next && (cln == CL_U);
+          const uint32_t ch = (cl == CL_U) ? (c | 0x20u) : c;
+          const uint64_t bytes = uint64_t(pre) | (eaten ? 0ull : (uint64_t(ch) << (8 * np)));
+          const uint32_t total = np + (eaten ? 0u : 1u);
+          // append `total` bytes to the ring through the partial word ow
+          const uint32_t sh = (filled & 3) * 8;
+          const uint64_t acc = uint64_t(ow) | (bytes << sh);
+          const int nf = filled + int(total);
+          if ((nf >> 2) != (filled >> 2)) {
+            ring[((filled >> 2) & (kRingWords - 1)) * 32] = uint32_t(acc);
+            ow = uint32_t(acc >> 32);
           } else {
-            // a space right before the first letter of a capitalised word is replaced by the
-            // marker (js:976-979): the capital emits "<marker>␠x", the space emits nothing
-            const bool eaten = (c == ' ') && has_next && (cn - 'A' < 26u);
-            if (!eaten) put(c);
-            if (cl == CL_O) in_word = false;
+            ow = uint32_t(acc);
           }
-          rl2 = rl1;
-          rl1 = c;
+          filled = nf;
+          // carries
+          in_word = (cl == CL_U) ? true : ((cl == CL_L || cl == CL_O) ? false : in_word);
+          cl2 = cl1;
+          cl1 = cl;
+          sp1 = (c == ' ');
         }
-        if (filled & 3) ring[((filled >> 2) & (kRingWords - 1)) * 32] = ow;   // publish the partial word
       }
-      const bool exhausted = (CAP == 0) ? true : (rc >= total_c);
-      const int len_data = (CAP == 0) ? slen : (exhausted ? filled : 0x3FFFFFFF);
-      bool finished = bad || (i >= len_data);
-      bool skip = finished;
+      if (running && (filled & 3)) ring[((filled >> 2) & (kRingWords - 1)) * 32] = ow;   // publish the partial word
+    }
 
-      // =========================== consumer: one token step ==================================
-      if (!skip && !have) {
-        uint32_t x;
-        const int l = longest(i + cshift, min(len_data - i, M), kRootStart, x);   // go:1049
-        if (l == 0) {                                                             // go:1269-1276
-          if (V.unk != 0xFFFFFFu) emit(V.unk);
-          i++;
-          miss++;
-          fd = 0;
-          skip = true;
-        } else {
-          idx = x;
-          len = l;
-          have = true;
+    // ============================ step setup ===================================================
+    const bool exhausted = (CAP == 0) ? true : (rc >= total_c);
+    const int len_data = (CAP == 0) ? slen : (exhausted ? filled : 0x3FFFFFFF);
+    const bool finished = running && (bad || i >= len_data);
+    const bool stepping = running && !finished;
+    const bool seek = stepping && !have;           // this iteration only finds the current token
+    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
+    if (stepping && have) {
+      r0 = __ldg(&V.rec[2 * idx]);
+      r1 = __ldg(&V.rec[2 * idx + 1]);
+    }
+    const uint32_t oflag = r0.x & 0xFFu;
+    const int alen1 = int(r0.x >> 24), alen2 = int(r1.x & 0xFFu);
+    const int i1 = i + len;
+    bool look = false;
+    if (stepping && have)
+      look = (i1 < len_data) && (((oflag & 32u) == 0) || s_begin[ring_byte(i1 + cshift)] != 12);   // go:1057
+    // the (up to) three look-ahead positions; a seeking lane has the single position i
+    const int base0 = seek ? 0 : len;
+    const int base1 = alen1 - fd, base2 = alen2 - fd;
+    uint32_t todo = 0;                              // bit j: walk at position j still to do
+    if (stepping) {
+      todo = 1u;                                    // position 0 is always wanted (next current token)
+      if (have && look && alen1 != 0) todo |= 2u;
+      if (have && look && alen1 != 0 && alen2 != 0) todo |= 4u;   // nested: go:1163
+    }
+    uint32_t x0 = 0, x1 = 0, x2 = 0;
+    int l0 = 0, l1 = 0, l2 = 0;
+
+    // ============================ WALK (two passes share the code) =============================
+    uint32_t need = 0;                              // bit j: retry wanted at position j
+    uint32_t xb0 = 0, xb1 = 0, xb2 = 0;
+    int lb0 = 0, lb1 = 0, lb2 = 0;
+    uint32_t bflag0 = 0, bflag1 = 0, bflag2 = 0;
+    int bnw0 = 0, bnw1 = 0, bnw2 = 0, nb0 = 0, nb1 = 0, nb2 = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+      uint32_t queue = (pass == 0) ? todo : need;
+      if (pass == 1 && !__any_sync(FULL, queue != 0)) break;
+      bool walking = false;
+      int j = 0, c = 0, d = 0, maxd = 0, best_len = 0;
+      uint32_t node = 0, best = 0, sig = 0;
+      for (;;) {
+        if (!__any_sync(FULL, walking || queue != 0)) break;
+        if (!walking && queue != 0) {               // pop this lane's next position
+          j = __ffs(queue) - 1;
+          queue &= queue - 1;
+          const int p = i + (j == 0 ? base0 : (j == 1 ? base1 : base2));
+          const int room = len_data - p;
+          c = p + cshift;
+          d = 0;
+          maxd = (pass == 0) ? min(room, M) : min(room, M - V.off);
+          node = (pass == 0) ? kRootStart : (V.space_start & 0xFFFFFFu);
+          sig = V.space_start >> 24;
+          best = 0;
+          best_len = 0;
+          walking = true;
+        }
+        if (walking) {
+          bool end = (d >= maxd);
+          if (!end) {
+            const uint32_t b = ring_byte(c + d);
+            uint32_t val;
+            if (node == kRootStart) {
+              val = s_root[b];
+            } else if (((sig >> sig_bit_of(b)) & 1u) == 0) {
+              val = kNoVal;                         // no child of this node starts with b
+            } else {
+              const uint32_t key = (node << 8) | b;
+              uint32_t h = (key * 0x9E3779B1u) >> V.edge_shift;
+              uint2 e = __ldg(&V.edges[h]);
+              while (e.x != key && e.x != kNoVal) {  // linear probing, load factor <= 1/4
+                h = (h + 1) & V.edge_mask;
+                e = __ldg(&V.edges[h]);
+              }
+              val = (e.x == key) ? e.y : kNoVal;
+            }
+            if (val == kNoVal) {
+              end = true;
+            } else {
+              node = val & 0xFFFFFFu;
+              sig = val >> 24;
+              d++;
+              if (node < V.n_info) { best = node; best_len = d; }
+            }
+          }
+          if (end) {
+            walking = false;
+            if (pass == 0) {
+              if (j == 0) { x0 = best; l0 = best_len; } else if (j == 1) { x1 = best; l1 = best_len; } else { x2 = best; l2 = best_len; }
+            } else {
+              if (j == 0) { xb0 = best; lb0 = best_len; } else if (j == 1) { xb1 = best; lb1 = best_len; } else { xb2 = best; lb2 = best_len; }
+            }
+          }
         }
       }
-      if (!skip) {
-      const uint4 r0 = __ldg(&V.rec[2 * idx]);
-      const uint4 r1 = __ldg(&V.rec[2 * idx + 1]);
-      const uint32_t oflag = r0.x & 0xFFu;
+      if (pass == 0) {
+        // second-token attributes of the plain results and which positions want the retry
+        const bool sc = stepping && have && look;
+        if (sc && l0 > 0) { const uint32_t w = __ldg(&V.rec[2 * x0]).x; bflag0 = w & 0xFFu; bnw0 = int((w >> 8) & 0xFFu); const int qq = i + base0 + l0; nb0 = s_begin[(qq < len_data) ? ring_byte(qq + cshift) : 0u]; }
+        if (sc && l1 > 0) { const uint32_t w = __ldg(&V.rec[2 * x1]).x; bflag1 = w & 0xFFu; bnw1 = int((w >> 8) & 0xFFu); const int qq = i + base1 + l1; nb1 = s_begin[(qq < len_data) ? ring_byte(qq + cshift) : 0u]; }
+        if (sc && l2 > 0) { const uint32_t w = __ldg(&V.rec[2 * x2]).x; bflag2 = w & 0xFFu; bnw2 = int((w >> 8) & 0xFFu); const int qq = i + base2 + l2; nb2 = s_begin[(qq < len_data) ? ring_byte(qq + cshift) : 0u]; }
+        if (sc && can_retry) {
+          if (l0 > 0 && (bflag0 & 2u) && nb0 == 1 && bnw0 == 0) need |= 1u;   // go:1088
+          if (l1 > 0 && (bflag1 & 2u) && nb1 == 1 && bnw1 == 0) need |= 2u;
+          if (l2 > 0 && (bflag2 & 2u) && nb2 == 1 && bnw2 == 0) need |= 4u;
+        }
+      }
+    }
+
+    // ============================ SCORE + PICK =================================================
+    if (seek) {
+      if (l0 == 0) {                                // no token covers this byte (go:1269-1276)
+        if (V.unk != 0xFFFFFFu) emit(V.unk);
+        i++;
+        miss++;
+        fd = 0;
+      } else {
+        idx = x0;
+        len = l0;
+        have = true;
+      }
+    } else if (stepping) {
       const int onw = int((r0.x >> 8) & 0xFFu);
-      const int alen1 = int(r0.x >> 24), alen2 = int(r1.x & 0xFFu);
-      const int i1 = i + len;
-      const bool look = (i1 < len_data) && (((oflag & 32u) == 0) || s_begin[ring_byte(i1 + cshift)] != 12);   // go:1057
-
-      int best = kNegScore, best_b = kNegScore;   // best plain / best retry score so far
-      int w_plain = 0, w_retry = 0;               // branch that holds it (first wins on ties)
-      uint32_t nx_plain = 0, nx_retry = 0;        // second token of that branch
-      int nl_plain = 0, nl_retry = 0;
-      int nbase_plain = 0, nbase_retry = 0;
-      uint32_t x0 = 0;                            // primary plain look-ahead (next current token)
-      int l0 = 0;
-#pragma unroll
-      for (int br = 0; br < 3; br++) {
-        int base = len;
-        uint32_t aflag = oflag;
-        int anw = onw;
-        bool exists = true;
-        if (br == 1) { base = alen1 - fd; aflag = (r1.x >> 8) & 0xFFu; anw = int((r1.x >> 16) & 0xFFu); exists = alen1 != 0; }
-        if (br == 2) { base = alen2 - fd; aflag = (r1.x >> 24) & 0xFFu; anw = int(r1.y & 0xFFu); exists = alen1 != 0 && alen2 != 0; }
-        const int p = i + base;
-        if (!(exists && (look || br == 0) && p <= len_data)) continue;
-        const int room = len_data - p;
-        uint32_t x;
-        const int l = longest(p + cshift, min(room, M), kRootStart, x);
-        if (br == 0) { x0 = x; l0 = l; }
-        if (!look || l == 0) continue;
-        const int nw = anw - fd;
-        const uint32_t w0 = __ldg(&V.rec[2 * x]).x;
-        const uint32_t bflag = w0 & 0xFFu;
-        const int bnw = int((w0 >> 8) & 0xFFu);
-        const int q1 = p + l;
-        const int nb = s_begin[(q1 < len_data) ? ring_byte(q1 + cshift) : 0u];
-        int sc = pair_score(base + l, aflag, nw, bflag, bnw, nb, false);
-        if (br != 0) sc -= 100 * int(base + l < len) + 10000 * int(base + l == len);   // go:1132-1133
-        if (sc > best) { best = sc; w_plain = br; nx_plain = x; nl_plain = l; nbase_plain = base; }
-        // " "-prefixed retry when the second token starts inside a word (go:1088-1107)
-        if (V.delete_token != 0xFFFFFFu && (bflag & 2u) && nb == 1 && bnw == 0 && V.space_start != kNoVal) {
-          uint32_t xb;
-          const int lb = longest(p + cshift, min(room, M - V.off), V.space_start, xb);
-          if (lb + V.off > l + 1) {
-            const uint32_t wb = __ldg(&V.rec[2 * xb]).x;
-            const uint32_t bflag2 = wb & 0xFFu;
-            const int bnw2 = int((wb >> 8) & 0xFFu);
-            const int q2 = p + lb;
-            const int nb2 = s_begin[(q2 < len_data) ? ring_byte(q2 + cshift) : 0u];
-            int sb = pair_score(base + lb, aflag, nw, bflag2, bnw2, nb2, true);
-            if (br != 0) sb -= 100 * int(base + lb < len) + 10000 * int(base + lb == len);
-            if (sb > best_b) { best_b = sb; w_retry = br; nx_retry = xb; nl_retry = lb; nbase_retry = base; }
-          }
+      const uint32_t aflag1 = (r1.x >> 8) & 0xFFu, aflag2 = (r1.x >> 24) & 0xFFu;
+      const int anw1 = int((r1.x >> 16) & 0xFFu), anw2 = int(r1.y & 0xFFu);
+      int best_s = kNegScore, pick = -1;            // pick: 0..2 plain, 3..5 retry
+      if (look) {
+        // plain candidates in the order s1, s2, s3 (strict > keeps the first maximum)
+        if (l0 > 0) {
+          const int sc = pair_score(base0 + l0, oflag, onw - fd, bflag0, bnw0, nb0, false);
+          if (sc > best_s) { best_s = sc; pick = 0; }
+        }
+        if ((todo & 2u) && l1 > 0) {
+          const int bl = base1 + l1;
+          const int sc = pair_score(bl, aflag1, anw1 - fd, bflag1, bnw1, nb1, false) - 100 * int(bl < len) - 10000 * int(bl == len);
+          if (sc > best_s) { best_s = sc; pick = 1; }
+        }
+        if ((todo & 4u) && l2 > 0) {
+          const int bl = base2 + l2;
+          const int sc = pair_score(bl, aflag2, anw2 - fd, bflag2, bnw2, nb2, false) - 100 * int(bl < len) - 10000 * int(bl == len);
+          if (sc > best_s) { best_s = sc; pick = 2; }
+        }
+        // retries in the order s1b, s2b, s3b; a plain score keeps a tie
+        if ((need & 1u) && lb0 + V.off > l0 + 1) {
+          const uint32_t w = __ldg(&V.rec[2 * xb0]).x;
+          const int qq = i + base0 + lb0;
+          const int nb = s_begin[(qq < len_data) ? ring_byte(qq + cshift) : 0u];
+          const int sc = pair_score(base0 + lb0, oflag, onw - fd, w & 0xFFu, int((w >> 8) & 0xFFu), nb, true);
+          if (sc > best_s) { best_s = sc; pick = 3; }
+        }
+        if ((need & 2u) && lb1 + V.off > l1 + 1) {
+          const uint32_t w = __ldg(&V.rec[2 * xb1]).x;
+          const int bl = base1 + lb1, qq = i + bl;
+          const int nb = s_begin[(qq < len_data) ? ring_byte(qq + cshift) : 0u];
+          const int sc = pair_score(bl, aflag1, anw1 - fd, w & 0xFFu, int((w >> 8) & 0xFFu), nb, true) - 100 * int(bl < len) - 10000 * int(bl == len);
+          if (sc > best_s) { best_s = sc; pick = 4; }
+        }
+        if ((need & 4u) && lb2 + V.off > l2 + 1) {
+          const uint32_t w = __ldg(&V.rec[2 * xb2]).x;
+          const int bl = base2 + lb2, qq = i + bl;
+          const int nb = s_begin[(qq < len_data) ? ring_byte(qq + cshift) : 0u];
+          const int sc = pair_score(bl, aflag2, anw2 - fd, w & 0xFFu, int((w >> 8) & 0xFFu), nb, true) - 100 * int(bl < len) - 10000 * int(bl == len);
+          if (sc > best_s) { best_s = sc; pick = 5; }
         }
       }
-      // tie order s1,s2,s3,s1b,s2b,s3b (go:1217-1262): strict > above keeps the first of each
-      // kind; a plain score wins a tie against a retry score
       const uint32_t id0 = r0.y, id1 = r0.z, id2 = r0.w;
-      if (best == kNegScore && best_b == kNegScore) {
-        emit(id0);                                 // go:1265-1267
+      if (pick < 0) {
+        emit(id0);                                   // go:1265-1267
         i += len;
         fd = 0;
         have = (l0 > 0);
         idx = x0;
         len = l0;
-      } else if (best >= best_b) {
-        emit(w_plain == 0 ? id0 : (w_plain == 1 ? id1 : id2));
-        i += nbase_plain;
-        idx = nx_plain;
-        len = nl_plain;
-        fd = 0;
-        have = true;
       } else {
-        emit(w_retry == 0 ? id0 : (w_retry == 1 ? id1 : id2));
-        if (STORE) emit(V.delete_token);           // Count() adds only 1 here (quirk Q2)
-        i += nbase_retry;
-        idx = nx_retry;
-        len = nl_retry;
-        fd = 1;
+        const int br = pick >= 3 ? pick - 3 : pick;
+        emit(br == 0 ? id0 : (br == 1 ? id1 : id2));
+        if (pick >= 3 && STORE) emit(V.delete_token);   // Count() adds only 1 here (quirk Q2)
+        i += (br == 0 ? base0 : (br == 1 ? base1 : base2));
+        if (pick >= 3) { idx = (br == 0 ? xb0 : (br == 1 ? xb1 : xb2)); len = (br == 0 ? lb0 : (br == 1 ? lb1 : lb2)); fd = 1; }
+        else { idx = (br == 0 ? x0 : (br == 1 ? x1 : x2)); len = (br == 0 ? l0 : (br == 1 ? l1 : l2)); fd = 0; }
         have = true;
       }
-      }  // !skip
-      if (finished) {
-        if (bad) { cnt = 0; miss = 0; }
-        A.counts[s] = STORE ? min(cnt, cap) : cnt;
-        A.need[s] = cnt;
-        A.missing[s] = miss;
-        A.status[s] = bad ? 13 : 0;
-        if (STORE && cnt > cap) atomicExch(A.overflow, 1u);
-        running = false;
-      }
-    }  // running
+    }
+    if (finished) {
+      if (bad) { cnt = 0; miss = 0; }
+      A.counts[s] = STORE ? min(cnt, cap) : cnt;
+      A.need[s] = cnt;
+      A.missing[s] = miss;
+      A.status[s] = bad ? 13 : 0;
+      if (STORE && cnt > cap) atomicExch(A.overflow, 1u);
+      running = false;
+    }
   }
 }
 

@@ -170,7 +170,7 @@ int parse_vocab(const uint8_t* file, size_t n, HostTables* t, std::string* err) 
   for (const Edge& e : edge_list)
     if (e.parent != kRoot) sig[e.parent] |= uint8_t(1u << sig_bit(e.byte));
   uint32_t bits = 4;
-  while ((1ull << bits) < edge_list.size() * 2 + 2) bits++;
+  while ((1ull << bits) < edge_list.size() * 4 + 2) bits++;  // load factor <= 1/4
   t->edge_bits = bits;
   t->edges.assign(size_t(1) << bits, ~0ull);
   for (int b = 0; b < 256; b++) t->root_child[b] = kNone;
