@@ -1,0 +1,85 @@
+"""The C ABI without a GPU: the library loads, exports what include/tmgpu.h declares, parses
+vocabularies, builds correct device tables, and refuses to compute without a device."""
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from workloads import corpus, vocabgen
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_library_exports_every_declared_symbol(built):
+    from tokenmonster_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "tmgpu.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(tmgpu_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 18
+    lib = _lib.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/tmgpu.h but not exported"
+        assert name in _lib.PROTOTYPES, f"{name} has no ctypes prototype"
+    assert b"sm_100a" in lib.tmgpu_version()
+
+
+def test_host_only_vocab_and_no_cpu_path(built):
+    from tokenmonster_b200 import TmgpuError, Vocab
+    with open(os.path.join(GOLD, "gpt2.vocab"), "rb") as f:
+        vb = f.read()
+    v = Vocab(vb, device=-1)
+    assert len(v) == 50238 and v.charset() == "UTF-8" and v.capcode() == 0 and v.max_token_length() == 40
+    assert v.highest_token_id() == 50256 and v.unk_token_id() is None and v.default_encoding_length() == 2
+    for call in (lambda: v.tokenize("hello"), lambda: v.tokenize_count("hello"), lambda: v.decode([1, 2, 3])):
+        with pytest.raises(TmgpuError) as e:
+            call()
+        assert e.value.code == 2 and "no CPU path" in str(e.value)
+
+
+def test_vocab_error_codes(built):
+    from tokenmonster_b200 import TmgpuError, Vocab
+    with open(os.path.join(GOLD, "small_nocap.vocab"), "rb") as f:
+        good = f.read()
+    for bad in (good[:100], good + b"x", b"\x09" + good[1:]):
+        with pytest.raises(TmgpuError) as e:
+            Vocab(bad, device=-1)
+        assert e.value.code == 14
+    swapped = vocabgen.raw_vocab([(b"b", 0, 0, 0, vocabgen.DNE, vocabgen.DNE), (b"a", 1, 0, 0, vocabgen.DNE, vocabgen.DNE)])
+    with pytest.raises(TmgpuError) as e:
+        Vocab(swapped, device=-1)
+    assert e.value.code == 15
+    level1 = b"\x01" + good[1:]
+    with pytest.raises(TmgpuError) as e:
+        Vocab(level1, device=-1)
+    assert e.value.code == 17
+    with pytest.raises(TmgpuError) as e:
+        Vocab.load("/nonexistent/x.vocab", device=-1)
+    assert e.value.code == 12
+
+
+@pytest.mark.parametrize("name", ["small_cap2", "small_nocap", "gpt2"])
+def test_device_trie_equals_oracle_dictionary(built, name):
+    """Walk the tables the kernels walk (host copy) against the oracle's longest-prefix search."""
+    from tokenmonster_b200 import Vocab
+    with open(os.path.join(GOLD, name + ".vocab"), "rb") as f:
+        vb = f.read()
+    v, o = Vocab(vb, device=-1), oracle.OracleVocab(vb, "port")
+    text = corpus.base_text(3, 120_000, 0.5, pool=3000)
+    if o.capcode == 2:
+        text = o.normalize(text)
+    rng = random.Random(9)
+    m = o.max_token_length
+    for _ in range(4000):
+        a = rng.randrange(len(text) - 64)
+        w = text[a:a + rng.randrange(1, m + 1)]
+        assert v._trie_lookup(w) == o.longest_prefix(w)
+        wi, wl = o.longest_prefix((b" " + w)[:m])
+        gi, gl = v._trie_lookup(w[:m - 1], spaced=True)
+        if wl <= 1:
+            assert gl == 0 or gl + 1 == wl
+        else:
+            assert (gi, gl + 1) == (wi, wl)

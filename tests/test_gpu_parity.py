@@ -1,0 +1,191 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle and the
+committed reference fixtures.  Bit-exact bar (integer / byte / index work)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from workloads import configs, corpus, vocabgen
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+KERNELS = ["1", "4", "8", "32"]   # TMGPU_GROUP: lane-per-string kernel and three widths of the group kernel
+
+
+def gold_vocab(name):
+    if name == "unit_cpp":
+        return vocabgen.unit_cpp_vocab()
+    with open(os.path.join(GOLD, name + ".vocab"), "rb") as f:
+        return f.read()
+
+
+def make_vocab(vb, group="1", cta=None):
+    from tokenmonster_b200 import Vocab
+    os.environ["TMGPU_GROUP"] = group
+    if cta:
+        os.environ["TMGPU_CTA"] = str(cta)
+    else:
+        os.environ.pop("TMGPU_CTA", None)
+    return Vocab(vb, device=0)
+
+
+def flat(texts):
+    off = np.zeros(len(texts) + 1, np.uint64)
+    off[1:] = np.cumsum([len(t) for t in texts])
+    return np.frombuffer(b"".join(texts), np.uint8), off
+
+
+def check_batch(v, chk, data, off, enc):
+    r = v.tokenize_batch(data, off, enc)
+    counts, cmiss, cstat = v.count_batch(data, off)
+    for s in range(len(off) - 1):
+        raw = data[int(off[s]):int(off[s + 1])].tobytes()
+        try:
+            want, miss = chk.tokenize(raw)
+            wc, _ = chk.tokenize(raw, mode=1)
+            st = 0
+        except oracle.OracleError as e:
+            want, miss, wc, st = np.zeros(0, np.uint32), 0, 0, e.status
+        assert np.array_equal(r[s].astype(np.uint32), want), f"string {s} ids differ"
+        assert int(r.missing[s]) == miss and int(r.status[s]) == st
+        assert int(counts[s]) == wc and int(cmiss[s]) == miss and int(cstat[s]) == st
+    return r
+
+
+@pytest.mark.parametrize("group", KERNELS)
+@pytest.mark.parametrize("name", ["unit_cpp", "small_cap2", "small_nocap", "gpt2"])
+def test_reference_golden_vectors(built, name, group):
+    """Outputs of the reference's own C++ runtime (tests/golden/make_golden.py)."""
+    with open(os.path.join(GOLD, "cases.json")) as f:
+        rows = json.load(f)[name]["rows"]
+    v = make_vocab(gold_vocab(name), group)
+    data, off = flat([bytes.fromhex(r["in"]) for r in rows])
+    encs = [4] if v.info.n_reverse > 65536 else [2, 3, 4]
+    for enc in encs:
+        r = v.tokenize_batch(data, off, enc)
+        assert not r.status.any()
+        for s, row in enumerate(rows):
+            assert r[s].astype(np.uint32).tolist() == row["ids"]
+            assert int(r.missing[s]) == row["missing"]
+            ser = r.raw[int(r.tok_off[s]) * enc:int(r.tok_off[s + 1]) * enc].tobytes()
+            assert ser.hex() == row[f"ser{enc}"]
+        back, boff = v.decode_batch(r.raw, r.tok_off, enc)
+        for s, row in enumerate(rows):
+            assert back[int(boff[s]):int(boff[s + 1])].tobytes().hex() == row["decoded"]
+    counts, _, _ = v.count_batch(data, off)
+    assert counts.tolist() == [row["count"] for row in rows]
+    v.close()
+
+
+@pytest.mark.parametrize("group", KERNELS)
+@pytest.mark.parametrize("name", ["c3", "c2", "c4", "c1"])
+def test_seeded_batches_against_oracle(built, name, group):
+    vb = configs.vocab_bytes(name)
+    v, chk = make_vocab(vb, group), oracle.OracleVocab(vb, "port")
+    base = corpus.base_text(31 + len(name), 1 << 19, configs.CONFIGS[name]["code"])
+    data, off = corpus.make_batch(base, 1500, 0, 900, 5, "cpu")
+    data, off = data.numpy(), off.numpy().astype(np.uint64)
+    enc = 2 if configs.CONFIGS[name]["ids"] <= 65536 else 4
+    r = check_batch(v, chk, data, off, enc)
+    # decode round trip on the device, compared with the oracle's decode
+    back, boff = v.decode_batch(r.raw, r.tok_off, enc)
+    for s in range(0, len(off) - 1, 7):
+        assert back[int(boff[s]):int(boff[s + 1])].tobytes() == chk.decode(r[s].astype(np.uint32))
+    v.close()
+
+
+@pytest.mark.parametrize("group,cta", [("1", 256), ("1", 768), ("1", 1024), ("8", None)])
+def test_edge_cases(built, group, cta):
+    """Empty / 1-byte / unaligned / non-ASCII / look-ahead at the very end / offsets not starting at 0."""
+    vb = gold_vocab("small_cap2")
+    v, chk = make_vocab(vb, group, cta), oracle.OracleVocab(vb, "port")
+    texts = [b"", b"a", b"A", b" ", b"", b"ab", b"Hello", b"x" * 3, "café".encode(), b"The End", b"\n", b"A" * 70 + b"b",
+             b"HTTP" * 40, b"9" * 33, b"don't", b"", b"a" * 1000, ("é" * 5).encode(), b"ok after bad"]
+    for pad in range(0, 17, 3):   # shift every string through all 16-byte alignments
+        data, off = flat([b"#" * pad] + texts)
+        check_batch(v, chk, data, off, 2)
+    data, off = flat(texts)
+    r = v.tokenize_batch(np.concatenate([np.zeros(5, np.uint8), data]), off + 5, 2)   # off[0] != 0
+    assert np.array_equal(r.tokens, v.tokenize_batch(data, off, 2).tokens)
+    assert r.status[8] == 13 and r.status[17] == 13 and int(r.tok_off[9] - r.tok_off[8]) == 0
+    v.close()
+
+
+def test_long_documents(built):
+    """64 KiB documents (BASELINE configs[3] shape): tokenize + detokenize round trip is the identity."""
+    vb = configs.vocab_bytes("c4")
+    v, chk = make_vocab(vb, "1"), oracle.OracleVocab(vb, "port")
+    base = corpus.base_text(404, 1 << 20, 0.9)
+    data, off = corpus.make_batch(base, 24, 65536, 65536, 3, "cpu")
+    data, off = data.numpy(), off.numpy().astype(np.uint64)
+    r = v.tokenize_batch(data, off, 2)
+    for s in (0, 11, 23):
+        want, _ = chk.tokenize(data[int(off[s]):int(off[s + 1])].tobytes())
+        assert np.array_equal(r[s].astype(np.uint32), want)
+    back, boff = v.decode_batch(r.raw, r.tok_off, 2)
+    assert np.array_equal(boff, off) and np.array_equal(back, data)   # NFD on ASCII + capcode 0 = identity
+    v.close()
+
+
+def test_slab_overflow_rerun(built):
+    """More ids than bytes (+16): single-byte vocabulary under capcode 2, alternating case.
+    The library notices the overflow and re-runs with exact sizes."""
+    vb = vocabgen.generate_vocab([], capcode=2, charset=1, normflag=1, level=3, reserve=8)
+    v, chk = make_vocab(vb, "1"), oracle.OracleVocab(vb, "port")
+    texts = [b"aAbBcCdD" * 20, b"plain lower case text", b"xY" * 200, b""]
+    data, off = flat(texts)
+    r = check_batch(v, chk, data, off, 2)
+    assert int(r.tok_off[1]) > len(texts[0]) + 16
+    v.close()
+
+
+def test_device_resident_path_matches_host_path(built):
+    import torch
+    from tokenmonster_b200.device import DeviceWorkspace
+    vb = configs.vocab_bytes("c2")
+    v = make_vocab(vb, "1")
+    base = corpus.base_text(9, 1 << 19, 0.3)
+    data, off = corpus.make_batch(base, 4000, 16, 700, 8, "cuda")
+    ws = DeviceWorkspace(v, 4000, int(off[-1]))
+    ws.launch_tokenize(data, off, 2, 0)
+    res = ws.results()
+    host = v.tokenize_batch(data.cpu().numpy(), off.cpu().numpy().astype(np.uint64), 2)
+    assert res["n_tokens"] == host.n_tokens
+    assert np.array_equal(res["tokens_u8"].cpu().numpy(), host.raw)
+    assert np.array_equal(res["tok_off"].cpu().numpy().astype(np.uint64), host.tok_off)
+    dbytes, doff = ws.decode(res["tokens_u8"], res["tok_off"], 2)
+    back, boff = v.decode_batch(host.raw, host.tok_off, 2)
+    assert np.array_equal(dbytes.cpu().numpy(), back) and np.array_equal(doff.cpu().numpy().astype(np.uint64), boff)
+    assert len(ws.kernel_times_ms()) == 1 and ws.launches() >= 1
+    ws.close()
+    v.close()
+
+
+def test_full_size_properties(built):
+    """BASELINE configs[1] at full size (1,000,000 strings): size-independent properties --
+    per-string id counts equal the Count kernel except where a retry emitted the delete token,
+    decode(tokenize(x)) == x for ASCII text, and a strided sample equals the oracle."""
+    import torch
+    from tokenmonster_b200.device import DeviceWorkspace
+    vb = configs.vocab_bytes("c2")
+    v, chk = make_vocab(vb, "1"), oracle.OracleVocab(vb, "port")
+    cfg = configs.CONFIGS["c2"]
+    base = corpus.base_text(cfg["seed"], 16 << 20, cfg["code"])
+    data, off = corpus.make_batch(base, 1_000_000, cfg["lo"], cfg["hi"], cfg["seed"] + 1, "cuda")
+    ws = DeviceWorkspace(v, 1_000_000, int(off[-1]))
+    ws.launch_tokenize(data, off, 2, 0)
+    res = ws.results()
+    assert int((res["status"] != 0).sum()) == 0
+    toks, toff = res["tokens_u8"].clone(), res["tok_off"].clone()
+    dbytes, doff = ws.decode(toks, toff, 2)
+    assert torch.equal(doff, off) and torch.equal(dbytes, data)      # lossless: capcode + NFD round trip
+    h_data, h_off = data.cpu().numpy(), off.cpu().numpy()
+    ids = toks.cpu().numpy().view(np.uint16)
+    t = toff.cpu().numpy()
+    for s in range(0, 1_000_000, 4999):
+        want, _ = chk.tokenize(h_data[int(h_off[s]):int(h_off[s + 1])].tobytes())
+        assert np.array_equal(ids[int(t[s]):int(t[s + 1])].astype(np.uint32), want)
+    ws.close()
+    v.close()

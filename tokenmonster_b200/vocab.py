@@ -202,11 +202,16 @@ class Vocab:
 
     # ---- decode ----------------------------------------------------------------------
     def decode_batch(self, tokens, tok_off, enc_len: int = 4):
-        """Batched Vocab.DecodeSerialized: returns (bytes array uint8, offsets uint64[n+1])."""
+        """Batched Vocab.DecodeSerialized: returns (bytes array uint8, offsets uint64[n+1]).
+
+        tokens: bytes / uint8 array = the serialized enc_len-byte stream; any other integer array =
+        ids, which are packed to enc_len bytes here."""
         if enc_len not in (2, 3, 4):
             raise TmgpuError(1, "Invalid encoding length")
         if isinstance(tokens, (bytes, bytearray, memoryview)):
-            raw = np.frombuffer(tokens, dtype=np.uint8)
+            raw = np.frombuffer(tokens, dtype=np.uint8)        # already the serialized stream
+        elif isinstance(tokens, np.ndarray) and tokens.dtype == np.uint8:
+            raw = tokens                                        # serialized stream as a byte array
         else:
             t = np.ascontiguousarray(tokens)
             if enc_len == 2:
