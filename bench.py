@@ -179,7 +179,7 @@ def run_reference(args):
     cfg = configs.CONFIGS[args.config]
     n = args.strings or cfg["n"]
     vb = configs.vocab_bytes(args.config)
-    sample_n = min(n, 60000)
+    sample_n = min(n, 600000)
     data, off = configs.batch(args.config, sample_n, "cpu")
     data_np, off_np = data.numpy(), off.numpy().astype(np.uint64)
     threads = os.cpu_count() or 1
@@ -293,6 +293,27 @@ def main():
     stop.set()
     th.join(timeout=3)
 
+    # ---- N > 1: the single-root path (one NCCL scatter of bytes, one gather of ids) -----------
+    root_line = None
+    if world > 1:
+        from tokenmonster_b200.dist import gpu_compute, tokenize_from_root
+        comp = gpu_compute(ws, enc)
+        for _ in range(2):
+            out = tokenize_from_root(data if rank == 0 else None, off if rank == 0 else None, comp, 0, dev)
+        sync_all()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        out = tokenize_from_root(data if rank == 0 else None, off if rank == 0 else None, comp, 0, dev)
+        r1.record()
+        sync_all()
+        tr = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            same = bool(torch.equal(out[0], res["tokens_u8"]))   # identical bytes to the 1-GPU result
+            root_line = {"value": total_bytes / (float(tr[0]) / 1e3) / 1e6, "unit": UNIT, "ms": float(tr[0]),
+                         "what": "rank 0's batch scattered over all ranks by bytes, tokenized, ids gathered back "
+                                 "(NCCL grouped send/recv); strong scaling of one batch", "identical_to_1gpu": same}
+
     # ---- reduce over ranks --------------------------------------------------------------------
     t = torch.tensor([elapsed_ms, e2e_s, float(total_bytes), float(n_tokens)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -330,8 +351,10 @@ def main():
                      "algorithmic_bytes_per_launch": total_bytes, "peak_source": peak_src},
         "clocks": summarize_clocks(samples),
         "tokens_per_step": all_tokens, "chars_per_token": all_bytes / max(all_tokens, 1.0), "strings_failed": bad_status,
-        "lanes_per_string": int(os.environ.get("TMGPU_GROUP", "8")),
+        "kernel_mapping": {"1": "lane-per-string (T2)"}.get(os.environ.get("TMGPU_GROUP", "1"), "lanes-over-branches G=" + os.environ.get("TMGPU_GROUP", "1")),
     }
+    if root_line:
+        line["root_scatter_gather"] = root_line
     if args.check:
         from oracle import oracle
         chk = oracle.OracleVocab(vb, "port")
@@ -342,7 +365,7 @@ def main():
             ok += 1
         line["checked_strings"] = ok
     if not args.no_cpu_baseline:
-        sample_n = min(n, 120000)
+        sample_n = min(n, 600000)
         cb = cpu_reference_rate(vb, h_np, h_off[:sample_n + 1], budget_s=12.0)
         line["cpu_baseline"] = cb
     print(json.dumps(line))
