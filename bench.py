@@ -203,13 +203,33 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit_line(line)
     return 0
 
 
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route everything libraries print on fd 1 (e.g. NCCL's version banner) to stderr; the one JSON
+    line goes to the real stdout through emit_line()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_line(obj):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -368,7 +388,7 @@ def main():
         sample_n = min(n, 600000)
         cb = cpu_reference_rate(vb, h_np, h_off[:sample_n + 1], budget_s=12.0)
         line["cpu_baseline"] = cb
-    print(json.dumps(line))
+    emit_line(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

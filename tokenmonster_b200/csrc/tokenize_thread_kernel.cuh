@@ -48,7 +48,9 @@ struct ThreadCfg {
   static constexpr int WARPS = BLOCK / 32;
   static constexpr int RING_BYTES = WARPS * kRingWords * 32 * 4;   // interleaved rings
   static constexpr int RING_BASE = kSmemRingBase;
-  static constexpr int SMEM = RING_BASE + RING_BYTES;
+  static constexpr int POOL_BASE = RING_BASE + RING_BYTES;         // per warp: 96 tasks, 96 results, counter
+  static constexpr int POOL_WARP_BYTES = 96 * 8 + 96 * 4 + 16;
+  static constexpr int SMEM = POOL_BASE + WARPS * POOL_WARP_BYTES;
 };
 
 template <int BLOCK, int CAP, bool STORE>
@@ -67,6 +69,10 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
   const uint8_t* s_begin = smem + 1024;
   const int lane = threadIdx.x & 31;
   uint32_t* ring = reinterpret_cast<uint32_t*>(smem + Cfg::RING_BASE) + (threadIdx.x >> 5) * (kRingWords * 32) + lane;
+  uint8_t* pool = smem + Cfg::POOL_BASE + (threadIdx.x >> 5) * Cfg::POOL_WARP_BYTES;
+  uint2* task = reinterpret_cast<uint2*>(pool);
+  uint32_t* res = reinterpret_cast<uint32_t*>(pool + 96 * 8);
+  int* next_task = reinterpret_cast<int*>(pool + 96 * 8 + 96 * 4);
 
   const VocabDev& V = A.v;
   const int M = V.max_len;
@@ -288,6 +294,10 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
     int l0 = 0, l1 = 0, l2 = 0;
 
     // ============================ WALK (two passes share the code) =============================
+    // All walks of the warp's 32 strings go into one pool in shared memory and the 32 lanes take
+    // them one at a time (shared-memory atomic counter), whoever the owner is: a long walk no
+    // longer keeps 31 lanes waiting, the loop runs for ~(total trie steps)/32 iterations.
+    // Task = {ring coordinate, owner lane | position j | max depth}; result = len<<24 | index.
     uint32_t need = 0;                              // bit j: retry wanted at position j
     uint32_t xb0 = 0, xb1 = 0, xb2 = 0;
     int lb0 = 0, lb1 = 0, lb2 = 0;
@@ -295,31 +305,59 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
     int bnw0 = 0, bnw1 = 0, bnw2 = 0, nb0 = 0, nb1 = 0, nb2 = 0;
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
-      uint32_t queue = (pass == 0) ? todo : need;
-      if (pass == 1 && !__any_sync(FULL, queue != 0)) break;
-      bool walking = false;
-      int j = 0, c = 0, d = 0, maxd = 0, best_len = 0;
-      uint32_t node = 0, best = 0, sig = 0;
-      for (;;) {
-        if (!__any_sync(FULL, walking || queue != 0)) break;
-        if (!walking && queue != 0) {               // pop this lane's next position
-          j = __ffs(queue) - 1;
-          queue &= queue - 1;
-          const int p = i + (j == 0 ? base0 : (j == 1 ? base1 : base2));
-          const int room = len_data - p;
-          c = p + cshift;
-          d = 0;
-          maxd = (pass == 0) ? min(room, M) : min(room, M - V.off);
-          node = (pass == 0) ? kRootStart : (V.space_start & 0xFFFFFFu);
-          sig = V.space_start >> 24;
-          best = 0;
-          best_len = 0;
-          walking = true;
+      const uint32_t queue = (pass == 0) ? todo : need;
+      // compact the tasks of all lanes: position j of lane t gets slot  (#tasks of lower j) + rank
+      const uint32_t m0 = __ballot_sync(FULL, queue & 1u), m1 = __ballot_sync(FULL, queue & 2u),
+                     m2 = __ballot_sync(FULL, queue & 4u);
+      const int n0 = __popc(m0), n1 = __popc(m1), ntask = n0 + n1 + __popc(m2);
+      if (ntask == 0) {
+        if (pass == 1) break;
+        continue;
+      }
+      const uint32_t lt = (1u << lane) - 1u;
+      const int maxd_cap = (pass == 0) ? M : (M - V.off);
+#pragma unroll
+      for (int jj = 0; jj < 3; jj++) {
+        res[jj * 32 + lane] = 0;
+        if (queue & (1u << jj)) {
+          const int slot = (jj == 0 ? 0 : (jj == 1 ? n0 : n0 + n1)) + __popc((jj == 0 ? m0 : (jj == 1 ? m1 : m2)) & lt);
+          const int p = i + (jj == 0 ? base0 : (jj == 1 ? base1 : base2));
+          task[slot] = make_uint2(uint32_t(p + cshift),
+                                  uint32_t(lane) | (uint32_t(jj) << 5) | (uint32_t(max(0, min(len_data - p, maxd_cap))) << 8));
         }
+      }
+      if (lane == 0) *next_task = 0;
+      __syncwarp();
+      bool walking = false, dry = false;
+      int c = 0, d = 0, maxd = 0, best_len = 0, slot_out = 0;
+      uint32_t node = 0, best = 0, sig = 0;
+      const uint32_t* col = ring;                   // ring column of the task's owner
+      for (;;) {
+        if (!walking && !dry) {                     // take the next task of the pool
+          const int t = atomicAdd(next_task, 1);
+          if (t < ntask) {
+            const uint2 tk = task[t];
+            const int owner = int(tk.y & 31u);
+            c = int(tk.x);
+            d = 0;
+            maxd = int(tk.y >> 8);
+            slot_out = int((tk.y >> 5) & 3u) * 32 + owner;
+            col = ring - lane + owner;
+            node = (pass == 0) ? kRootStart : (V.space_start & 0xFFFFFFu);
+            sig = V.space_start >> 24;
+            best = 0;
+            best_len = 0;
+            walking = true;
+          } else {
+            dry = true;
+          }
+        }
+        if (!__any_sync(FULL, walking)) break;
         if (walking) {
           bool end = (d >= maxd);
           if (!end) {
-            const uint32_t b = ring_byte(c + d);
+            const int cc = c + d;
+            const uint32_t b = (col[((cc >> 2) & (kRingWords - 1)) * 32] >> ((cc & 3) * 8)) & 0xFFu;
             uint32_t val;
             if (node == kRootStart) {
               val = s_root[b];
@@ -346,14 +384,24 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
           }
           if (end) {
             walking = false;
-            if (pass == 0) {
-              if (j == 0) { x0 = best; l0 = best_len; } else if (j == 1) { x1 = best; l1 = best_len; } else { x2 = best; l2 = best_len; }
-            } else {
-              if (j == 0) { xb0 = best; lb0 = best_len; } else if (j == 1) { xb1 = best; lb1 = best_len; } else { xb2 = best; lb2 = best_len; }
-            }
+            res[slot_out] = best | (uint32_t(best_len) << 24);
           }
         }
       }
+      __syncwarp();
+      {
+        const uint32_t ra = res[lane], rb = res[32 + lane], rcv = res[64 + lane];
+        if (pass == 0) {
+          x0 = ra & 0xFFFFFFu; l0 = int(ra >> 24);
+          x1 = rb & 0xFFFFFFu; l1 = int(rb >> 24);
+          x2 = rcv & 0xFFFFFFu; l2 = int(rcv >> 24);
+        } else {
+          xb0 = ra & 0xFFFFFFu; lb0 = int(ra >> 24);
+          xb1 = rb & 0xFFFFFFu; lb1 = int(rb >> 24);
+          xb2 = rcv & 0xFFFFFFu; lb2 = int(rcv >> 24);
+        }
+      }
+      __syncwarp();
       if (pass == 0) {
         // second-token attributes of the plain results and which positions want the retry
         const bool sc = stepping && have && look;
