@@ -126,6 +126,17 @@ int tmgpu_decode_batch(tmgpu_vocab* v, const uint8_t* tokens, const uint64_t* to
                        uint8_t enc_len, tmgpu_bytes** out);
 void tmgpu_bytes_free(tmgpu_bytes* b);
 
+/* ---- streaming decode: Vocab.NewDecoder / Decoder.Decode / DecodeSerialized / Flush ----------
+ *      (go/tokenmonster.go:450-740; python Vocab.decoder(), py:273) for a BATCH of n streams.
+ * Stream s consumes ids [tok_off[s], tok_off[s+1]) of this call; its incomplete UTF-8 / UTF-16
+ * tail (go:149-219) and its capcode decoder flags persist on the device until the next call. */
+typedef struct tmgpu_decoder tmgpu_decoder;
+int tmgpu_decoder_create(tmgpu_vocab* v, uint32_t n_streams, tmgpu_decoder** out);
+void tmgpu_decoder_destroy(tmgpu_decoder* d);
+int tmgpu_decoder_decode(tmgpu_decoder* d, const uint8_t* tokens, const uint64_t* tok_off,
+                         uint8_t enc_len, tmgpu_bytes** out);
+int tmgpu_decoder_flush(tmgpu_decoder* d, tmgpu_bytes** out);
+
 /* ---- device-resident path (inputs already in HBM; used for the kernel roofline figure and
  *      by the sharded multi-GPU host) -------------------------------------------------------
  * A workspace owns the device output buffers for batches up to (max_strings, max_bytes).

@@ -189,3 +189,43 @@ def test_full_size_properties(built):
         assert np.array_equal(ids[int(t[s]):int(t[s + 1])].astype(np.uint32), want)
     ws.close()
     v.close()
+
+
+@pytest.mark.parametrize("name", ["unit_cpp", "small_cap2", "small_nocap", "gpt2"])
+def test_streaming_decoder_golden(built, name):
+    """Decoder.Decode in three uneven pieces + Flush, against the reference's outputs (go:701-740)."""
+    with open(os.path.join(GOLD, "cases.json")) as f:
+        rows = json.load(f)[name]["rows"]
+    v = make_vocab(gold_vocab(name), "1")
+    d = v.decoder(len(rows))
+    ids = [np.array(r["ids"], np.uint32) for r in rows]
+    cuts = [(len(x) // 3, (2 * len(x)) // 3) for x in ids]
+    got = [d.decode_batch([x[:a] for x, (a, b) in zip(ids, cuts)]),
+           d.decode_batch([x[a:b] for x, (a, b) in zip(ids, cuts)]),
+           d.decode_batch([x[b:] for x, (a, b) in zip(ids, cuts)]),
+           d.flush()]
+    for s, row in enumerate(rows):
+        assert [g[s].hex() for g in got] == row["stream"], f"stream {s}"
+    d.close()
+    v.close()
+
+
+def test_streaming_decoder_splits_utf8_and_capcode_state(built):
+    """Ids that cut multi-byte characters (gpt2 byte-level pieces) and capcode markers split across
+    calls, one id at a time, against the oracle's Decoder."""
+    for name, texts in (("gpt2", ["naïve café — 日本語 😀 done", "€uro", "x"]),
+                        ("small_cap2", [b"Hello WORLD and CamelCase HTTP/2 don't", b"THE END", b""])):
+        vb = gold_vocab(name)
+        v, chk = make_vocab(vb, "1"), oracle.OracleVocab(vb, "port")
+        texts = [t.encode() if isinstance(t, str) else t for t in texts]
+        ids = [chk.tokenize(t)[0] for t in texts]
+        d, od = v.decoder(len(texts)), [chk.new_decoder() for _ in texts]
+        steps = max(len(x) for x in ids)
+        for k in range(steps):
+            chunk = [x[k:k + 1] for x in ids]
+            got = d.decode_batch(chunk)
+            want = [o.decode(c) for o, c in zip(od, chunk)]
+            assert got == want, f"{name} step {k}"
+        assert d.flush() == [o.flush() for o in od]
+        d.close()
+        v.close()

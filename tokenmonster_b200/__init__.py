@@ -8,6 +8,6 @@ Package layout (hot path only):
   dist.py      sharded multi-GPU host (one process per GPU)
 """
 from ._lib import TmgpuError, lib  # noqa: F401
-from .vocab import TokenizeResult, Vocab, load  # noqa: F401
+from .vocab import Decoder, TokenizeResult, Vocab, load  # noqa: F401
 
-__all__ = ["Vocab", "load", "TokenizeResult", "TmgpuError", "lib"]
+__all__ = ["Vocab", "Decoder", "load", "TokenizeResult", "TmgpuError", "lib"]

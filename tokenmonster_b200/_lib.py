@@ -59,6 +59,10 @@ PROTOTYPES = {
     "tmgpu_decode_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8,
                                      C.POINTER(C.POINTER(Bytes))]),
     "tmgpu_bytes_free": (None, [C.POINTER(Bytes)]),
+    "tmgpu_decoder_create": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "tmgpu_decoder_destroy": (None, [C.c_void_p]),
+    "tmgpu_decoder_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint8, C.POINTER(C.POINTER(Bytes))]),
+    "tmgpu_decoder_flush": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(Bytes))]),
     "tmgpu_workspace_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p)]),
     "tmgpu_workspace_destroy": (None, [C.c_void_p]),
     "tmgpu_tokenize_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8, C.c_int,

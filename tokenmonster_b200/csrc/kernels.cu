@@ -67,7 +67,8 @@ __device__ __forceinline__ uint32_t rev_length(const VocabDev& V, uint32_t id, i
 
 __global__ void __launch_bounds__(256) decode_size_kernel(VocabDev V, const uint8_t* __restrict__ tokens,
                                                           const int64_t* __restrict__ tok_off, uint32_t n, int enc,
-                                                          uint32_t* __restrict__ raw_len) {
+                                                          uint32_t* __restrict__ raw_len,
+                                                          const uint64_t* __restrict__ prefix_off) {
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
   for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n; s += warps) {
@@ -76,19 +77,26 @@ __global__ void __launch_bounds__(256) decode_size_kernel(VocabDev V, const uint
     for (uint64_t k = t0 + lane; k < t1; k += 32) sum += rev_length(V, load_id(tokens, k, enc), enc);
 #pragma unroll
     for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
-    if (lane == 0) raw_len[s] = sum;
+    if (lane == 0) raw_len[s] = sum + (prefix_off ? uint32_t(prefix_off[s + 1] - prefix_off[s]) : 0u);
   }
 }
 
 __global__ void __launch_bounds__(256) decode_copy_kernel(VocabDev V, const uint8_t* __restrict__ tokens,
                                                           const int64_t* __restrict__ tok_off, uint32_t n, int enc,
                                                           const uint64_t* __restrict__ raw_off,
-                                                          uint8_t* __restrict__ out) {
+                                                          uint8_t* __restrict__ out,
+                                                          const uint64_t* __restrict__ prefix_off,
+                                                          const uint8_t* __restrict__ prefix) {
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
   for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n; s += warps) {
     const uint64_t t0 = uint64_t(tok_off[s]), t1 = uint64_t(tok_off[s + 1]);
     uint64_t at = raw_off[s];
+    if (prefix_off) {  // streaming decoder: the stream's remainder comes first (go:717)
+      const uint64_t p0 = prefix_off[s], pl = prefix_off[s + 1] - p0;
+      for (uint64_t k = lane; k < pl; k += 32) out[at + k] = prefix[p0 + k];
+      at += pl;
+    }
     for (uint64_t kb = t0; kb < t1; kb += 32) {
       const uint64_t k = kb + lane;
       uint32_t id = 0, l = 0;
@@ -120,12 +128,16 @@ __global__ void __launch_bounds__(256) decode_copy_kernel(VocabDev V, const uint
 __global__ void __launch_bounds__(256) capcode_decode_kernel(const uint8_t* __restrict__ src,
                                                              const uint64_t* __restrict__ raw_off, uint32_t n,
                                                              uint8_t* __restrict__ dst,
-                                                             uint32_t* __restrict__ out_len) {
+                                                             uint32_t* __restrict__ out_len,
+                                                             const uint32_t* __restrict__ len_in,
+                                                             uint8_t* __restrict__ state) {
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
     const uint8_t* in = src + raw_off[s];
     uint8_t* out = dst + raw_off[s];
-    const uint32_t len = uint32_t(raw_off[s + 1] - raw_off[s]);
-    bool in_word = false, in_char = false, del = false, ignore = false;
+    const uint32_t len = len_in ? len_in[s] : uint32_t(raw_off[s + 1] - raw_off[s]);
+    // streaming decoder: the four flags of capcode.Decoder persist across calls (js:1009-1012)
+    const uint32_t st0 = state ? state[s] : 0u;
+    bool in_word = st0 & 1u, in_char = st0 & 2u, del = st0 & 4u, ignore = st0 & 8u;
     uint32_t o = 0;
     for (uint32_t i = 0; i < len; i++) {
       uint32_t r = in[i];
@@ -162,6 +174,71 @@ __global__ void __launch_bounds__(256) capcode_decode_kernel(const uint8_t* __re
       ignore = false;
     }
     out_len[s] = o;
+    if (state) state[s] = uint8_t((in_word ? 1u : 0u) | (in_char ? 2u : 0u) | (del ? 4u : 0u) | (ignore ? 8u : 0u));
+  }
+}
+
+// Streaming decoder: how many bytes at the end of each stream's text are an incomplete UTF-8 /
+// UTF-16 sequence and must wait for the next call (go/tokenmonster.go:149-219, including the
+// quirk that a truncated UTF-8 sequence reports the MISSING byte count).
+__global__ void __launch_bounds__(256) stream_tail_kernel(const uint8_t* __restrict__ raw,
+                                                          const uint64_t* __restrict__ raw_off, uint32_t n,
+                                                          int charset, uint32_t* __restrict__ keep_len,
+                                                          uint32_t* __restrict__ rem_len) {
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    const uint8_t* b = raw + raw_off[s];
+    const long long len = (long long)(raw_off[s + 1] - raw_off[s]);
+    long long inc = 0;
+    if (len > 0 && charset == 1) {
+      if (b[len - 1] & 0x80) {
+        long long st = len - 1;
+        while (st >= 0 && (b[st] & 0xC0) == 0x80) st--;
+        if (st < 0) {
+          inc = len;
+        } else {
+          const uint32_t f = b[st];
+          int need;
+          if ((f & 0x80) == 0) need = 1;
+          else if ((f & 0xE0) == 0xC0) need = 2;
+          else if ((f & 0xF0) == 0xE0) need = 3;
+          else if ((f & 0xF8) == 0xF0) need = 4;
+          else need = 0;
+          const long long have = len - st;
+          if (need == 0) inc = have;
+          else if (have < need) inc = need - have;
+          else if (need == 1 && (f & 0xC0) != 0) inc = len;
+        }
+      }
+    } else if (len > 0 && charset == 2) {
+      if (len & 1) {
+        inc = 1;
+        if (len >= 3) {
+          const uint32_t u = b[len - 3] | (uint32_t(b[len - 2]) << 8);
+          if (u >= 0xD800 && u <= 0xDBFF) inc = 3;
+        }
+      } else {
+        const uint32_t last = b[len - 2] | (uint32_t(b[len - 1]) << 8);
+        const uint32_t first = b[0] | (uint32_t(b[1]) << 8);
+        if (last >= 0xD800 && last <= 0xDBFF) inc = 2;
+        else if (first >= 0xDC00 && first <= 0xDFFF) inc = 2;
+      }
+    }
+    if (inc > len) inc = len;
+    keep_len[s] = uint32_t(len - inc);
+    rem_len[s] = uint32_t(inc);
+  }
+}
+
+// copy each stream's incomplete tail into the new remainder buffer
+__global__ void __launch_bounds__(256) copy_tail_kernel(const uint8_t* __restrict__ raw,
+                                                        const uint64_t* __restrict__ raw_off,
+                                                        const uint32_t* __restrict__ keep_len,
+                                                        const uint64_t* __restrict__ rem_off, uint32_t n,
+                                                        uint8_t* __restrict__ rem) {
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    const uint8_t* a = raw + raw_off[s] + keep_len[s];
+    const uint64_t l = rem_off[s + 1] - rem_off[s];
+    for (uint64_t k = 0; k < l; k++) rem[rem_off[s] + k] = a[k];
   }
 }
 
@@ -284,20 +361,34 @@ cudaError_t launch_pack(const uint32_t* slab, const int64_t* off, uint32_t slab_
 }
 
 cudaError_t launch_decode_size(const VocabDev& v, const uint8_t* tokens, const int64_t* tok_off, uint32_t n, int enc,
-                               uint32_t* raw_len, int sms, cudaStream_t st) {
-  decode_size_kernel<<<sms * 8, 256, 0, st>>>(v, tokens, tok_off, n, enc, raw_len);
+                               uint32_t* raw_len, int sms, cudaStream_t st, const uint64_t* prefix_off) {
+  decode_size_kernel<<<sms * 8, 256, 0, st>>>(v, tokens, tok_off, n, enc, raw_len, prefix_off);
   return cudaGetLastError();
 }
 
 cudaError_t launch_decode_copy(const VocabDev& v, const uint8_t* tokens, const int64_t* tok_off, uint32_t n, int enc,
-                               const uint64_t* raw_off, uint8_t* out, int sms, cudaStream_t st) {
-  decode_copy_kernel<<<sms * 8, 256, 0, st>>>(v, tokens, tok_off, n, enc, raw_off, out);
+                               const uint64_t* raw_off, uint8_t* out, int sms, cudaStream_t st,
+                               const uint64_t* prefix_off, const uint8_t* prefix) {
+  decode_copy_kernel<<<sms * 8, 256, 0, st>>>(v, tokens, tok_off, n, enc, raw_off, out, prefix_off, prefix);
   return cudaGetLastError();
 }
 
 cudaError_t launch_capcode_decode(const uint8_t* src, const uint64_t* raw_off, uint32_t n, uint8_t* dst,
-                                  uint32_t* out_len, int sms, cudaStream_t st) {
-  capcode_decode_kernel<<<sms * 8, 256, 0, st>>>(src, raw_off, n, dst, out_len);
+                                  uint32_t* out_len, int sms, cudaStream_t st, const uint32_t* len_in,
+                                  uint8_t* state) {
+  capcode_decode_kernel<<<sms * 8, 256, 0, st>>>(src, raw_off, n, dst, out_len, len_in, state);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stream_tail(const uint8_t* raw, const uint64_t* raw_off, uint32_t n, int charset,
+                               uint32_t* keep_len, uint32_t* rem_len, int sms, cudaStream_t st) {
+  stream_tail_kernel<<<sms * 4, 256, 0, st>>>(raw, raw_off, n, charset, keep_len, rem_len);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_copy_tail(const uint8_t* raw, const uint64_t* raw_off, const uint32_t* keep_len,
+                             const uint64_t* rem_off, uint32_t n, uint8_t* rem, int sms, cudaStream_t st) {
+  copy_tail_kernel<<<sms * 4, 256, 0, st>>>(raw, raw_off, keep_len, rem_off, n, rem);
   return cudaGetLastError();
 }
 

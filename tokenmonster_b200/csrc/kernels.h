@@ -34,11 +34,17 @@ cudaError_t launch_pack(const uint32_t* slab, const int64_t* off, uint32_t slab_
                         const uint32_t* counts, const uint64_t* tok_off, uint8_t* out, uint32_t n, int enc,
                         int sms, cudaStream_t st);
 cudaError_t launch_decode_size(const VocabDev& v, const uint8_t* tokens, const int64_t* tok_off, uint32_t n, int enc,
-                               uint32_t* raw_len, int sms, cudaStream_t st);
+                               uint32_t* raw_len, int sms, cudaStream_t st, const uint64_t* prefix_off = nullptr);
 cudaError_t launch_decode_copy(const VocabDev& v, const uint8_t* tokens, const int64_t* tok_off, uint32_t n, int enc,
-                               const uint64_t* raw_off, uint8_t* out, int sms, cudaStream_t st);
+                               const uint64_t* raw_off, uint8_t* out, int sms, cudaStream_t st,
+                               const uint64_t* prefix_off = nullptr, const uint8_t* prefix = nullptr);
 cudaError_t launch_capcode_decode(const uint8_t* src, const uint64_t* raw_off, uint32_t n, uint8_t* dst,
-                                  uint32_t* out_len, int sms, cudaStream_t st);
+                                  uint32_t* out_len, int sms, cudaStream_t st, const uint32_t* len_in = nullptr,
+                                  uint8_t* state = nullptr);
+cudaError_t launch_stream_tail(const uint8_t* raw, const uint64_t* raw_off, uint32_t n, int charset,
+                               uint32_t* keep_len, uint32_t* rem_len, int sms, cudaStream_t st);
+cudaError_t launch_copy_tail(const uint8_t* raw, const uint64_t* raw_off, const uint32_t* keep_len,
+                             const uint64_t* rem_off, uint32_t n, uint8_t* rem, int sms, cudaStream_t st);
 cudaError_t launch_compact_bytes(const uint8_t* src, const uint64_t* src_off, const uint32_t* len,
                                  const uint64_t* dst_off, uint32_t n, uint8_t* dst, int sms, cudaStream_t st);
 

@@ -255,6 +255,10 @@ class Vocab:
             outs = [o.decode("utf-8", "replace") for o in outs]
         return outs[0] if single else outs
 
+    def decoder(self, n_streams: int = 1) -> "Decoder":
+        """python/tokenmonster.py:273 Vocab.decoder() / go NewDecoder :450 -- for n parallel streams."""
+        return Decoder(self, n_streams)
+
     # ---- (de)serialization helpers (py:916-943, go Deserialize :749-784) ----------------
     def deserialize_tokens(self, binary: bytes, enc_len: int = 0) -> np.ndarray:
         enc = enc_len or self.default_encoding_length()
@@ -271,6 +275,64 @@ class Vocab:
         idx = C.c_uint32()
         l = lib().tmgpu_selftest_trie_lookup(self._h, window, len(window), int(spaced), C.byref(idx))
         return (int(idx.value), l) if l else (None, 0)
+
+
+class Decoder:
+    """A batch of independent streaming decoders (go/tokenmonster.go:57-61, :450-740).
+
+    Each stream keeps, on the device, the incomplete UTF-8/16 tail of what it has decoded so far and
+    the capcode decoder flags, exactly like one reference `Decoder` object.  With n_streams == 1 the
+    methods take / return a single sequence, like python/tokenmonster.py:136."""
+
+    def __init__(self, vocab: Vocab, n_streams: int = 1):
+        self.vocab = vocab
+        self.n = n_streams
+        self._h = C.c_void_p()
+        check(lib().tmgpu_decoder_create(vocab._h, n_streams, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().tmgpu_decoder_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _take(self, res):
+        try:
+            b = res.contents
+            nb = int(b.n_bytes)
+            data = np.ctypeslib.as_array(b.bytes, shape=(nb,)).copy() if nb else np.zeros(0, np.uint8)
+            off = np.ctypeslib.as_array(b.off, shape=(self.n + 1,)).copy()
+        finally:
+            lib().tmgpu_bytes_free(res)
+        return [data[int(off[s]):int(off[s + 1])].tobytes() for s in range(self.n)]
+
+    def decode_batch(self, chunks) -> List[bytes]:
+        """chunks[s] = the next ids of stream s (may be empty)."""
+        if len(chunks) != self.n:
+            raise ValueError("one chunk per stream")
+        arrs = [np.asarray(c, dtype=np.uint32).reshape(-1) for c in chunks]
+        off = np.zeros(self.n + 1, np.uint64)
+        off[1:] = np.cumsum([len(a) for a in arrs], dtype=np.uint64)
+        flat = np.ascontiguousarray(np.concatenate(arrs) if arrs else np.zeros(0, np.uint32), dtype=np.uint32)
+        res = C.POINTER(_lib.Bytes)()
+        check(lib().tmgpu_decoder_decode(self._h, flat.ctypes.data if flat.size else None, off.ctypes.data, 4,
+                                         C.byref(res)))
+        return self._take(res)
+
+    def decode(self, tokens):
+        out = self.decode_batch([tokens] if self.n == 1 else tokens)
+        return out[0] if self.n == 1 else out
+
+    def flush(self):
+        res = C.POINTER(_lib.Bytes)()
+        check(lib().tmgpu_decoder_flush(self._h, C.byref(res)))
+        out = self._take(res)
+        return out[0] if self.n == 1 else out
 
 
 def load(path: str, device: int = 0) -> Vocab:
