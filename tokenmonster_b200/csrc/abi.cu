@@ -46,7 +46,11 @@ struct tmgpu_vocab {
   int64_t* h_off = nullptr;       // pinned
   size_t h_off_cap = 0;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t d2h_stream = nullptr;
   cudaEvent_t chunk_ev[32] = {};
+  cudaEvent_t done_ev[32] = {};
+  uint64_t* d_run = nullptr;      // device: running id total + per-chunk {base, total}
+  uint64_t* h_info = nullptr;     // pinned mirror of the per-chunk {base, total}
   // pinned host blocks handed out as results and taken back by tmgpu_result_free / bytes_free
   struct PinnedBlock { void* p; size_t bytes; bool used; };
   std::vector<PinnedBlock> pinned;
@@ -188,11 +192,20 @@ extern "C" int tmgpu_vocab_create(const uint8_t* file_bytes, size_t n, int devic
     g_err = "cudaStreamCreate failed";
     return fail(TMGPU_E_CUDA);
   }
-  for (auto& e : v->chunk_ev) {
-    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&v->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_err = "cudaStreamCreate failed";
+    return fail(TMGPU_E_CUDA);
+  }
+  for (int k = 0; k < 32; k++) {
+    if (cudaEventCreateWithFlags(&v->chunk_ev[k], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&v->done_ev[k], cudaEventDisableTiming) != cudaSuccess) {
       g_err = "cudaEventCreate failed";
       return fail(TMGPU_E_CUDA);
     }
+  }
+  if (cudaMalloc(&v->d_run, 8 * 80) != cudaSuccess || cudaMallocHost(&v->h_info, 8 * 80) != cudaSuccess) {
+    g_err = "allocation of the chunk bookkeeping failed";
+    return fail(TMGPU_E_NOMEM);
   }
   VocabDev& d = v->dev;
   std::vector<uint8_t> image(1280);
@@ -244,8 +257,13 @@ extern "C" void tmgpu_vocab_destroy(tmgpu_vocab* v) {
   if (v->h_off) cudaFreeHost(v->h_off);
   if (v->stream) cudaStreamDestroy(v->stream);
   if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
+  if (v->d2h_stream) cudaStreamDestroy(v->d2h_stream);
   for (auto& e : v->chunk_ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : v->done_ev)
+    if (e) cudaEventDestroy(e);
+  if (v->d_run) cudaFree(v->d_run);
+  if (v->h_info) cudaFreeHost(v->h_info);
   for (auto& b : v->pinned) cudaFreeHost(b.p);
   delete v;
 }
@@ -580,12 +598,15 @@ static int stage_input(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off,
     v->h_off[i] = int64_t(off[i] - base);
   }
   *total = off[n] - base;
+  // watermark = 0, then the offsets; the compute stream may start once both are on the device
+  v->h_info[40] = 0;
+  CU(cudaMemcpyAsync(v->d_run + 4, v->h_info + 40, 8, cudaMemcpyHostToDevice, v->copy_stream));
   CU(cudaMemcpyAsync(v->d_off, v->h_off, (size_t(n) + 1) * 8, cudaMemcpyHostToDevice, v->copy_stream));
-  // chunks of ~equal bytes; few enough that every launch still fills the GPU
-  int want = int(*total / (24ull << 20)) + 1;
-  if (want > 8) want = 8;
-  const int by_strings = int(n / (uint32_t(v->sms) * 800u));  // keep every launch big enough for full CTAs
-  if (want > by_strings) want = by_strings < 1 ? 1 : by_strings;
+  CU(cudaEventRecord(v->chunk_ev[31], v->copy_stream));
+  // chunks of ~equal bytes; after each one the watermark (bytes landed) moves forward
+  int want = int(*total / (16ull << 20)) + 1;
+  if (want > 24) want = 24;
+  if (n < uint32_t(v->sms) * 800u) want = 1;   // small batches: one copy, then the plain path
   if (plan) plan->clear();
   uint32_t s0 = 0;
   const uint32_t pad = v->ws->slab_pad;
@@ -602,6 +623,8 @@ static int stage_input(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off,
     }
     const uint64_t b0 = uint64_t(v->h_off[s0]), b1 = uint64_t(v->h_off[s1]);
     if (b1 > b0) CU(cudaMemcpyAsync(v->d_in + b0, data + base + b0, b1 - b0, cudaMemcpyHostToDevice, v->copy_stream));
+    v->h_info[41 + c] = b1;
+    CU(cudaMemcpyAsync(v->d_run + 4, v->h_info + 41 + c, 8, cudaMemcpyHostToDevice, v->copy_stream));
     CU(cudaEventRecord(v->chunk_ev[c], v->copy_stream));
     if (plan) plan->push_back({s0, s1, b0 + uint64_t(pad) * s0, v->chunk_ev[c]});
     s0 = s1;
@@ -636,6 +659,40 @@ static int rerun_if_overflow(tmgpu_vocab* v, uint32_t n, uint8_t enc_len, std::v
   return TMGPU_OK;
 }
 
+// Large host batches: ONE launch of the tokenize kernel runs while the strings are still being
+// copied in.  stage_input() issues the H2D copies in chunks on the copy stream and, after each,
+// an 8-byte copy that advances a device "watermark" (bytes landed); a lane that pulls a string
+// beyond the watermark sleeps until its bytes are there.  No SM is needed to move the watermark
+// (it is a DMA write), so the persistent kernel can own the whole GPU.
+static int tokenize_streamed(tmgpu_vocab* v, uint32_t n, uint8_t enc_len, cudaEvent_t offsets_ready) {
+  tmgpu_workspace* ws = v->ws;
+  cudaStream_t st = v->stream;
+  ws->last_launches = 0;
+  CU(cudaMemsetAsync(ws->work_counter, 0, 4 * tmgpu_workspace::kMaxChunks, st));
+  CU(cudaMemsetAsync(ws->overflow, 0, 4, st));
+  CU(cudaMemsetAsync(ws->counts + n, 0, 4, st));
+  CU(cudaStreamWaitEvent(st, offsets_ready, 0));
+  TokenizeArgs a{};
+  a.v = v->dev;
+  a.data = v->d_in;
+  a.off = v->d_off;
+  a.n = n;
+  a.slab = ws->slab;
+  a.slab_pad = ws->slab_pad;
+  a.counts = ws->counts;
+  a.need = ws->need;
+  a.missing = ws->missing;
+  a.status = ws->status;
+  a.work_counter = ws->work_counter;
+  a.overflow = ws->overflow;
+  a.watermark = reinterpret_cast<const unsigned long long*>(v->d_run + 4);
+  CU(launch_tokenize(a, v->group, true, v->sms, st, nullptr));
+  CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, ws->counts, ws->tok_off, n + 1, st));
+  CU(launch_pack(ws->slab, v->d_off, ws->slab_pad, nullptr, ws->counts, ws->tok_off, ws->tokens, n, enc_len, v->sms, st));
+  ws->last_launches = 4;
+  return TMGPU_OK;
+}
+
 extern "C" int tmgpu_tokenize_batch(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off, uint32_t n,
                                     uint8_t enc_len, tmgpu_result** out) {
   if (!v || !off || !out || (!data && n && off[n] != off[0])) {
@@ -654,6 +711,10 @@ extern "C" int tmgpu_tokenize_batch(tmgpu_vocab* v, const uint8_t* data, const u
   std::vector<ChunkPlan> plan;
   if ((rc = stage_input(v, data, off, n, &total, &plan))) return rc;
   tmgpu_workspace* ws = v->ws;
+  if (plan.size() > 1 && v->host.max_len != 0) {
+    // streamed: the kernel is already chasing the copies (stage_input armed the watermark)
+    if ((rc = tokenize_streamed(v, n, enc_len, v->chunk_ev[31]))) return rc;
+  } else
   if ((rc = tokenize_on_stream(ws, v->d_in, v->d_off, n, enc_len, 0, v->stream, nullptr, ws->slab, ws->tokens, &plan)))
     return rc;
   std::vector<void*> temp;

@@ -46,6 +46,22 @@ __global__ void __launch_bounds__(256) pack_tokens_kernel(const uint32_t* __rest
   }
 }
 
+// chunked host path: turn a chunk's local offsets into global ones, then advance the running total
+__global__ void __launch_bounds__(256) finish_chunk_kernel(const uint64_t* __restrict__ loc_off, uint32_t n_c,
+                                                           const uint64_t* __restrict__ run_total,
+                                                           uint64_t* __restrict__ tok_off) {
+  const uint64_t base = *run_total;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k <= n_c; k += gridDim.x * blockDim.x)
+    tok_off[k] = base + loc_off[k];
+}
+
+__global__ void advance_total_kernel(const uint64_t* __restrict__ chunk_total, uint64_t* __restrict__ run_total,
+                                     uint64_t* __restrict__ info) {
+  info[0] = *run_total;
+  info[1] = *chunk_total;
+  *run_total += *chunk_total;
+}
+
 // ------------------------------------------------------------------------------------------
 // decode
 // ------------------------------------------------------------------------------------------
@@ -357,6 +373,13 @@ cudaError_t launch_pack(const uint32_t* slab, const int64_t* off, uint32_t slab_
   if (enc == 2) pack_tokens_kernel<2><<<grid, 256, 0, st>>>(slab, off, slab_pad, slab_off, counts, tok_off, out, n);
   else if (enc == 3) pack_tokens_kernel<3><<<grid, 256, 0, st>>>(slab, off, slab_pad, slab_off, counts, tok_off, out, n);
   else pack_tokens_kernel<4><<<grid, 256, 0, st>>>(slab, off, slab_pad, slab_off, counts, tok_off, out, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_finish_chunk(const uint64_t* loc_off, uint32_t n_c, uint64_t* run_total, uint64_t* tok_off,
+                                uint64_t* info, int sms, cudaStream_t st) {
+  finish_chunk_kernel<<<sms * 2, 256, 0, st>>>(loc_off, n_c, run_total, tok_off);
+  advance_total_kernel<<<1, 1, 0, st>>>(loc_off + n_c, run_total, info);
   return cudaGetLastError();
 }
 

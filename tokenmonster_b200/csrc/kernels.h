@@ -23,6 +23,8 @@ struct TokenizeArgs {
   uint8_t* status;           // n
   uint32_t* work_counter;    // zeroed before launch
   uint32_t* overflow;        // set to 1 if any string exceeded its slab capacity
+  const unsigned long long* watermark;  // optional: input bytes that have landed in `data` so far (host path
+                             // streams the batch in while the kernel runs); NULL = everything is there
 };
 
 size_t scan_temp_bytes(uint32_t n_items);
@@ -33,6 +35,8 @@ cudaError_t launch_tokenize(const TokenizeArgs& a, int group, bool store, int sm
 cudaError_t launch_pack(const uint32_t* slab, const int64_t* off, uint32_t slab_pad, const uint64_t* slab_off,
                         const uint32_t* counts, const uint64_t* tok_off, uint8_t* out, uint32_t n, int enc,
                         int sms, cudaStream_t st);
+cudaError_t launch_finish_chunk(const uint64_t* loc_off, uint32_t n_c, uint64_t* run_total, uint64_t* tok_off,
+                                uint64_t* info, int sms, cudaStream_t st);
 cudaError_t launch_decode_size(const VocabDev& v, const uint8_t* tokens, const int64_t* tok_off, uint32_t n, int enc,
                                uint32_t* raw_len, int sms, cudaStream_t st, const uint64_t* prefix_off = nullptr);
 cudaError_t launch_decode_copy(const VocabDev& v, const uint8_t* tokens, const int64_t* tok_off, uint32_t n, int enc,

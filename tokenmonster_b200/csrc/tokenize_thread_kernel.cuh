@@ -140,6 +140,10 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
       } else {
         const int64_t o0 = A.off[s];
         slen = int(A.off[s + 1] - o0);
+        if (A.watermark) {   // the batch is still streaming in: wait until this string has landed
+          const unsigned long long need_bytes = static_cast<unsigned long long>(o0 + slen);
+          while (*reinterpret_cast<const volatile unsigned long long*>(A.watermark) < need_bytes) __nanosleep(500);
+        }
         const uint8_t* g0 = A.data + o0;
         slab_base = A.slab_off ? A.slab_off[s] : uint64_t(o0 - A.off[0]) + uint64_t(A.slab_pad) * s;
         cap = A.slab_off ? uint32_t(A.slab_off[s + 1] - A.slab_off[s]) : uint32_t(slen) + A.slab_pad;
