@@ -83,3 +83,35 @@ def test_device_trie_equals_oracle_dictionary(built, name):
             assert gl == 0 or gl + 1 == wl
         else:
             assert (gi, gl + 1) == (wi, wl)
+
+
+def _build_cpp_smoke(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "cpp_smoke")
+    so_dir = os.path.join(ROOT, "tokenmonster_b200")
+    subprocess.run(["g++", "-std=c++20", "-O1", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp_smoke.cpp"), "-L" + so_dir, "-ltmgpu",
+                    "-Wl,-rpath," + so_dir, "-o", exe], check=True)
+    voc = str(tmp_path / "unit.vocab")
+    with open(voc, "wb") as f:
+        f.write(vocabgen.unit_cpp_vocab())
+    return exe, voc
+
+
+def test_cpp_mirror_header_compiles_and_refuses_without_gpu(built, tmp_path):
+    """include/tokenmonster_gpu.hpp (mirror of tokenmonster-cpp's hpp:52-112) links against the C ABI."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu variant")
+    exe, voc = _build_cpp_smoke(tmp_path)
+    r = subprocess.run([exe, voc], capture_output=True, text=True)
+    assert r.returncode == 0 and "no CPU path" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_runs_unit_cpp_assertions_on_gpu(built, tmp_path):
+    import subprocess
+    exe, voc = _build_cpp_smoke(tmp_path)
+    r = subprocess.run([exe, voc, "gpu"], capture_output=True, text=True)
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr

@@ -80,7 +80,7 @@ def test_reference_golden_vectors(built, name, group):
 
 
 @pytest.mark.parametrize("group", KERNELS)
-@pytest.mark.parametrize("name", ["c3", "c2", "c4", "c1"])
+@pytest.mark.parametrize("name", ["c3", "c2", "c4", "c1", "c5"])
 def test_seeded_batches_against_oracle(built, name, group):
     vb = configs.vocab_bytes(name)
     v, chk = make_vocab(vb, group), oracle.OracleVocab(vb, "port")
