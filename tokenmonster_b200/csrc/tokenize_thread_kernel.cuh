@@ -46,11 +46,15 @@ constexpr int kRingWords = kRingBytes / 4;
 template <int BLOCK>
 struct ThreadCfg {
   static constexpr int WARPS = BLOCK / 32;
-  static constexpr int RING_BYTES = WARPS * kRingWords * 32 * 4;   // interleaved rings
-  static constexpr int RING_BASE = kSmemRingBase;
-  static constexpr int POOL_BASE = RING_BASE + RING_BYTES;         // per warp: 96 tasks, 96 results, counter
-  static constexpr int POOL_WARP_BYTES = 96 * 8 + 96 * 4 + 16;
-  static constexpr int SMEM = POOL_BASE + WARPS * POOL_WARP_BYTES;
+  // one contiguous block per warp: interleaved rings, then the walk pool (96 tasks, 96 results,
+  // counter) -- every pointer of a warp is a constant offset from one base register
+  static constexpr int RING_WARP_BYTES = kRingWords * 32 * 4;
+  static constexpr int TASK_OFF = RING_WARP_BYTES;
+  static constexpr int RES_OFF = TASK_OFF + 96 * 8;
+  static constexpr int CTR_OFF = RES_OFF + 96 * 4;
+  static constexpr int WARP_BYTES = CTR_OFF + 16;
+  static constexpr int WARP_BASE = kSmemRingBase;
+  static constexpr int SMEM = WARP_BASE + WARPS * WARP_BYTES;
 };
 
 template <int BLOCK, int CAP, bool STORE>
@@ -68,11 +72,11 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
   const uint32_t* s_root = reinterpret_cast<const uint32_t*>(smem);
   const uint8_t* s_begin = smem + 1024;
   const int lane = threadIdx.x & 31;
-  uint32_t* ring = reinterpret_cast<uint32_t*>(smem + Cfg::RING_BASE) + (threadIdx.x >> 5) * (kRingWords * 32) + lane;
-  uint8_t* pool = smem + Cfg::POOL_BASE + (threadIdx.x >> 5) * Cfg::POOL_WARP_BYTES;
-  uint2* task = reinterpret_cast<uint2*>(pool);
-  uint32_t* res = reinterpret_cast<uint32_t*>(pool + 96 * 8);
-  int* next_task = reinterpret_cast<int*>(pool + 96 * 8 + 96 * 4);
+  uint8_t* wbase = smem + Cfg::WARP_BASE + (threadIdx.x >> 5) * Cfg::WARP_BYTES;
+  uint32_t* ring = reinterpret_cast<uint32_t*>(wbase) + lane;          // word w of this lane: ring[(w & 31) * 32]
+  uint2* task = reinterpret_cast<uint2*>(wbase + Cfg::TASK_OFF);
+  uint32_t* res = reinterpret_cast<uint32_t*>(wbase + Cfg::RES_OFF);
+  int* next_task = reinterpret_cast<int*>(wbase + Cfg::CTR_OFF);
 
   const VocabDev& V = A.v;
   const int M = V.max_len;
@@ -184,8 +188,8 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
         if (!__any_sync(FULL, must)) break;
         const bool want = running && rc < total_c && filled + 4 <= i + (kRingBytes - 4);
         if (want) {
-          // keep >= 2 raw bytes in the window so the next character can be peeked
-          while (avail < 2 && rc + avail < total_c) {
+          // keep >= 5 raw bytes in the window: 4 for the fast path + 1 to peek at the next character
+          while (avail < 5 && rc + avail < total_c) {
             const int nwc = rc + avail;            // first coordinate not yet in the window
             {
               const int wc = nwc & ~3;
@@ -200,6 +204,35 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
               const int skip = nwc - wc;           // non-zero only for the first, unaligned word
               win |= uint64_t(wq >> (8 * skip)) << (8 * avail);
               avail += 4 - skip;
+            }
+          }
+          // fast path: four characters that are all lower-case letters or spaces, after a letter or a
+          // space, encode to themselves (js:969-974: no "D " is due; js:976-979: no capital follows
+          // inside; the space rule only needs the 5th character)
+          {
+            const uint32_t w4 = uint32_t(win);
+            const uint32_t low = (w4 + 0x1F1F1F1Fu) & ~(w4 + 0x05050505u);             // 'a'..'z'
+            const uint32_t y = w4 ^ 0x20202020u;
+            const uint32_t spc = ~(((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y);              // == ' '
+            const uint32_t c5 = uint32_t(win >> 32) & 0xFFu;
+            const bool prev_ok = sp1 || cl1 == CL_U || cl1 == CL_L;
+            const bool tail_ok = ((w4 >> 24) != ' ') || (rc + 4 >= total_c) || !(c5 - 'A' < 26u);
+            if (prev_ok && tail_ok && rc + 4 <= total_c && (w4 & 0x80808080u) == 0 &&
+                ((low | spc) & 0x80808080u) == 0x80808080u) {
+              const uint32_t sh = (filled & 3) * 8;
+              const uint64_t acc = uint64_t(ow) | (uint64_t(w4) << sh);
+              ring[((filled >> 2) & (kRingWords - 1)) * 32] = uint32_t(acc);   // 4 bytes always complete a word
+              ow = uint32_t(acc >> 32);
+              filled += 4;
+              win >>= 32;
+              avail -= 4;
+              rc += 4;
+              const uint32_t b2 = (w4 >> 16) & 0xFFu, b3 = w4 >> 24;
+              in_word = false;
+              cl2 = (b2 == ' ') ? uint32_t(CL_O) : uint32_t(CL_L);
+              cl1 = (b3 == ' ') ? uint32_t(CL_O) : uint32_t(CL_L);
+              sp1 = (b3 == ' ');
+              continue;
             }
           }
           const uint32_t c = uint32_t(win) & 0xFFu;
