@@ -137,6 +137,35 @@ int tmgpu_decoder_decode(tmgpu_decoder* d, const uint8_t* tokens, const uint64_t
                          uint8_t enc_len, tmgpu_bytes** out);
 int tmgpu_decoder_flush(tmgpu_decoder* d, tmgpu_bytes** out);
 
+/* ---- server wire format: the payloads of tokenmonsterserver's jobs, taken and produced as-is ----
+ *      (training/tokenmonsterserver.go:189-209 protocol comment; python client py:341-552)
+ * Request payload of jobs 1, 2-4 and 20:  [u32 n] then n x ([u64 len][len bytes]), little endian.
+ * The request goes to the GPU verbatim (no host repack; the kernel skips the 8-byte headers) and
+ * the reply payload is framed on the device, so the server writes `payload` straight to stdout
+ * behind its 9-byte header {status_code, u64 len}.
+ *   tmgpu_wire_tokenize  job 1 (server:339-394): reply [u32 n] n x ([u64 bytes][ids]); ids are 2
+ *                        bytes each when the vocabulary has <= 65536 ids, else 4 (server:351-354,
+ *                        the width python's deserialize_tokens expects).  A string that fails
+ *                        normalization yields an empty entry; status_code is 13 only if string 0
+ *                        failed, like the server (:379-381), else 0.
+ *   tmgpu_wire_count     job 20 as python's tokenize_count sends it (py:485-552): reply [u32 n]
+ *                        n x [u64 count].  (The reference server has no case 20 -- SURVEY quirk Q3.)
+ *   tmgpu_wire_decode    jobs 2/3/4 (server:396-446), enc_len = the job number: entries hold
+ *                        serialized ids; reply [u32 n] n x ([u64 len][decoded bytes]).  Every
+ *                        entry is decoded from its own body (the reference's multi-entry branch
+ *                        passes the wrong slice, server:429). */
+typedef struct tmgpu_wire_reply {
+  uint8_t status_code; /* first byte of the server's response header */
+  uint64_t len;        /* payload bytes */
+  uint8_t* payload;    /* pinned host memory owned by the library */
+  void* priv;
+} tmgpu_wire_reply;
+int tmgpu_wire_tokenize(tmgpu_vocab* v, const uint8_t* payload, uint64_t len, tmgpu_wire_reply** out);
+int tmgpu_wire_count(tmgpu_vocab* v, const uint8_t* payload, uint64_t len, tmgpu_wire_reply** out);
+int tmgpu_wire_decode(tmgpu_vocab* v, uint8_t enc_len, const uint8_t* payload, uint64_t len,
+                      tmgpu_wire_reply** out);
+void tmgpu_wire_reply_free(tmgpu_wire_reply* r);
+
 /* ---- device-resident path (inputs already in HBM; used for the kernel roofline figure and
  *      by the sharded multi-GPU host) -------------------------------------------------------
  * A workspace owns the device output buffers for batches up to (max_strings, max_bytes).

@@ -40,6 +40,27 @@ def test_host_only_vocab_and_no_cpu_path(built):
         assert e.value.code == 2 and "no CPU path" in str(e.value)
 
 
+def test_wire_payload_validation_needs_no_gpu(built):
+    """Truncated server payloads are refused before any device work (the server trusts its client,
+    training/tokenmonsterserver.go:355-376; a library cannot)."""
+    import struct
+    from tokenmonster_b200 import TmgpuError, Vocab
+    with open(os.path.join(GOLD, "gpt2.vocab"), "rb") as f:
+        v = Vocab(f.read(), device=-1)
+    good = struct.pack("<I", 1) + struct.pack("<Q", 5) + b"hello"
+    for bad in (b"", b"\x01\x00", good[:9], good[:-1], struct.pack("<I", 2) + good[4:]):
+        for call in (v.wire_tokenize, v.wire_count, lambda p: v.wire_decode(p, 2)):
+            with pytest.raises(TmgpuError) as e:
+                call(bad)
+            assert e.value.code == 1
+    with pytest.raises(TmgpuError) as e:
+        v.wire_decode(good, 5)
+    assert e.value.code == 1
+    with pytest.raises(TmgpuError) as e:
+        v.wire_tokenize(good)          # well-formed, but this vocabulary has no device
+    assert e.value.code == 2
+
+
 def test_vocab_error_codes(built):
     from tokenmonster_b200 import TmgpuError, Vocab
     with open(os.path.join(GOLD, "small_nocap.vocab"), "rb") as f:

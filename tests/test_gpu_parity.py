@@ -229,3 +229,104 @@ def test_streaming_decoder_splits_utf8_and_capcode_state(built):
         assert d.flush() == [o.flush() for o in od]
         d.close()
         v.close()
+
+
+# ---- server wire format (training/tokenmonsterserver.go jobs 1, 2-4; python client job 20) ----------
+def wire_request(items):
+    import struct
+    return struct.pack("<I", len(items)) + b"".join(struct.pack("<Q", len(x)) + x for x in items)
+
+
+def wire_entries(reply):
+    import struct
+    n = struct.unpack_from("<I", reply, 0)[0]
+    at, out = 4, []
+    for _ in range(n):
+        l = struct.unpack_from("<Q", reply, at)[0]
+        at += 8
+        out.append(reply[at:at + l])
+        at += l
+    assert at == len(reply)
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c2", "c3", "gpt2"])
+def test_wire_tokenize_count_decode_against_oracle(built, name):
+    import struct
+    vb = gold_vocab(name) if name == "gpt2" else configs.vocab_bytes(name)
+    v, chk = make_vocab(vb, "1"), oracle.OracleVocab(vb, "port")
+    base = corpus.base_text(21, 1 << 18, 0.4)
+    d, o = corpus.make_batch(base, 700, 0, 500, 4, "cpu")
+    d, o = d.numpy(), o.numpy()
+    texts = [d[int(o[s]):int(o[s + 1])].tobytes() for s in range(len(o) - 1)] + [b"", b"x", b""]
+    enc = 4 if len(v) > 65536 else 2
+    st, reply = v.wire_tokenize(wire_request(texts))
+    got = wire_entries(reply)
+    assert st == 0 and len(got) == len(texts)
+    dt = np.uint16 if enc == 2 else np.uint32
+    for s, t in enumerate(texts):
+        want, _ = chk.tokenize(t)
+        assert np.array_equal(np.frombuffer(got[s], dt).astype(np.uint32), want), f"entry {s}"
+    st, creply = v.wire_count(wire_request(texts))
+    assert st == 0 and struct.unpack_from("<I", creply, 0)[0] == len(texts) and len(creply) == 4 + 8 * len(texts)
+    for s, t in enumerate(texts):
+        assert struct.unpack_from("<Q", creply, 4 + 8 * s)[0] == chk.tokenize(t, mode=1)[0]
+    # decode: the reply of job 1 is, entry for entry, a valid request of job `enc`
+    st, dreply = v.wire_decode(reply, enc)
+    back = wire_entries(dreply)
+    for s, t in enumerate(texts):
+        want, _ = chk.tokenize(t)
+        assert back[s] == chk.decode(want), f"decode entry {s}"
+    # 3-byte ids and a dangling byte (whole ids only, go:845)
+    ids = [chk.tokenize(t)[0] for t in texts[:50]]
+    e3 = [b"".join(int(i).to_bytes(3, "little") for i in a) + b"\x07" for a in ids]
+    st, d3 = v.wire_decode(wire_request(e3), 3)
+    assert [chk.decode(a) for a in ids] == wire_entries(d3)
+    v.close()
+
+
+@pytest.mark.gpu
+def test_wire_tokenize_streamed_batch_equals_flat_batch(built):
+    """A payload big enough for the chunked upload + watermark path (>16 MB, >118k strings)."""
+    vb = configs.vocab_bytes("c2")
+    v = make_vocab(vb, "1")
+    base = corpus.base_text(33, 1 << 20, 0.4)
+    d, o = corpus.make_batch(base, 160000, 0, 300, 11, "cpu")
+    d, o = d.numpy(), o.numpy().astype(np.uint64)
+    flat_res = v.tokenize_batch(d, o, 2)
+    lens = np.diff(o).astype("<u8")
+    # build the request with numpy: [u32 n] then [u64 len][bytes] per string
+    pos = 4 + 8 * np.arange(1, len(lens) + 1, dtype=np.uint64) + o[:-1]
+    req = np.zeros(4 + 8 * len(lens) + len(d), np.uint8)
+    req[:4] = np.frombuffer(np.uint32(len(lens)).tobytes(), np.uint8)
+    hdr = (pos - 8)[:, None] + np.arange(8, dtype=np.uint64)[None, :]
+    req[hdr.reshape(-1)] = lens.view(np.uint8)
+    idx = np.repeat(pos - o[:-1], lens.astype(np.int64)) + np.arange(len(d), dtype=np.uint64)
+    req[idx] = d
+    st, reply = v.wire_tokenize(req)
+    assert st == 0
+    rep = np.frombuffer(reply, np.uint8)
+    tl = np.diff(flat_res.tok_off).astype(np.uint64) * 2
+    assert len(rep) == 4 + 8 * len(tl) + int(tl.sum())
+    tpos = 4 + 8 * np.arange(1, len(tl) + 1, dtype=np.uint64) + np.concatenate([[0], np.cumsum(tl)[:-1]]).astype(np.uint64)
+    thdr = (tpos - 8)[:, None] + np.arange(8, dtype=np.uint64)[None, :]
+    assert np.array_equal(rep[thdr.reshape(-1)], tl.astype("<u8").view(np.uint8))
+    tidx = np.repeat(tpos, tl.astype(np.int64)) + (np.arange(int(tl.sum()), dtype=np.uint64) -
+                                                     np.repeat(np.cumsum(tl) - tl, tl.astype(np.int64)))
+    assert np.array_equal(rep[tidx], flat_res.raw)
+    v.close()
+
+
+@pytest.mark.gpu
+def test_wire_status_code_follows_entry_zero(built):
+    vb = configs.vocab_bytes("c2")
+    v = make_vocab(vb, "1")
+    st, reply = v.wire_tokenize(wire_request(["café".encode(), b"plain"]))
+    got = wire_entries(reply)
+    assert st == 13 and got[0] == b"" and len(got[1]) > 0          # server:379-381
+    st, reply = v.wire_tokenize(wire_request([b"plain", "café".encode()]))
+    assert st == 0 and wire_entries(reply)[1] == b""
+    st, reply = v.wire_tokenize(wire_request([]))
+    assert st == 0 and reply == b"\x00\x00\x00\x00"
+    v.close()

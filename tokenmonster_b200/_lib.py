@@ -37,6 +37,10 @@ class Bytes(C.Structure):
     _fields_ = [("n", C.c_uint32), ("n_bytes", C.c_uint64), ("bytes", u8p), ("off", u64p), ("priv", C.c_void_p)]
 
 
+class WireReply(C.Structure):
+    _fields_ = [("status_code", C.c_uint8), ("len", C.c_uint64), ("payload", u8p), ("priv", C.c_void_p)]
+
+
 class DeviceView(C.Structure):
     _fields_ = [("tokens", C.c_void_p), ("tok_off", C.c_void_p), ("missing", C.c_void_p), ("status", C.c_void_p),
                 ("n_tokens", C.c_void_p), ("counts", C.c_void_p)]
@@ -63,6 +67,11 @@ PROTOTYPES = {
     "tmgpu_decoder_destroy": (None, [C.c_void_p]),
     "tmgpu_decoder_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint8, C.POINTER(C.POINTER(Bytes))]),
     "tmgpu_decoder_flush": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(Bytes))]),
+    "tmgpu_wire_tokenize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.POINTER(WireReply))]),
+    "tmgpu_wire_count": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.POINTER(WireReply))]),
+    "tmgpu_wire_decode": (C.c_int, [C.c_void_p, C.c_uint8, C.c_void_p, C.c_uint64,
+                                    C.POINTER(C.POINTER(WireReply))]),
+    "tmgpu_wire_reply_free": (None, [C.POINTER(WireReply)]),
     "tmgpu_workspace_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p)]),
     "tmgpu_workspace_destroy": (None, [C.c_void_p]),
     "tmgpu_tokenize_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8, C.c_int,

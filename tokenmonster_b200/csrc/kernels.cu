@@ -46,20 +46,23 @@ __global__ void __launch_bounds__(256) pack_tokens_kernel(const uint32_t* __rest
   }
 }
 
-// chunked host path: turn a chunk's local offsets into global ones, then advance the running total
-__global__ void __launch_bounds__(256) finish_chunk_kernel(const uint64_t* __restrict__ loc_off, uint32_t n_c,
-                                                           const uint64_t* __restrict__ run_total,
-                                                           uint64_t* __restrict__ tok_off) {
-  const uint64_t base = *run_total;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k <= n_c; k += gridDim.x * blockDim.x)
-    tok_off[k] = base + loc_off[k];
-}
-
-__global__ void advance_total_kernel(const uint64_t* __restrict__ chunk_total, uint64_t* __restrict__ run_total,
-                                     uint64_t* __restrict__ info) {
-  info[0] = *run_total;
-  info[1] = *chunk_total;
-  *run_total += *chunk_total;
+// Reply framing of the server protocol (training/tokenmonsterserver.go:382-392, :435-445):
+// [u32 n] then, per string, [u64 byte length][payload].  One warp per string; `unit` is the
+// item size of src_off (the encoding length for ids, 1 for decoded bytes).
+__global__ void __launch_bounds__(256) wire_frame_kernel(const uint8_t* __restrict__ src,
+                                                         const uint64_t* __restrict__ src_off, uint32_t unit,
+                                                         uint32_t n, uint8_t* __restrict__ dst) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w0 == 0 && lane < 4) dst[lane] = uint8_t(n >> (8 * lane));
+  for (uint32_t s = w0; s < n; s += warps) {
+    const uint64_t b0 = src_off[s] * unit, len = (src_off[s + 1] - src_off[s]) * unit;
+    uint8_t* d = dst + 4 + 8ull * (s + 1) + b0;
+    if (lane < 8) d[int(lane) - 8] = uint8_t(len >> (8 * lane));
+    const uint8_t* a = src + b0;
+    for (uint64_t k = lane; k < len; k += 32) d[k] = a[k];
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -376,10 +379,9 @@ cudaError_t launch_pack(const uint32_t* slab, const int64_t* off, uint32_t slab_
   return cudaGetLastError();
 }
 
-cudaError_t launch_finish_chunk(const uint64_t* loc_off, uint32_t n_c, uint64_t* run_total, uint64_t* tok_off,
-                                uint64_t* info, int sms, cudaStream_t st) {
-  finish_chunk_kernel<<<sms * 2, 256, 0, st>>>(loc_off, n_c, run_total, tok_off);
-  advance_total_kernel<<<1, 1, 0, st>>>(loc_off + n_c, run_total, info);
+cudaError_t launch_wire_frame(const uint8_t* src, const uint64_t* src_off, uint32_t unit, uint32_t n, uint8_t* dst,
+                              int sms, cudaStream_t st) {
+  wire_frame_kernel<<<sms * 8, 256, 0, st>>>(src, src_off, unit, n, dst);
   return cudaGetLastError();
 }
 

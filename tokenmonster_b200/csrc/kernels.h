@@ -13,6 +13,8 @@ struct TokenizeArgs {
   VocabDev v;
   const uint8_t* data;       // all strings back to back (16-byte aligned base)
   const int64_t* off;        // n + 1 byte offsets
+  const int64_t* ends;       // optional n end offsets when strings are not back to back (the server's
+                             // wire payload keeps an 8-byte length header in front of each string)
   uint32_t n;
   uint32_t* slab;            // u32 ids; string s at (off[s]-off[0]) + slab_pad*s unless slab_off
   uint32_t slab_pad;         // extra capacity per string (ids)
@@ -35,8 +37,9 @@ cudaError_t launch_tokenize(const TokenizeArgs& a, int group, bool store, int sm
 cudaError_t launch_pack(const uint32_t* slab, const int64_t* off, uint32_t slab_pad, const uint64_t* slab_off,
                         const uint32_t* counts, const uint64_t* tok_off, uint8_t* out, uint32_t n, int enc,
                         int sms, cudaStream_t st);
-cudaError_t launch_finish_chunk(const uint64_t* loc_off, uint32_t n_c, uint64_t* run_total, uint64_t* tok_off,
-                                uint64_t* info, int sms, cudaStream_t st);
+// reply framing of the server protocol: [u32 n] then per string [u64 byte length][unit * items]
+cudaError_t launch_wire_frame(const uint8_t* src, const uint64_t* src_off, uint32_t unit, uint32_t n, uint8_t* dst,
+                              int sms, cudaStream_t st);
 cudaError_t launch_decode_size(const VocabDev& v, const uint8_t* tokens, const int64_t* tok_off, uint32_t n, int enc,
                                uint32_t* raw_len, int sms, cudaStream_t st, const uint64_t* prefix_off = nullptr);
 cudaError_t launch_decode_copy(const VocabDev& v, const uint8_t* tokens, const int64_t* tok_off, uint32_t n, int enc,

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kBlockThreads) tokenize_kernel(const TokenizeA
         no_more = true;
       } else {
         const int64_t o0 = A.off[s];
-        slen = int(A.off[s + 1] - o0);
+        slen = int((A.ends ? A.ends[s] : A.off[s + 1]) - o0);
         if (A.watermark) {   // the batch is still streaming in: wait until this string has landed
           const unsigned long long need_bytes = static_cast<unsigned long long>(o0 + slen);
           while (*reinterpret_cast<const volatile unsigned long long*>(A.watermark) < need_bytes) __nanosleep(500);

@@ -236,6 +236,33 @@ class Vocab:
             lib().tmgpu_bytes_free(res)
         return data, boff
 
+    # ---- server wire format ------------------------------------------------------------
+    def _wire(self, fn, payload, *lead):
+        buf = np.frombuffer(payload, dtype=np.uint8) if not isinstance(payload, np.ndarray) else payload
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        res = C.POINTER(_lib.WireReply)()
+        check(fn(self._h, *lead, buf.ctypes.data if buf.size else None, buf.size, C.byref(res)))
+        try:
+            r = res.contents
+            n = int(r.len)
+            body = np.ctypeslib.as_array(r.payload, shape=(n,)).tobytes() if n else b""
+            return int(r.status_code), body
+        finally:
+            lib().tmgpu_wire_reply_free(res)
+
+    def wire_tokenize(self, payload):
+        """Job 1 of tokenmonsterserver (training/tokenmonsterserver.go:339-394): the request payload
+        python's Vocab.tokenize builds (py:410-483) -> (status_code, reply payload)."""
+        return self._wire(lib().tmgpu_wire_tokenize, payload)
+
+    def wire_count(self, payload):
+        """Job 20 as python's tokenize_count sends it (py:485-552) -> (status_code, reply payload)."""
+        return self._wire(lib().tmgpu_wire_count, payload)
+
+    def wire_decode(self, payload, enc_len: int):
+        """Jobs 2/3/4 (server:396-446; py:341-408) -> (status_code, reply payload)."""
+        return self._wire(lib().tmgpu_wire_decode, payload, enc_len)
+
     def decode(self, tokens, as_bytes: bool = True):
         """python/tokenmonster.py:341 -- ids -> text; a list of id lists -> list of texts."""
         def is_seq_of_seq(x):
