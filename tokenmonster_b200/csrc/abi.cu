@@ -14,6 +14,8 @@
 
 #include "../../include/tmgpu.h"
 #include "kernels.h"
+#include "unicode_dev.h"
+#include "unicode_tables.h"
 #include "vocab_tables.h"
 
 using namespace tmgpu;
@@ -35,6 +37,8 @@ struct tmgpu_vocab {
   int sms = 0;
   int group = 1;    // 1 = lane-per-string kernel (default); 4/8/16/32 = lanes-over-branches kernel
   VocabDev dev{};
+  bool unicode = false;           // non-ASCII strings go through the device normalizer (else status 13)
+  UnicodeDev uni{};
   std::vector<void*> allocs;
   cudaStream_t stream = nullptr;
   std::mutex mu;
@@ -74,6 +78,14 @@ struct tmgpu_workspace {
   uint32_t* overflow = nullptr;
   void* scan_temp = nullptr;
   size_t scan_bytes = 0;
+  // device normalizer (non-ASCII strings): work list, placement, scratch text
+  uint32_t* uni_list = nullptr;          // n
+  int64_t* uni_begin = nullptr;          // n
+  int64_t* uni_end = nullptr;            // n
+  unsigned long long* uni_ctr = nullptr; // {strings, scratch bytes}
+  uint8_t* uni_text = nullptr;
+  uint64_t uni_text_cap = 0;
+  uint32_t last_unicode = 0;             // strings the normalizer handled in the most recent launch
   // decode
   uint32_t* raw_len = nullptr;  // n + 1
   uint64_t* raw_off = nullptr;  // n + 1
@@ -233,6 +245,21 @@ extern "C" int tmgpu_vocab_create(const uint8_t* file_bytes, size_t n, int devic
   d.capcode = h.capcode;
   d.normflag = h.normflag;
   d.charset = h.charset;
+  // UTF-8 vocabularies that normalize: non-ASCII strings are normalized on the device too
+  if (h.charset == 1 && ((h.normflag & 7u) != 0 || h.capcode == 2)) {
+    const UnicodeHost& t = unicode_host_tables();
+    UnicodeDev& u = v->uni;
+    if ((rc = upload(v, t.stage1, t.n_stage1, &u.stage1)) || (rc = upload(v, t.stage2, t.n_stage2, &u.stage2)) ||
+        (rc = upload(v, t.dkey, t.n_decomp, &u.dkey)) || (rc = upload(v, t.didx, t.n_decomp + 1, &u.didx)) ||
+        (rc = upload(v, t.ddata, t.n_ddata, &u.ddata)) || (rc = upload(v, t.lkey, t.n_lower, &u.lkey)) ||
+        (rc = upload(v, t.lval, t.n_lower, &u.lval)) || (rc = upload(v, t.ukey, t.n_upper, &u.ukey)) ||
+        (rc = upload(v, t.uval, t.n_upper, &u.uval)))
+      return fail(rc);
+    u.n_decomp = uint32_t(t.n_decomp);
+    u.n_lower = uint32_t(t.n_lower);
+    u.n_upper = uint32_t(t.n_upper);
+    v->unicode = true;
+  }
   *out = v;
   return TMGPU_OK;
 }
@@ -298,6 +325,36 @@ extern "C" int tmgpu_selftest_trie_lookup(const tmgpu_vocab* v, const uint8_t* w
   return host_trie_lookup(v->host, window, n, spaced, index);
 }
 
+// Table self-check (host): what the generated Unicode data says about one code point, so that
+// CPU-only CI can compare the whole table with an independent source (Python's unicodedata).
+// Returns the property word; lower/upper = simple case mappings; decomp gets the full canonical
+// decomposition (up to 4 code points, Hangul excluded), *n_decomp its length.
+extern "C" uint32_t tmgpu_selftest_unicode(uint32_t cp, uint32_t* lower, uint32_t* upper, uint32_t* decomp,
+                                           int* n_decomp) {
+  const UnicodeHost& t = unicode_host_tables();
+  if (n_decomp) *n_decomp = 0;
+  if (lower) *lower = cp;
+  if (upper) *upper = cp;
+  if (cp >= 0x110000u) return 0;
+  const uint32_t prop = t.stage2[size_t(t.stage1[cp >> 7]) * 128u + (cp & 127u)];
+  auto find = [](const uint32_t* keys, size_t n, uint32_t c) -> long {
+    long lo = 0, hi = long(n) - 1;
+    while (lo <= hi) {
+      long mid = (lo + hi) / 2;
+      if (keys[mid] == c) return mid;
+      if (keys[mid] < c) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+  };
+  if ((prop & 16u) && lower) { long k = find(t.lkey, t.n_lower, cp); if (k >= 0) *lower = t.lval[k]; }
+  if ((prop & 32u) && upper) { long k = find(t.ukey, t.n_upper, cp); if (k >= 0) *upper = t.uval[k]; }
+  if ((prop & 8u) && decomp && n_decomp) {
+    long k = find(t.dkey, t.n_decomp, cp);
+    if (k >= 0) for (uint32_t j = t.didx[k]; j < t.didx[k + 1] && *n_decomp < 4; j++) decomp[(*n_decomp)++] = t.ddata[j];
+  }
+  return prop;
+}
+
 // ------------------------------------------------------------------------------------------
 // workspace
 // ------------------------------------------------------------------------------------------
@@ -305,6 +362,7 @@ extern "C" void tmgpu_workspace_destroy(tmgpu_workspace* ws) {
   if (!ws) return;
   if (ws->v && ws->v->device >= 0) cudaSetDevice(ws->v->device);
   for (void* p : ws->allocs) cudaFree(p);
+  if (ws->uni_text) cudaFree(ws->uni_text);
   for (int i = 0; i < tmgpu_workspace::kEv; i++) {
     if (ws->ev0[i]) cudaEventDestroy(ws->ev0[i]);
     if (ws->ev1[i]) cudaEventDestroy(ws->ev1[i]);
@@ -344,6 +402,12 @@ extern "C" int tmgpu_workspace_create(tmgpu_vocab* v, uint32_t max_strings, uint
   A(&ws->overflow, 4);
   ws->scan_bytes = scan_temp_bytes(uint32_t(n1)) + 256;
   A(reinterpret_cast<uint8_t**>(&ws->scan_temp), ws->scan_bytes);
+  if (v->unicode) {
+    A(&ws->uni_list, n1);
+    A(&ws->uni_begin, n1);
+    A(&ws->uni_end, n1);
+    A(&ws->uni_ctr, 2);
+  }
   A(&ws->raw_len, n1);
   A(&ws->raw_off, n1);
   A(&ws->out_len, n1);
@@ -388,6 +452,63 @@ struct ChunkPlan {
   uint64_t slab_base;    // (off[s0] - off[0]) + slab_pad * s0
   cudaEvent_t ready;     // may be null
 };
+
+// Strings the tokenize kernel gave up on (first byte >= 0x80 under a normalizing vocabulary) are
+// normalized by the device normalizer and tokenized by a second launch that reads the normalized
+// text verbatim.  One small D2H tells the host whether there are any; ASCII batches pay only that.
+static int unicode_pass(tmgpu_workspace* ws, const TokenizeArgs& first, bool store, cudaStream_t st) {
+  tmgpu_vocab* v = ws->v;
+  ws->last_unicode = 0;
+  if (!v->unicode || first.n == 0 || v->host.max_len == 0) return TMGPU_OK;
+  CU(cudaMemsetAsync(ws->uni_ctr, 0, 16, st));
+  CU(launch_select_refused(first.status, first.off, first.ends, first.n, ws->uni_list, ws->uni_begin, ws->uni_ctr,
+                           v->sms, st));
+  unsigned long long h[2] = {0, 0};
+  CU(cudaMemcpyAsync(h, ws->uni_ctr, 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  ws->last_launches++;
+  if (h[0] == 0) return TMGPU_OK;
+  if (ws->uni_text_cap < h[1] + 64) {
+    if (ws->uni_text) cudaFree(ws->uni_text);
+    ws->uni_text = nullptr;
+    ws->uni_text_cap = h[1] + h[1] / 4 + 4096;
+    cudaError_t e = cudaMalloc(&ws->uni_text, ws->uni_text_cap);
+    if (e != cudaSuccess) {
+      ws->uni_text_cap = 0;
+      g_err = std::string("cudaMalloc(normalizer scratch): ") + cudaGetErrorString(e);
+      return TMGPU_E_NOMEM;
+    }
+  }
+  NormalizeArgs na{};
+  na.U = v->uni;
+  na.data = first.data;
+  na.off = first.off;
+  na.ends = first.ends;
+  na.list = ws->uni_list;
+  na.n_list = reinterpret_cast<const uint32_t*>(ws->uni_ctr);
+  na.scratch = ws->uni_text;
+  na.n_begin = ws->uni_begin;
+  na.n_end = ws->uni_end;
+  na.normflag = v->host.normflag;
+  na.capcode = v->host.capcode;
+  CU(launch_unicode_normalize(na, v->sms, st));
+  TokenizeArgs b = first;
+  b.data = ws->uni_text;
+  b.off = ws->uni_begin;
+  b.ends = ws->uni_end;
+  b.n = uint32_t(h[0]);
+  b.list = ws->uni_list;
+  b.raw_off = first.off;
+  b.raw_ends = first.ends;
+  b.prenorm = 1;
+  b.watermark = nullptr;
+  b.work_counter = ws->work_counter + (tmgpu_workspace::kMaxChunks - 1);
+  CU(cudaMemsetAsync(b.work_counter, 0, 4, st));
+  CU(launch_tokenize(b, 1, store, v->sms, st, nullptr));
+  ws->last_launches += 2;
+  ws->last_unicode = uint32_t(h[0]);
+  return TMGPU_OK;
+}
 
 static int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t* d_off, uint32_t n,
                               uint8_t enc_len, int mode, cudaStream_t st, const uint64_t* slab_off,
@@ -443,6 +564,10 @@ static int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const 
     ws->ev_head = (e + 1) % tmgpu_workspace::kEv;
     if (ws->ev_count < tmgpu_workspace::kEv) ws->ev_count++;
     ws->last_launches++;
+  }
+  {
+    int rc = unicode_pass(ws, a, mode == 0, st);
+    if (rc) return rc;
   }
   if (mode == 0) {
     CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, ws->counts, ws->tok_off, n + 1, st));
@@ -707,6 +832,12 @@ static int tokenize_streamed(tmgpu_vocab* v, uint32_t n, uint8_t enc_len, cudaEv
   a.overflow = ws->overflow;
   a.watermark = reinterpret_cast<const unsigned long long*>(v->d_run + 4);
   CU(launch_tokenize(a, v->group, true, v->sms, st, nullptr));
+  {
+    TokenizeArgs whole = a;
+    whole.watermark = nullptr;
+    int rc = unicode_pass(ws, whole, true, st);
+    if (rc) return rc;
+  }
   CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, ws->counts, ws->tok_off, n + 1, st));
   CU(launch_pack(ws->slab, v->d_off, ws->slab_pad, nullptr, ws->counts, ws->tok_off, ws->tokens, n, enc_len, v->sms, st));
   ws->last_launches = 4;

@@ -11,6 +11,7 @@
 
 #include "tokenize_kernel.cuh"
 #include "tokenize_thread_kernel.cuh"
+#include "unicode_normalize.cuh"
 
 namespace tmgpu {
 
@@ -339,7 +340,8 @@ static cudaError_t launch_thr(const TokenizeArgs& a, int sms, cudaStream_t st, i
 }
 
 cudaError_t launch_tokenize(const TokenizeArgs& a, int group, bool store, int sms, cudaStream_t st, int* grid_out) {
-  const int cap = a.v.capcode;
+  const int cap = a.prenorm ? 0 : a.v.capcode;   // pre-normalized text is read verbatim
+  if (a.prenorm) group = 1;
   if (group == 1) {  // one thread per string; big CTAs share a big edge cache when the batch fills them
     static const int forced = getenv("TMGPU_CTA") ? atoi(getenv("TMGPU_CTA")) : 0;  // experiment hook
     int cta = forced ? forced : (a.n >= uint32_t(sms) * 768u ? 1024 : 256);
@@ -376,6 +378,18 @@ cudaError_t launch_pack(const uint32_t* slab, const int64_t* off, uint32_t slab_
   if (enc == 2) pack_tokens_kernel<2><<<grid, 256, 0, st>>>(slab, off, slab_pad, slab_off, counts, tok_off, out, n);
   else if (enc == 3) pack_tokens_kernel<3><<<grid, 256, 0, st>>>(slab, off, slab_pad, slab_off, counts, tok_off, out, n);
   else pack_tokens_kernel<4><<<grid, 256, 0, st>>>(slab, off, slab_pad, slab_off, counts, tok_off, out, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_select_refused(const uint8_t* status, const int64_t* off, const int64_t* ends, uint32_t n,
+                                  uint32_t* list, int64_t* n_begin, unsigned long long* ctr, int sms,
+                                  cudaStream_t st) {
+  select_refused_kernel<<<sms * 4, 256, 0, st>>>(status, off, ends, n, list, n_begin, ctr);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_unicode_normalize(const NormalizeArgs& a, int sms, cudaStream_t st) {
+  unicode_normalize_kernel<<<sms * 8, 128, 0, st>>>(a);
   return cudaGetLastError();
 }
 

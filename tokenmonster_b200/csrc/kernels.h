@@ -6,6 +6,7 @@
 #include <cstdint>
 
 #include "device_tables.h"
+#include "unicode_dev.h"
 
 namespace tmgpu {
 
@@ -25,6 +26,12 @@ struct TokenizeArgs {
   uint8_t* status;           // n
   uint32_t* work_counter;    // zeroed before launch
   uint32_t* overflow;        // set to 1 if any string exceeded its slab capacity
+  // second pass over strings the device normalizer rewrote (unicode_normalize.cuh): work item k
+  // reads its text at off[k]..ends[k] and reports as string list[k]
+  const uint32_t* list;      // optional: work item -> string index
+  const int64_t* raw_off;    // with list: the strings' own offsets (slab placement and capacity)
+  const int64_t* raw_ends;
+  uint32_t prenorm;          // text is already normalized: no ASCII check, no case folding, CAP = 0
   const unsigned long long* watermark;  // optional: input bytes that have landed in `data` so far (host path
                              // streams the batch in while the kernel runs); NULL = everything is there
 };
@@ -40,6 +47,10 @@ cudaError_t launch_pack(const uint32_t* slab, const int64_t* off, uint32_t slab_
 // reply framing of the server protocol: [u32 n] then per string [u64 byte length][unit * items]
 cudaError_t launch_wire_frame(const uint8_t* src, const uint64_t* src_off, uint32_t unit, uint32_t n, uint8_t* dst,
                               int sms, cudaStream_t st);
+cudaError_t launch_select_refused(const uint8_t* status, const int64_t* off, const int64_t* ends, uint32_t n,
+                                  uint32_t* list, int64_t* n_begin, unsigned long long* ctr, int sms,
+                                  cudaStream_t st);
+cudaError_t launch_unicode_normalize(const NormalizeArgs& a, int sms, cudaStream_t st);
 cudaError_t launch_decode_size(const VocabDev& v, const uint8_t* tokens, const int64_t* tok_off, uint32_t n, int enc,
                                uint32_t* raw_len, int sms, cudaStream_t st, const uint64_t* prefix_off = nullptr);
 cudaError_t launch_decode_copy(const VocabDev& v, const uint8_t* tokens, const int64_t* tok_off, uint32_t n, int enc,

@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
   const VocabDev& V = A.v;
   const int M = V.max_len;
   const int LA = 2 * M + 2;
-  const bool want_ascii = (V.normflag != 0) || (CAP != 0);
-  const bool to_lower = (V.normflag & 2) != 0;
+  const bool want_ascii = !A.prenorm && ((V.normflag != 0) || (CAP != 0));
+  const bool to_lower = !A.prenorm && (V.normflag & 2) != 0;
   const bool can_retry = (V.delete_token != 0xFFFFFFu) && (V.space_start != kNoVal);
 
   auto ring_byte = [&](int c) -> uint32_t {
@@ -138,19 +138,29 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
     __syncwarp();
     // ============================ take a new string ============================================
     if (!running && !no_more) {
-      s = atomicAdd(A.work_counter, 1u);
-      if (s >= A.n) {
+      const uint32_t item = atomicAdd(A.work_counter, 1u);
+      if (item >= A.n) {
         no_more = true;
+      } else if (A.list && A.ends[item] < A.off[item]) {
+        // the normalizer refused this string: its status 13 from the first pass stands
       } else {
-        const int64_t o0 = A.off[s];
-        slen = int((A.ends ? A.ends[s] : A.off[s + 1]) - o0);
+        s = A.list ? A.list[item] : item;
+        const int64_t o0 = A.off[item];
+        slen = int((A.ends ? A.ends[item] : A.off[item + 1]) - o0);
         if (A.watermark) {   // the batch is still streaming in: wait until this string has landed
           const unsigned long long need_bytes = static_cast<unsigned long long>(o0 + slen);
           while (*reinterpret_cast<const volatile unsigned long long*>(A.watermark) < need_bytes) __nanosleep(500);
         }
         const uint8_t* g0 = A.data + o0;
-        slab_base = A.slab_off ? A.slab_off[s] : uint64_t(o0 - A.off[0]) + uint64_t(A.slab_pad) * s;
-        cap = A.slab_off ? uint32_t(A.slab_off[s + 1] - A.slab_off[s]) : uint32_t(slen) + A.slab_pad;
+        if (A.list) {   // placement follows the string's own (raw) extent, like the first pass
+          const int64_t r0 = A.raw_off[s];
+          const int64_t r1 = A.raw_ends ? A.raw_ends[s] : A.raw_off[s + 1];
+          slab_base = A.slab_off ? A.slab_off[s] : uint64_t(r0 - A.raw_off[0]) + uint64_t(A.slab_pad) * s;
+          cap = A.slab_off ? uint32_t(A.slab_off[s + 1] - A.slab_off[s]) : uint32_t(r1 - r0) + A.slab_pad;
+        } else {
+          slab_base = A.slab_off ? A.slab_off[s] : uint64_t(o0 - A.off[0]) + uint64_t(A.slab_pad) * s;
+          cap = A.slab_off ? uint32_t(A.slab_off[s + 1] - A.slab_off[s]) : uint32_t(slen) + A.slab_pad;
+        }
         galign = int(reinterpret_cast<uintptr_t>(g0) & 15);
         ga = g0 - galign;
         cshift = (CAP == 0) ? galign : 0;
