@@ -193,3 +193,40 @@ def test_non_ascii_batch_large_and_streamed(built):
         want, miss, st = cache[t]
         assert int(r.status[s]) == st and np.array_equal(r[s].astype(np.uint32), want), s
     v.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("capcode,normflag", [(2, 1), (0, 1), (2, 7)])
+def test_non_ascii_decode_and_round_trip(built, capcode, normflag):
+    """Decode (capcode decoder with Unicode classes and simple upper-casing) against the oracle, the
+    NFD round trip, and the streaming decoder fed one id at a time."""
+    from tokenmonster_b200 import Vocab
+    os.environ["TMGPU_GROUP"] = "1"
+    vb = make_unicode_vocab(capcode, normflag)
+    v, chk = Vocab(vb, device=0), oracle.OracleVocab(vb, "port")
+    grow = [" ⱯⱯⱯⱯⱯⱯⱯⱯ ⱭⱭⱭ".encode(), "ȾȾȾ ⱯⱭ x".encode(), " ǅ ǄǄ ǆ".encode()]      # capitals longer than their lower case
+    texts = [t for t in unicode_texts(31 + capcode, 300) + EDGE + grow if expect(chk, t, normflag, capcode)[2] == 0]
+    off = np.zeros(len(texts) + 1, np.uint64)
+    off[1:] = np.cumsum([len(t) for t in texts])
+    r = v.tokenize_batch(np.frombuffer(b"".join(texts), np.uint8), off, 4)
+    back, boff = v.decode_batch(r.raw, r.tok_off, 4)
+    for s, t in enumerate(texts):
+        got = back[int(boff[s]):int(boff[s + 1])].tobytes()
+        keys = chk.decode(r[s], raw=True)                       # the concatenated token keys
+        want = uo.capcode_decode(keys.decode("utf-8")).encode() if capcode == 2 else keys
+        assert got == want, (s, t)
+        if normflag == 1:
+            assert got.decode() == ud.normalize("NFD", t.decode()), (s, t)   # lossless up to NFD
+    # streaming: one id per call, state (partial UTF-8 + capcode flags) carried on the device
+    some = [s for s in range(len(texts)) if 0 < len(r[s]) <= 60][:48]
+    dec = v.decoder(len(some))
+    outs = [b""] * len(some)
+    for step in range(max(len(r[s]) for s in some)):
+        chunk = [r[s][step:step + 1] for s in some]
+        for k, piece in enumerate(dec.decode_batch(chunk)):
+            outs[k] += piece
+    tail = dec.flush()
+    for k, s in enumerate(some):
+        assert outs[k] + tail[k] == back[int(boff[s]):int(boff[s + 1])].tobytes(), (k, texts[s])
+    dec.close()
+    v.close()

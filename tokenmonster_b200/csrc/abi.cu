@@ -952,9 +952,11 @@ extern "C" int tmgpu_count_batch(tmgpu_vocab* v, const uint8_t* data, const uint
 static int ensure_decode_cap(tmgpu_workspace* ws, uint64_t bytes) {
   if (ws->dec_cap >= bytes + 64) return TMGPU_OK;
   uint64_t cap = bytes + bytes / 8 + 4096;
+  // capcode decode of non-ASCII text may grow a W-word by half (2-byte letter -> 3-byte capital)
+  const uint64_t wide = ws->v->unicode ? cap + cap / 2 + 64 : cap;
   int rc = dev_alloc(ws->allocs, &ws->raw, cap);
-  if (!rc) rc = dev_alloc(ws->allocs, &ws->dec, cap);
-  if (!rc) rc = dev_alloc(ws->allocs, &ws->dense, cap);
+  if (!rc) rc = dev_alloc(ws->allocs, &ws->dec, wide);
+  if (!rc) rc = dev_alloc(ws->allocs, &ws->dense, wide);
   if (rc) return rc;
   ws->dec_cap = cap;  // earlier (smaller) buffers stay in the pool until the workspace dies
   return TMGPU_OK;
@@ -990,13 +992,15 @@ static int decode_on_stream(tmgpu_workspace* ws, const uint8_t* d_tokens, const 
   }
   CU(cudaMemsetAsync(ws->out_len + n, 0, 4, st));
   if (n) {
-    CU(launch_capcode_decode(ws->raw, ws->raw_off, n, ws->dec, ws->out_len, v->sms, st));
+    CU(launch_capcode_decode(ws->raw, ws->raw_off, n, ws->dec, ws->out_len, v->sms, st, nullptr, nullptr,
+                             v->unicode ? &v->uni : nullptr));
     ws->last_launches++;
   }
   CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, ws->out_len, ws->out_off, n + 1, st));
   ws->last_launches++;
   if (n) {
-    CU(launch_compact_bytes(ws->dec, ws->raw_off, ws->out_len, ws->out_off, n, ws->dense, v->sms, st));
+    CU(launch_compact_bytes(ws->dec, ws->raw_off, ws->out_len, ws->out_off, n, ws->dense, v->sms, st,
+                            v->unicode ? 1 : 0));
     ws->last_launches++;
   }
   uint64_t total = 0;
@@ -1445,7 +1449,8 @@ extern "C" int tmgpu_decoder_decode(tmgpu_decoder* d, const uint8_t* tokens, con
     CU(launch_copy_tail(ws->raw, ws->raw_off, d->keep_len, d->new_off, n, d->new_rem, v->sms, st));
     lens = d->keep_len;
     if (v->host.capcode == 2) {
-      CU(launch_capcode_decode(ws->raw, ws->raw_off, n, ws->dec, ws->out_len, v->sms, st, d->keep_len, d->cc_state));
+      CU(launch_capcode_decode(ws->raw, ws->raw_off, n, ws->dec, ws->out_len, v->sms, st, d->keep_len, d->cc_state,
+                               v->unicode ? &v->uni : nullptr));
       src = ws->dec;
       lens = ws->out_len;
     }
@@ -1454,7 +1459,9 @@ extern "C" int tmgpu_decoder_decode(tmgpu_decoder* d, const uint8_t* tokens, con
   if (lens != ws->out_len && n) CU(cudaMemcpyAsync(ws->out_len, lens, size_t(n) * 4, cudaMemcpyDeviceToDevice, st));
   CU(cudaMemsetAsync(ws->out_len + n, 0, 4, st));
   CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, ws->out_len, ws->out_off, n + 1, st));
-  if (n) CU(launch_compact_bytes(src, ws->raw_off, ws->out_len, ws->out_off, n, ws->dense, v->sms, st));
+  if (n)
+    CU(launch_compact_bytes(src, ws->raw_off, ws->out_len, ws->out_off, n, ws->dense, v->sms, st,
+                            (src == ws->dec && v->unicode) ? 1 : 0));
   uint64_t total = 0;
   CU(cudaMemcpyAsync(&total, ws->out_off + n, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));

@@ -142,18 +142,21 @@ __global__ void __launch_bounds__(256) decode_copy_kernel(VocabDev V, const uint
 }
 
 // capcode level-2 decoder, one thread per string (javascript/tokenmonster.js:1007-1065; the
-// stateless form used by Vocab.Decode, go/tokenmonster.go:788-796).  ASCII classes; non-ASCII
-// code points pass through unchanged and a pending delete swallows a whole UTF-8 sequence.
-// Decoding never grows the text, so the result is written at the same offsets of `dst`.
+// stateless form used by Vocab.Decode, go/tokenmonster.go:788-796).  ASCII text never grows, so
+// the result is written at the same offsets of `dst`.  With `wide` (vocabularies whose text may
+// be non-ASCII) code points are classified and upper-cased through the Unicode tables (simple
+// mappings, as Go's unicode.ToUpper); inside a W-word a 2-byte letter may become a 3-byte one,
+// so string s is written at raw_off[s] + (raw_off[s]+1)/2, a region of 1.5x its length.
 __global__ void __launch_bounds__(256) capcode_decode_kernel(const uint8_t* __restrict__ src,
                                                              const uint64_t* __restrict__ raw_off, uint32_t n,
                                                              uint8_t* __restrict__ dst,
                                                              uint32_t* __restrict__ out_len,
                                                              const uint32_t* __restrict__ len_in,
-                                                             uint8_t* __restrict__ state) {
+                                                             uint8_t* __restrict__ state, const UnicodeDev U,
+                                                             int wide) {
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
     const uint8_t* in = src + raw_off[s];
-    uint8_t* out = dst + raw_off[s];
+    uint8_t* out = dst + raw_off[s] + (wide ? ((raw_off[s] + 1) >> 1) : 0ull);
     const uint32_t len = len_in ? len_in[s] : uint32_t(raw_off[s + 1] - raw_off[s]);
     // streaming decoder: the four flags of capcode.Decoder persist across calls (js:1009-1012)
     const uint32_t st0 = state ? state[s] : 0u;
@@ -168,14 +171,36 @@ __global__ void __launch_bounds__(256) capcode_decode_kernel(const uint8_t* __re
         if (del) del = false;
         else { out[o++] = ' '; if (!ignore) in_word = false; }
       } else if (r >= 0x80) {
-        if (del) {
-          while (i + 1 < len && (in[i + 1] & 0xC0) == 0x80) i++;
-          del = false;
-        } else {
-          in_char = false;
-          out[o++] = uint8_t(r);
-          while (i + 1 < len && (in[i + 1] & 0xC0) == 0x80) out[o++] = in[++i];
+        // one code point (a malformed sequence is passed through byte by byte)
+        uint32_t cp = 0;
+        int l = wide ? utf8_decode(in + i, int64_t(len - i), &cp) : 0;
+        if (l == 0) {
+          l = 1;
+          while (i + l < len && (in[i + l] & 0xC0) == 0x80) l++;
+          cp = 0xFFFFFFFFu;
         }
+        const uint32_t prop = (cp != 0xFFFFFFFFu) ? uni_prop(U, cp) : 0u;
+        const uint32_t cl = (cp != 0xFFFFFFFFu) ? uni_class(cp, prop) : uint32_t(UC_O);
+        bool raise = false;
+        if (del) {
+          del = false;                                   // js:1042-1043: the code point is swallowed
+          i += l - 1;
+          ignore = false;
+          continue;
+        } else if (in_char) {
+          in_char = false;
+          raise = true;                                  // js:1045-1046
+        } else if (in_word) {
+          if (cl == UC_LL || cl == UC_LU) raise = true;  // js:1048-1049
+          else if (!(cl == UC_ND || cl == UC_APO || cl == UC_MN || cl == UC_MO)) in_word = false;
+        }
+        const uint32_t up = (raise && cp != 0xFFFFFFFFu) ? uni_upper(U, cp, prop) : cp;
+        if (up != cp) {
+          o += utf8_put(out + o, up);
+        } else {
+          for (int k = 0; k < l; k++) out[o++] = in[i + k];
+        }
+        i += l - 1;
       } else if (del) {
         del = false;
       } else if (in_char) {
@@ -267,11 +292,11 @@ __global__ void __launch_bounds__(256) compact_bytes_kernel(const uint8_t* __res
                                                             const uint64_t* __restrict__ src_off,
                                                             const uint32_t* __restrict__ len,
                                                             const uint64_t* __restrict__ dst_off, uint32_t n,
-                                                            uint8_t* __restrict__ dst) {
+                                                            uint8_t* __restrict__ dst, int wide) {
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
   for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n; s += warps) {
-    const uint8_t* a = src + src_off[s];
+    const uint8_t* a = src + src_off[s] + (wide ? ((src_off[s] + 1) >> 1) : 0ull);
     uint8_t* b = dst + dst_off[s];
     const uint32_t l = len[s];
     for (uint32_t k = lane; k < l; k += 32) b[k] = a[k];
@@ -414,8 +439,9 @@ cudaError_t launch_decode_copy(const VocabDev& v, const uint8_t* tokens, const i
 
 cudaError_t launch_capcode_decode(const uint8_t* src, const uint64_t* raw_off, uint32_t n, uint8_t* dst,
                                   uint32_t* out_len, int sms, cudaStream_t st, const uint32_t* len_in,
-                                  uint8_t* state) {
-  capcode_decode_kernel<<<sms * 8, 256, 0, st>>>(src, raw_off, n, dst, out_len, len_in, state);
+                                  uint8_t* state, const UnicodeDev* uni) {
+  capcode_decode_kernel<<<sms * 8, 256, 0, st>>>(src, raw_off, n, dst, out_len, len_in, state,
+                                                 uni ? *uni : UnicodeDev{}, uni ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -432,8 +458,9 @@ cudaError_t launch_copy_tail(const uint8_t* raw, const uint64_t* raw_off, const 
 }
 
 cudaError_t launch_compact_bytes(const uint8_t* src, const uint64_t* src_off, const uint32_t* len,
-                                 const uint64_t* dst_off, uint32_t n, uint8_t* dst, int sms, cudaStream_t st) {
-  compact_bytes_kernel<<<sms * 8, 256, 0, st>>>(src, src_off, len, dst_off, n, dst);
+                                 const uint64_t* dst_off, uint32_t n, uint8_t* dst, int sms, cudaStream_t st,
+                                 int wide) {
+  compact_bytes_kernel<<<sms * 8, 256, 0, st>>>(src, src_off, len, dst_off, n, dst, wide);
   return cudaGetLastError();
 }
 

@@ -58,12 +58,13 @@ cudaError_t launch_decode_copy(const VocabDev& v, const uint8_t* tokens, const i
                                const uint64_t* prefix_off = nullptr, const uint8_t* prefix = nullptr);
 cudaError_t launch_capcode_decode(const uint8_t* src, const uint64_t* raw_off, uint32_t n, uint8_t* dst,
                                   uint32_t* out_len, int sms, cudaStream_t st, const uint32_t* len_in = nullptr,
-                                  uint8_t* state = nullptr);
+                                  uint8_t* state = nullptr, const UnicodeDev* uni = nullptr);
 cudaError_t launch_stream_tail(const uint8_t* raw, const uint64_t* raw_off, uint32_t n, int charset,
                                uint32_t* keep_len, uint32_t* rem_len, int sms, cudaStream_t st);
 cudaError_t launch_copy_tail(const uint8_t* raw, const uint64_t* raw_off, const uint32_t* keep_len,
                              const uint64_t* rem_off, uint32_t n, uint8_t* rem, int sms, cudaStream_t st);
 cudaError_t launch_compact_bytes(const uint8_t* src, const uint64_t* src_off, const uint32_t* len,
-                                 const uint64_t* dst_off, uint32_t n, uint8_t* dst, int sms, cudaStream_t st);
+                                 const uint64_t* dst_off, uint32_t n, uint8_t* dst, int sms, cudaStream_t st,
+                                 int wide = 0);  // wide: segment s sits at src_off[s] + (src_off[s]+1)/2
 
 }  // namespace tmgpu
