@@ -45,8 +45,12 @@ extern "C" {
 
 /* per-string status[] values */
 #define TMGPU_S_OK 0
-#define TMGPU_S_NORMALIZE 13 /* normalization failed: non-ASCII input under NFD/capcode in this
-                                build (server status 13, go:963-966) -- result for it is empty */
+#define TMGPU_S_NORMALIZE 13 /* normalization failed (server status 13, go:963-966); the result for
+                                that string is empty.  Raised for: invalid UTF-8 or more than 30
+                                consecutive combining marks under a normalizing UTF-8 vocabulary;
+                                any byte >= 0x80 under a normalizing vocabulary whose charset is
+                                not UTF-8.  Non-ASCII text is otherwise normalized on the device
+                                (NFD, accents, lowercase, capcode; Unicode 15.0 tables). */
 
 typedef struct tmgpu_vocab tmgpu_vocab;
 
@@ -184,8 +188,10 @@ typedef struct tmgpu_device_view {
 int tmgpu_workspace_create(tmgpu_vocab* v, uint32_t max_strings, uint64_t max_bytes,
                            tmgpu_workspace** out);
 void tmgpu_workspace_destroy(tmgpu_workspace* ws);
-/* Launches the tokenize kernels on `stream` (void* = cudaStream_t; NULL = default stream) and
- * returns without synchronising.  mode: 0 = ids (enc_len 2/3/4), 1 = count only. */
+/* Launches the tokenize kernels on `stream` (void* = cudaStream_t; NULL = default stream).
+ * mode: 0 = ids (enc_len 2/3/4), 1 = count only.  Returns with the scan / pack kernels still in
+ * flight; under a vocabulary that normalizes UTF-8 text the call waits once, after the tokenize
+ * kernel, for a 16-byte read that says whether any string needs the non-ASCII pass. */
 int tmgpu_tokenize_device(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t* d_off,
                           uint32_t n, uint8_t enc_len, int mode, void* stream,
                           tmgpu_device_view* view);
