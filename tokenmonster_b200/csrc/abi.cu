@@ -491,7 +491,14 @@ static int unicode_pass(tmgpu_workspace* ws, const TokenizeArgs& first, bool sto
   na.n_end = ws->uni_end;
   na.normflag = v->host.normflag;
   na.capcode = v->host.capcode;
+  static const bool trace = getenv("TMGPU_TRACE") != nullptr;   // diagnostic: phase times on stderr
+  cudaEvent_t te[3] = {};
+  if (trace) {
+    for (auto& e : te) cudaEventCreate(&e);
+    cudaEventRecord(te[0], st);
+  }
   CU(launch_unicode_normalize(na, v->sms, st));
+  if (trace) cudaEventRecord(te[1], st);
   TokenizeArgs b = first;
   b.data = ws->uni_text;
   b.off = ws->uni_begin;
@@ -505,6 +512,16 @@ static int unicode_pass(tmgpu_workspace* ws, const TokenizeArgs& first, bool sto
   b.work_counter = ws->work_counter + (tmgpu_workspace::kMaxChunks - 1);
   CU(cudaMemsetAsync(b.work_counter, 0, 4, st));
   CU(launch_tokenize(b, 1, store, v->sms, st, nullptr));
+  if (trace) {
+    cudaEventRecord(te[2], st);
+    cudaEventSynchronize(te[2]);
+    float a = 0, c = 0;
+    cudaEventElapsedTime(&a, te[0], te[1]);
+    cudaEventElapsedTime(&c, te[1], te[2]);
+    fprintf(stderr, "[tmgpu] non-ASCII pass: %llu strings, scratch %llu B, normalize %.3f ms, tokenize %.3f ms\n", h[0],
+            h[1], a, c);
+    for (auto& e : te) cudaEventDestroy(e);
+  }
   ws->last_launches += 2;
   ws->last_unicode = uint32_t(h[0]);
   return TMGPU_OK;

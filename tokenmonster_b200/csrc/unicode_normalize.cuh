@@ -27,6 +27,8 @@ namespace tmgpu {
 enum : uint32_t { UC_O = 0, UC_LU = 1, UC_LL = 2, UC_LO = 3, UC_ND = 4, UC_MN = 5, UC_MO = 6, UC_APO = 7, UC_SP = 8 };
 
 __device__ __forceinline__ uint32_t uni_prop(const UnicodeDev& U, uint32_t cp) {
+  if (cp < 128u)   // ASCII needs no table: class + case bits, no decomposition, ccc 0
+    return (cp - 'A' < 26u) ? (UC_LU | 16u) : (cp - 'a' < 26u) ? (UC_LL | 32u) : (cp - '0' < 10u) ? uint32_t(UC_ND) : 0u;
   if (cp >= 0x110000u) return 0;
   return U.stage2[uint32_t(U.stage1[cp >> 7]) * 128u + (cp & 127u)];
 }
