@@ -77,6 +77,7 @@ PROTOTYPES = {
     "tmgpu_tokenize_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8, C.c_int,
                                         C.c_void_p, C.POINTER(DeviceView)]),
     "tmgpu_last_launch_count": (C.c_int, [C.c_void_p]),
+    "tmgpu_last_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32 * 4)]),
     "tmgpu_workspace_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     "tmgpu_decode_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8, C.c_void_p,
                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),

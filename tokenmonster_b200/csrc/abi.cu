@@ -86,6 +86,23 @@ struct tmgpu_workspace {
   uint8_t* uni_text = nullptr;
   uint64_t uni_text_cap = 0;
   uint32_t last_unicode = 0;             // strings the normalizer handled in the most recent launch
+  // long documents tokenized in chunks (chunking.cuh): per document ...
+  uint32_t* ck_n = nullptr;              // n + 1: chunks of the document (0 = not chunked)
+  uint64_t* ck_base = nullptr;           // n + 1: exclusive scan
+  uint8_t* ck_skip = nullptr;            // n
+  uint8_t* ck_fail = nullptr;            // n
+  uint32_t* ck_list = nullptr;           // n: documents to redo with one lane
+  int64_t* ck_fb = nullptr;              // n
+  int64_t* ck_fe = nullptr;              // n
+  unsigned long long* ck_ctr = nullptr;
+  // ... and per chunk (grown on demand)
+  ChunkItem* ck_items = nullptr;
+  ChunkOut* ck_out = nullptr;
+  uint32_t *ck_ids = nullptr, *ck_pos = nullptr, *ck_miss = nullptr;   // chunks x log capacity
+  uint32_t *ck_sb = nullptr, *ck_se = nullptr, *ck_sd = nullptr;
+  uint64_t ck_chunks_cap = 0;
+  std::vector<void*> ck_allocs;
+  uint32_t last_chunked = 0, last_chunk_redo = 0;   // chunks launched / documents redone, last launch
   // decode
   uint32_t* raw_len = nullptr;  // n + 1
   uint64_t* raw_off = nullptr;  // n + 1
@@ -363,6 +380,7 @@ extern "C" void tmgpu_workspace_destroy(tmgpu_workspace* ws) {
   if (ws->v && ws->v->device >= 0) cudaSetDevice(ws->v->device);
   for (void* p : ws->allocs) cudaFree(p);
   if (ws->uni_text) cudaFree(ws->uni_text);
+  for (void* p : ws->ck_allocs) cudaFree(p);
   for (int i = 0; i < tmgpu_workspace::kEv; i++) {
     if (ws->ev0[i]) cudaEventDestroy(ws->ev0[i]);
     if (ws->ev1[i]) cudaEventDestroy(ws->ev1[i]);
@@ -408,6 +426,14 @@ extern "C" int tmgpu_workspace_create(tmgpu_vocab* v, uint32_t max_strings, uint
     A(&ws->uni_end, n1);
     A(&ws->uni_ctr, 2);
   }
+  A(&ws->ck_n, n1);
+  A(&ws->ck_base, n1);
+  A(&ws->ck_skip, n1);
+  A(&ws->ck_fail, n1);
+  A(&ws->ck_list, n1);
+  A(&ws->ck_fb, n1);
+  A(&ws->ck_fe, n1);
+  A(&ws->ck_ctr, 2);
   A(&ws->raw_len, n1);
   A(&ws->raw_off, n1);
   A(&ws->out_len, n1);
@@ -445,6 +471,23 @@ extern "C" int tmgpu_workspace_kernel_times(tmgpu_workspace* ws, float* ms_out, 
 
 extern "C" int tmgpu_last_launch_count(const tmgpu_workspace* ws) { return ws ? ws->last_launches : 0; }
 
+// What the most recent tokenize / count call did besides the plain launch: out[0] = strings that
+// went through the non-ASCII normalizer, out[1] = chunks launched for long documents, out[2] =
+// chunked documents redone by a single lane, out[3] = kernels launched.  `ws` may be NULL: then
+// the vocabulary's internal workspace (host-buffer calls) is reported.
+extern "C" int tmgpu_last_stats(const tmgpu_vocab* v, const tmgpu_workspace* ws, uint32_t out[4]) {
+  if (!ws && v) ws = v->ws;
+  if (!ws || !out) {
+    g_err = "tmgpu_last_stats: no workspace yet";
+    return TMGPU_E_ARG;
+  }
+  out[0] = ws->last_unicode;
+  out[1] = ws->last_chunked;
+  out[2] = ws->last_chunk_redo;
+  out[3] = uint32_t(ws->last_launches);
+  return TMGPU_OK;
+}
+
 // A host-buffer batch is tokenized in chunks of strings so that the H2D copy of chunk k+1 overlaps
 // the kernel of chunk k: `ready` is recorded on the copy stream after the chunk's bytes landed.
 struct ChunkPlan {
@@ -452,6 +495,121 @@ struct ChunkPlan {
   uint64_t slab_base;    // (off[s0] - off[0]) + slab_pad * s0
   cudaEvent_t ready;     // may be null
 };
+
+// ---- long documents in chunks (chunking.cuh) -----------------------------------------------------
+// Phase 1 (before the main launch): decide which documents are chunked.  Returns the number of
+// chunks (0 = nothing to do); the main launch then skips those documents via ws->ck_skip.
+static int chunk_plan(tmgpu_workspace* ws, const TokenizeArgs& a, cudaStream_t st, uint32_t* total_out) {
+  tmgpu_vocab* v = ws->v;
+  *total_out = 0;
+  ws->last_chunked = 0;
+  ws->last_chunk_redo = 0;
+  static const bool off = getenv("TMGPU_NO_CHUNKS") != nullptr;   // diagnostic: one lane per document always
+  const HostTables& h = v->host;
+  if (off || a.n == 0 || a.n >= uint32_t(v->sms) * 512u || h.max_len == 0 || h.charset == 2 || a.slab_off) return TMGPU_OK;
+  CU(launch_chunk_count(a.off, a.ends, a.n, ws->ck_n, ws->ck_skip, v->sms, st));
+  CU(cudaMemsetAsync(ws->ck_n + a.n, 0, 4, st));
+  CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, ws->ck_n, ws->ck_base, a.n + 1, st));
+  uint64_t total = 0;
+  CU(cudaMemcpyAsync(&total, ws->ck_base + a.n, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (total == 0 || total > (1ull << 21)) return TMGPU_OK;   // nothing long, or far too much for the logs
+  if (ws->ck_chunks_cap < total) {
+    for (void* p : ws->ck_allocs) cudaFree(p);
+    ws->ck_allocs.clear();
+    ws->ck_chunks_cap = 0;
+    const uint64_t cap = total + total / 4 + 64, log = cap * chunk_log_capacity();
+    int rc = 0;
+    auto A = [&](auto** p, size_t count) {
+      if (!rc) rc = dev_alloc(ws->ck_allocs, p, count);
+    };
+    A(&ws->ck_items, cap);
+    A(&ws->ck_out, cap);
+    A(&ws->ck_ids, log);
+    A(&ws->ck_pos, log);
+    A(&ws->ck_miss, log);
+    A(&ws->ck_sb, cap);
+    A(&ws->ck_se, cap);
+    A(&ws->ck_sd, cap);
+    if (rc) return rc;
+    ws->ck_chunks_cap = cap;
+  }
+  *total_out = uint32_t(total);
+  return TMGPU_OK;
+}
+
+// Phase 2 (after the main launch): tokenize the chunks, stitch, gather; documents whose chunks do
+// not meet are tokenized again by one lane each.
+static int chunk_run(tmgpu_workspace* ws, const TokenizeArgs& first, uint32_t total, int mode, cudaStream_t st) {
+  tmgpu_vocab* v = ws->v;
+  CU(cudaMemsetAsync(ws->ck_fail, 0, first.n, st));
+  CU(launch_chunk_fill(first.data, first.off, first.ends, first.n, ws->ck_n, ws->ck_base, total, ws->ck_items,
+                       ws->ck_fail, v->sms, st));
+  TokenizeArgs c = first;
+  c.n = total;
+  c.slab = ws->ck_ids;
+  c.skip = nullptr;
+  c.watermark = nullptr;
+  c.chunks = ws->ck_items;
+  c.c_pos = ws->ck_pos;
+  c.c_miss = ws->ck_miss;
+  c.c_out = ws->ck_out;
+  c.c_cap = chunk_log_capacity();
+  c.c_ov = chunk_overlap();
+  c.work_counter = ws->work_counter + (tmgpu_workspace::kMaxChunks - 2);
+  CU(cudaMemsetAsync(c.work_counter, 0, 4, st));
+  CU(launch_tokenize_chunks(c, v->sms, st));
+  StitchArgs sa{};
+  sa.off = first.off;
+  sa.ends = first.ends;
+  sa.n = first.n;
+  sa.n_chunks = ws->ck_n;
+  sa.chunk_base = ws->ck_base;
+  sa.c_out = ws->ck_out;
+  sa.c_pos = ws->ck_pos;
+  sa.c_miss = ws->ck_miss;
+  sa.c_cap = c.c_cap;
+  sa.slab_pad = first.slab_pad;
+  sa.count_mode = mode == 1;
+  sa.doc_fail = ws->ck_fail;
+  sa.seg_begin = ws->ck_sb;
+  sa.seg_end = ws->ck_se;
+  sa.seg_dst = ws->ck_sd;
+  sa.counts = first.counts;
+  sa.need = first.need;
+  sa.missing = first.missing;
+  sa.status = first.status;
+  sa.overflow = first.overflow;
+  CU(launch_chunk_stitch(sa, v->sms, st));
+  if (mode == 0)
+    CU(launch_chunk_gather(ws->ck_items, total, ws->ck_ids, c.c_cap, ws->ck_sb, ws->ck_se, ws->ck_sd, first.off,
+                           first.slab_pad, first.slab, v->sms, st));
+  CU(cudaMemsetAsync(ws->ck_ctr, 0, 8, st));
+  CU(launch_chunk_failed(ws->ck_fail, ws->ck_n, first.off, first.ends, first.n, ws->ck_list, ws->ck_fb, ws->ck_fe,
+                         ws->ck_ctr, v->sms, st));
+  unsigned long long redo = 0;
+  CU(cudaMemcpyAsync(&redo, ws->ck_ctr, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  ws->last_launches += 5 + (mode == 0 ? 1 : 0);
+  ws->last_chunked = total;
+  ws->last_chunk_redo = uint32_t(redo);
+  if (redo) {   // one lane per document, the ordinary way
+    TokenizeArgs b = first;
+    b.off = ws->ck_fb;
+    b.ends = ws->ck_fe;
+    b.n = uint32_t(redo);
+    b.list = ws->ck_list;
+    b.raw_off = first.off;
+    b.raw_ends = first.ends;
+    b.skip = nullptr;
+    b.watermark = nullptr;
+    b.work_counter = ws->work_counter + (tmgpu_workspace::kMaxChunks - 2);
+    CU(cudaMemsetAsync(b.work_counter, 0, 4, st));
+    CU(launch_tokenize(b, 1, mode == 0, v->sms, st, nullptr));
+    ws->last_launches++;
+  }
+  return TMGPU_OK;
+}
 
 // Strings the tokenize kernel gave up on (first byte >= 0x80 under a normalizing vocabulary) are
 // normalized by the device normalizer and tokenized by a second launch that reads the normalized
@@ -551,6 +709,13 @@ static int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const 
   a.status = ws->status;
   a.work_counter = ws->work_counter;
   a.overflow = ws->overflow;
+  uint32_t ck_total = 0;   // long documents of a small batch are tokenized in chunks (chunking.cuh)
+  if (n > 0 && (!chunks || chunks->size() == 1)) {
+    if (chunks && (*chunks)[0].ready) CU(cudaStreamWaitEvent(st, (*chunks)[0].ready, 0));
+    int rc = chunk_plan(ws, a, st, &ck_total);
+    if (rc) return rc;
+    if (ck_total) a.skip = ws->ck_skip;
+  }
   if (v->host.max_len == 0) {  // empty vocabulary: empty result, not an error (go:960-962)
     CU(cudaMemsetAsync(ws->counts, 0, (size_t(n) + 1) * 4, st));
     CU(cudaMemsetAsync(ws->missing, 0, size_t(n) * 4, st));
@@ -581,6 +746,11 @@ static int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const 
     ws->ev_head = (e + 1) % tmgpu_workspace::kEv;
     if (ws->ev_count < tmgpu_workspace::kEv) ws->ev_count++;
     ws->last_launches++;
+  }
+  if (ck_total) {
+    int rc = chunk_run(ws, a, ck_total, mode, st);
+    if (rc) return rc;
+    a.skip = nullptr;
   }
   {
     int rc = unicode_pass(ws, a, mode == 0, st);

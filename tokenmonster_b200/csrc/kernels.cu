@@ -12,6 +12,7 @@
 #include "tokenize_kernel.cuh"
 #include "tokenize_thread_kernel.cuh"
 #include "unicode_normalize.cuh"
+#include "chunking.cuh"
 
 namespace tmgpu {
 
@@ -394,6 +395,67 @@ cudaError_t launch_tokenize(const TokenizeArgs& a, int group, bool store, int sm
   TM_CASE(4)
 #undef TM_CASE
   return cudaErrorInvalidValue;
+}
+
+uint32_t chunk_log_capacity() { return kChunkLogCap; }
+uint32_t chunk_overlap() { return kChunkOverlap; }
+
+cudaError_t launch_chunk_count(const int64_t* off, const int64_t* ends, uint32_t n, uint32_t* n_chunks, uint8_t* skip,
+                               int sms, cudaStream_t st) {
+  chunk_count_kernel<<<sms * 2, 256, 0, st>>>(off, ends, n, n_chunks, skip);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chunk_fill(const uint8_t* data, const int64_t* off, const int64_t* ends, uint32_t n,
+                              const uint32_t* n_chunks, const uint64_t* chunk_base, uint32_t total, ChunkItem* items,
+                              uint8_t* doc_fail, int sms, cudaStream_t st) {
+  chunk_fill_kernel<<<sms * 2, 256, 0, st>>>(data, off, ends, n, n_chunks, chunk_base, total, items, doc_fail);
+  return cudaGetLastError();
+}
+
+// chunk launch: always the id-storing kernel (the stitcher needs the step log even for Count)
+cudaError_t launch_tokenize_chunks(const TokenizeArgs& a, int sms, cudaStream_t st) {
+  constexpr int B = 256;
+  constexpr int smem = ThreadCfg<B>::SMEM;
+  auto k0 = tokenize_thread_kernel<B, 0, true, true>;
+  auto k2 = tokenize_thread_kernel<B, 2, true, true>;
+  static bool configured = false;
+  static int per_sm0 = 1, per_sm2 = 1;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm0, k0, B, smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k2, B, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const bool cap2 = a.v.capcode == 2;
+  const long long want = (static_cast<long long>(a.n) + B - 1) / B;
+  const long long full = static_cast<long long>(sms) * (cap2 ? per_sm2 : per_sm0);
+  const int grid = int(want < full ? (want < 1 ? 1 : want) : full);
+  if (cap2) k2<<<grid, B, smem, st>>>(a);
+  else k0<<<grid, B, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chunk_stitch(const StitchArgs& a, int sms, cudaStream_t st) {
+  chunk_stitch_kernel<<<sms, 128, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chunk_gather(const ChunkItem* items, uint32_t total, const uint32_t* c_ids, uint32_t c_cap,
+                                const uint32_t* seg_begin, const uint32_t* seg_end, const uint32_t* seg_dst,
+                                const int64_t* off, uint32_t slab_pad, uint32_t* slab, int sms, cudaStream_t st) {
+  chunk_gather_kernel<<<sms * 8, 256, 0, st>>>(items, total, c_ids, c_cap, seg_begin, seg_end, seg_dst, off, slab_pad,
+                                               slab);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chunk_failed(const uint8_t* doc_fail, const uint32_t* n_chunks, const int64_t* off,
+                                const int64_t* ends, uint32_t n, uint32_t* list, int64_t* f_begin, int64_t* f_end,
+                                unsigned long long* ctr, int sms, cudaStream_t st) {
+  chunk_failed_kernel<<<sms * 2, 256, 0, st>>>(doc_fail, n_chunks, off, ends, n, list, f_begin, f_end, ctr);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_pack(const uint32_t* slab, const int64_t* off, uint32_t slab_pad, const uint64_t* slab_off,

@@ -10,6 +10,20 @@
 
 namespace tmgpu {
 
+// ---- long documents cut into speculative chunks (chunking.cuh) ---------------------------------
+struct ChunkItem {
+  int64_t start;     // byte offset of the chunk's first byte in `data`
+  int64_t next;      // start of the document's next chunk (document end for the last one)
+  uint32_t doc;      // string index
+  uint32_t flags;    // bit 0: last chunk of its document
+};
+struct ChunkOut {
+  uint32_t cnt;      // ids logged (capped at the chunk's capacity)
+  uint32_t n_norm;   // normalized bytes between this chunk's start and the next chunk's start
+  uint32_t miss;     // characters without a token over the whole run
+  uint32_t flags;    // 1 non-ASCII seen, 2 log overflow, 4 ran to the end of the document
+};
+
 struct TokenizeArgs {
   VocabDev v;
   const uint8_t* data;       // all strings back to back (16-byte aligned base)
@@ -32,6 +46,13 @@ struct TokenizeArgs {
   const int64_t* raw_off;    // with list: the strings' own offsets (slab placement and capacity)
   const int64_t* raw_ends;
   uint32_t prenorm;          // text is already normalized: no ASCII check, no case folding, CAP = 0
+  const uint8_t* skip;       // optional: strings another launch handles (documents tokenized in chunks)
+  // chunk launch (tokenize_thread_kernel<.., CHUNK = true>): n = number of chunks
+  const ChunkItem* chunks;
+  uint32_t* c_pos;           // per logged id: normalized position | forward-delete << 31 of its step
+  uint32_t* c_miss;          // per logged id: characters without a token before its step
+  ChunkOut* c_out;
+  uint32_t c_cap, c_ov;      // log capacity per chunk; how far a chunk runs past the next one's start
   const unsigned long long* watermark;  // optional: input bytes that have landed in `data` so far (host path
                              // streams the batch in while the kernel runs); NULL = everything is there
 };
@@ -47,6 +68,47 @@ cudaError_t launch_pack(const uint32_t* slab, const int64_t* off, uint32_t slab_
 // reply framing of the server protocol: [u32 n] then per string [u64 byte length][unit * items]
 cudaError_t launch_wire_frame(const uint8_t* src, const uint64_t* src_off, uint32_t unit, uint32_t n, uint8_t* dst,
                               int sms, cudaStream_t st);
+// long documents in chunks (chunking.cuh)
+struct StitchArgs {
+  const int64_t* off;            // documents
+  const int64_t* ends;
+  uint32_t n;
+  const uint32_t* n_chunks;      // per document
+  const uint64_t* chunk_base;    // exclusive scan of n_chunks
+  const ChunkOut* c_out;
+  const uint32_t* c_pos;
+  const uint32_t* c_miss;
+  uint32_t c_cap;
+  uint32_t slab_pad;
+  uint32_t count_mode;           // Vocab.Count: the delete token of a two-id step is not counted
+  uint8_t* doc_fail;             // in: planning failed; out: 1 = tokenize this document with one lane
+  // per chunk: the kept range of its log and where it goes in the document's slab slot
+  uint32_t* seg_begin;
+  uint32_t* seg_end;
+  uint32_t* seg_dst;
+  // per document
+  uint32_t* counts;
+  uint32_t* need;
+  uint32_t* missing;
+  uint8_t* status;
+  uint32_t* overflow;
+};
+
+uint32_t chunk_log_capacity();
+uint32_t chunk_overlap();
+cudaError_t launch_chunk_count(const int64_t* off, const int64_t* ends, uint32_t n, uint32_t* n_chunks, uint8_t* skip,
+                               int sms, cudaStream_t st);
+cudaError_t launch_chunk_fill(const uint8_t* data, const int64_t* off, const int64_t* ends, uint32_t n,
+                              const uint32_t* n_chunks, const uint64_t* chunk_base, uint32_t total, ChunkItem* items,
+                              uint8_t* doc_fail, int sms, cudaStream_t st);
+cudaError_t launch_tokenize_chunks(const TokenizeArgs& a, int sms, cudaStream_t st);
+cudaError_t launch_chunk_stitch(const StitchArgs& a, int sms, cudaStream_t st);
+cudaError_t launch_chunk_gather(const ChunkItem* items, uint32_t total, const uint32_t* c_ids, uint32_t c_cap,
+                                const uint32_t* seg_begin, const uint32_t* seg_end, const uint32_t* seg_dst,
+                                const int64_t* off, uint32_t slab_pad, uint32_t* slab, int sms, cudaStream_t st);
+cudaError_t launch_chunk_failed(const uint8_t* doc_fail, const uint32_t* n_chunks, const int64_t* off,
+                                const int64_t* ends, uint32_t n, uint32_t* list, int64_t* f_begin, int64_t* f_end,
+                                unsigned long long* ctr, int sms, cudaStream_t st);
 cudaError_t launch_select_refused(const uint8_t* status, const int64_t* off, const int64_t* ends, uint32_t n,
                                   uint32_t* list, int64_t* n_begin, unsigned long long* ctr, int sms,
                                   cudaStream_t st);

@@ -57,7 +57,13 @@ struct ThreadCfg {
   static constexpr int SMEM = WARP_BASE + WARPS * WARP_BYTES;
 };
 
-template <int BLOCK, int CAP, bool STORE>
+// CHUNK = true: the work items are speculative chunks of long documents (chunking.cuh).  A chunk
+// starts at a byte offset where the capcode encoder's state is known to be the initial one (right
+// after a non-alphanumeric, non-space, non-apostrophe ASCII character), assumes that a token
+// starts there, and runs OV normalized bytes past the start of the next chunk; every emitted id
+// is logged with the normalized position (and forward-delete flag) of the step that emitted it,
+// so that a stitch kernel can find the step where this chunk's sequence joins the next chunk's.
+template <int BLOCK, int CAP, bool STORE, bool CHUNK = false>
 __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const TokenizeArgs A) {
   using Cfg = ThreadCfg<BLOCK>;
   constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -112,6 +118,10 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
   uint32_t idx = 0;
   bool have = false;
   uint32_t cnt = 0, miss = 0;
+  // CHUNK: aligned raw coordinate where the next chunk starts, the normalized length up to there
+  // (-1 until the encoder has passed it), and whether this is the document's last chunk
+  int cross_c = 0, n_norm = -1;
+  bool last_chunk = false;
 
   auto load16 = [&](int c0) -> uint4 {           // raw bytes [c0, c0+16) of the aligned stream
     if (c0 + 16 <= total_c) return __ldg(reinterpret_cast<const uint4*>(ga + c0));
@@ -129,8 +139,14 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
     if ((m0 | m1 | m2 | m3) & 0x80808080u) bad = true;
     if (to_lower) { w.x = lower4(w.x); w.y = lower4(w.y); w.z = lower4(w.z); w.w = lower4(w.w); }
   };
-  auto emit = [&](uint32_t id) {
-    if (STORE && cnt < cap) A.slab[slab_base + cnt] = id;
+  auto emit = [&](uint32_t id, uint32_t pos_code = 0) {
+    if (STORE && cnt < cap) {
+      A.slab[slab_base + cnt] = id;
+      if (CHUNK) {
+        A.c_pos[slab_base + cnt] = pos_code;
+        A.c_miss[slab_base + cnt] = miss;
+      }
+    }
     cnt++;
   };
 
@@ -143,16 +159,30 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
         no_more = true;
       } else if (A.list && A.ends[item] < A.off[item]) {
         // the normalizer refused this string: its status 13 from the first pass stands
+      } else if (!CHUNK && A.skip && A.skip[item]) {
+        // a long document that is tokenized in chunks by another launch
       } else {
         s = A.list ? A.list[item] : item;
-        const int64_t o0 = A.off[item];
-        slen = int((A.ends ? A.ends[item] : A.off[item + 1]) - o0);
+        int64_t o0 = A.off[CHUNK ? 0 : item];
+        if (CHUNK) {
+          const ChunkItem ci = A.chunks[item];
+          o0 = ci.start;
+          slen = int((A.ends ? A.ends[ci.doc] : A.off[ci.doc + 1]) - o0);
+          last_chunk = (ci.flags & 1u) != 0;
+          n_norm = (CAP == 0 && !last_chunk) ? int(ci.next - ci.start) : -1;
+          cross_c = int(ci.next - ci.start);           // + galign below
+        } else {
+          slen = int((A.ends ? A.ends[item] : A.off[item + 1]) - o0);
+        }
         if (A.watermark) {   // the batch is still streaming in: wait until this string has landed
           const unsigned long long need_bytes = static_cast<unsigned long long>(o0 + slen);
           while (*reinterpret_cast<const volatile unsigned long long*>(A.watermark) < need_bytes) __nanosleep(500);
         }
         const uint8_t* g0 = A.data + o0;
-        if (A.list) {   // placement follows the string's own (raw) extent, like the first pass
+        if (CHUNK) {
+          slab_base = uint64_t(item) * A.c_cap;
+          cap = A.c_cap;
+        } else if (A.list) {   // placement follows the string's own (raw) extent, like the first pass
           const int64_t r0 = A.raw_off[s];
           const int64_t r1 = A.raw_ends ? A.raw_ends[s] : A.raw_off[s + 1];
           slab_base = A.slab_off ? A.slab_off[s] : uint64_t(r0 - A.raw_off[0]) + uint64_t(A.slab_pad) * s;
@@ -163,6 +193,7 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
         }
         galign = int(reinterpret_cast<uintptr_t>(g0) & 15);
         ga = g0 - galign;
+        if (CHUNK) cross_c += galign;
         cshift = (CAP == 0) ? galign : 0;
         total_c = galign + slen;
         filled = 0; bad = false;
@@ -301,6 +332,7 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
             ow = uint32_t(acc);
           }
           filled = nf;
+          if (CHUNK && rc == cross_c && n_norm < 0 && !last_chunk) n_norm = filled;
           // carries
           in_word = (cl == CL_U) ? true : ((cl == CL_L || cl == CL_O) ? false : in_word);
           cl2 = cl1;
@@ -314,7 +346,8 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
     // ============================ step setup ===================================================
     const bool exhausted = (CAP == 0) ? true : (rc >= total_c);
     const int len_data = (CAP == 0) ? slen : (exhausted ? filled : 0x3FFFFFFF);
-    const bool finished = running && (bad || i >= len_data);
+    const bool past = CHUNK && !last_chunk && n_norm >= 0 && i >= n_norm + int(A.c_ov);
+    const bool finished = running && (bad || i >= len_data || past);
     const bool stepping = running && !finished;
     const bool seek = stepping && !have;           // this iteration only finds the current token
     uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
@@ -466,7 +499,7 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
     // ============================ SCORE + PICK =================================================
     if (seek) {
       if (l0 == 0) {                                // no token covers this byte (go:1269-1276)
-        if (V.unk != 0xFFFFFFu) emit(V.unk);
+        if (V.unk != 0xFFFFFFu) emit(V.unk, uint32_t(i));
         i++;
         miss++;
         fd = 0;
@@ -521,7 +554,7 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
       }
       const uint32_t id0 = r0.y, id1 = r0.z, id2 = r0.w;
       if (pick < 0) {
-        emit(id0);                                   // go:1265-1267
+        emit(id0, uint32_t(i) | (uint32_t(fd) << 31));   // go:1265-1267
         i += len;
         fd = 0;
         have = (l0 > 0);
@@ -529,15 +562,23 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
         len = l0;
       } else {
         const int br = pick >= 3 ? pick - 3 : pick;
-        emit(br == 0 ? id0 : (br == 1 ? id1 : id2));
-        if (pick >= 3 && STORE) emit(V.delete_token);   // Count() adds only 1 here (quirk Q2)
+        emit(br == 0 ? id0 : (br == 1 ? id1 : id2), uint32_t(i) | (uint32_t(fd) << 31));
+        if (pick >= 3 && STORE) emit(V.delete_token, 0xFFFFFFFFu);   // Count() adds only 1 here (quirk Q2)
         i += (br == 0 ? base0 : (br == 1 ? base1 : base2));
         if (pick >= 3) { idx = (br == 0 ? xb0 : (br == 1 ? xb1 : xb2)); len = (br == 0 ? lb0 : (br == 1 ? lb1 : lb2)); fd = 1; }
         else { idx = (br == 0 ? x0 : (br == 1 ? x1 : x2)); len = (br == 0 ? l0 : (br == 1 ? l1 : l2)); fd = 0; }
         have = true;
       }
     }
-    if (finished) {
+    if (finished && CHUNK) {
+      ChunkOut co;
+      co.cnt = min(cnt, cap);
+      co.n_norm = uint32_t(n_norm < 0 ? 0 : n_norm);
+      co.miss = miss;
+      co.flags = (bad ? 1u : 0u) | (cnt > cap ? 2u : 0u) | ((i >= len_data && !bad) ? 4u : 0u);
+      A.c_out[s] = co;
+      running = false;
+    } else if (finished) {
       if (bad) { cnt = 0; miss = 0; }
       A.counts[s] = STORE ? min(cnt, cap) : cnt;
       A.need[s] = cnt;

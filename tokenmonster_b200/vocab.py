@@ -236,6 +236,13 @@ class Vocab:
             lib().tmgpu_bytes_free(res)
         return data, boff
 
+    def last_stats(self) -> dict:
+        """What the latest tokenize / count call did: strings through the non-ASCII normalizer,
+        chunks launched for long documents, chunked documents redone by one lane, kernel launches."""
+        out = (C.c_uint32 * 4)()
+        check(lib().tmgpu_last_stats(self._h, None, C.byref(out)))
+        return dict(unicode_strings=int(out[0]), chunks=int(out[1]), chunk_redo=int(out[2]), launches=int(out[3]))
+
     # ---- server wire format ------------------------------------------------------------
     def _wire(self, fn, payload, *lead):
         buf = np.frombuffer(payload, dtype=np.uint8) if not isinstance(payload, np.ndarray) else payload
