@@ -199,7 +199,7 @@ int tmgpu_tokenize_device(tmgpu_workspace* ws, const uint8_t* d_data, const int6
 int tmgpu_last_launch_count(const tmgpu_workspace* ws);
 /* What the most recent tokenize / count call did besides the plain launch: out[0] strings handled by
  * the non-ASCII normalizer, out[1] chunks launched for long documents (a batch too small to fill
- * the GPU has its documents above 8 KB cut into ~2 KB speculative chunks that are stitched
+ * the GPU has its documents above 4 KB cut into ~1 KB speculative chunks that are stitched
  * exactly), out[2] chunked documents that had to be redone by one lane,
  * out[3] kernels launched.  ws == NULL reports the vocabulary's internal workspace (host calls). */
 int tmgpu_last_stats(const tmgpu_vocab* v, const tmgpu_workspace* ws, uint32_t out[4]);

@@ -100,6 +100,7 @@ struct tmgpu_workspace {
   ChunkOut* ck_out = nullptr;
   uint32_t *ck_ids = nullptr, *ck_pos = nullptr, *ck_miss = nullptr;   // chunks x log capacity
   uint32_t *ck_sb = nullptr, *ck_se = nullptr, *ck_sd = nullptr;
+  uint32_t *ck_ma = nullptr, *ck_mb = nullptr, *ck_dl = nullptr, *ck_sm = nullptr, *ck_fl = nullptr;
   uint64_t ck_chunks_cap = 0;
   std::vector<void*> ck_allocs;
   uint32_t last_chunked = 0, last_chunk_redo = 0;   // chunks launched / documents redone, last launch
@@ -513,7 +514,7 @@ static int chunk_plan(tmgpu_workspace* ws, const TokenizeArgs& a, cudaStream_t s
   uint64_t total = 0;
   CU(cudaMemcpyAsync(&total, ws->ck_base + a.n, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  if (total == 0 || total > (1ull << 21)) return TMGPU_OK;   // nothing long, or far too much for the logs
+  if (total == 0 || total > (1ull << 19)) return TMGPU_OK;   // nothing long, or far too much for the logs
   if (ws->ck_chunks_cap < total) {
     for (void* p : ws->ck_allocs) cudaFree(p);
     ws->ck_allocs.clear();
@@ -531,6 +532,11 @@ static int chunk_plan(tmgpu_workspace* ws, const TokenizeArgs& a, cudaStream_t s
     A(&ws->ck_sb, cap);
     A(&ws->ck_se, cap);
     A(&ws->ck_sd, cap);
+    A(&ws->ck_ma, cap);
+    A(&ws->ck_mb, cap);
+    A(&ws->ck_dl, cap);
+    A(&ws->ck_sm, cap);
+    A(&ws->ck_fl, cap);
     if (rc) return rc;
     ws->ck_chunks_cap = cap;
   }
@@ -558,7 +564,14 @@ static int chunk_run(tmgpu_workspace* ws, const TokenizeArgs& first, uint32_t to
   c.c_ov = chunk_overlap();
   c.work_counter = ws->work_counter + (tmgpu_workspace::kMaxChunks - 2);
   CU(cudaMemsetAsync(c.work_counter, 0, 4, st));
+  static const bool trace = getenv("TMGPU_TRACE") != nullptr;   // diagnostic: phase times on stderr
+  cudaEvent_t te[4] = {};
+  if (trace) {
+    for (auto& e : te) cudaEventCreate(&e);
+    cudaEventRecord(te[0], st);
+  }
   CU(launch_tokenize_chunks(c, v->sms, st));
+  if (trace) cudaEventRecord(te[1], st);
   StitchArgs sa{};
   sa.off = first.off;
   sa.ends = first.ends;
@@ -575,22 +588,38 @@ static int chunk_run(tmgpu_workspace* ws, const TokenizeArgs& first, uint32_t to
   sa.seg_begin = ws->ck_sb;
   sa.seg_end = ws->ck_se;
   sa.seg_dst = ws->ck_sd;
+  sa.meet_a = ws->ck_ma;
+  sa.meet_b = ws->ck_mb;
+  sa.seg_dels = ws->ck_dl;
+  sa.seg_miss = ws->ck_sm;
+  sa.seg_flag = ws->ck_fl;
   sa.counts = first.counts;
   sa.need = first.need;
   sa.missing = first.missing;
   sa.status = first.status;
   sa.overflow = first.overflow;
-  CU(launch_chunk_stitch(sa, v->sms, st));
+  CU(launch_chunk_stitch(sa, total, ws->ck_items, v->sms, st));
+  if (trace) cudaEventRecord(te[2], st);
   if (mode == 0)
     CU(launch_chunk_gather(ws->ck_items, total, ws->ck_ids, c.c_cap, ws->ck_sb, ws->ck_se, ws->ck_sd, first.off,
                            first.slab_pad, first.slab, v->sms, st));
+  if (trace) {
+    cudaEventRecord(te[3], st);
+    cudaEventSynchronize(te[3]);
+    float t0 = 0, t1 = 0, t2 = 0;
+    cudaEventElapsedTime(&t0, te[0], te[1]);
+    cudaEventElapsedTime(&t1, te[1], te[2]);
+    cudaEventElapsedTime(&t2, te[2], te[3]);
+    fprintf(stderr, "[tmgpu] chunks: %u, tokenize %.3f ms, stitch %.3f ms, gather %.3f ms\n", total, t0, t1, t2);
+    for (auto& e : te) cudaEventDestroy(e);
+  }
   CU(cudaMemsetAsync(ws->ck_ctr, 0, 8, st));
   CU(launch_chunk_failed(ws->ck_fail, ws->ck_n, first.off, first.ends, first.n, ws->ck_list, ws->ck_fb, ws->ck_fe,
                          ws->ck_ctr, v->sms, st));
   unsigned long long redo = 0;
   CU(cudaMemcpyAsync(&redo, ws->ck_ctr, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  ws->last_launches += 5 + (mode == 0 ? 1 : 0);
+  ws->last_launches += 7 + (mode == 0 ? 1 : 0);
   ws->last_chunked = total;
   ws->last_chunk_redo = uint32_t(redo);
   if (redo) {   // one lane per document, the ordinary way

@@ -30,10 +30,12 @@
 
 namespace tmgpu {
 
-constexpr uint32_t kChunkBytes = 2048;     // nominal raw bytes per chunk
+constexpr uint32_t kChunkBytes = 1024;     // nominal raw bytes per chunk
 constexpr uint32_t kChunkMin = 4 * kChunkBytes;
-constexpr uint32_t kChunkOverlap = 384;    // normalized bytes a chunk runs into its successor
-constexpr uint32_t kChunkLogCap = 3 * kChunkBytes + kChunkOverlap + 64;   // ids logged per chunk
+constexpr uint32_t kChunkOverlap = 256;    // normalized bytes a chunk runs into its successor
+// ids logged per chunk (a chunk spans up to 1.5 x kChunkBytes raw bytes; text that yields more ids
+// than this -- alternating case under capcode -- sends the document to the one-lane path)
+constexpr uint32_t kChunkLogCap = kChunkBytes + kChunkBytes / 2 + kChunkOverlap + 64;
 
 __device__ __forceinline__ bool chunk_safe_after(uint32_t c) {
   // ASCII, not alphanumeric, not a space, not an apostrophe: the capcode encoder is "reset" behind it
@@ -91,86 +93,122 @@ __global__ void __launch_bounds__(256) chunk_fill_kernel(const uint8_t* __restri
   }
 }
 
-// one thread per chunked document, chunks in order
-__global__ void __launch_bounds__(128) chunk_stitch_kernel(const StitchArgs A) {
+// ---- stitch, in three small kernels --------------------------------------------------------------
+// A  (one thread per chunk)  where this chunk's log meets its successor's
+// B  (one warp per chunk)    the kept range [begin, end) of the chunk and its tallies
+// C  (one thread per document) running offsets, totals, verdict
+constexpr uint32_t kMeetNone = 0xFFFFFFFFu;   // the two logs never met
+constexpr uint32_t kMeetEnd = 0xFFFFFFFEu;    // no successor needed (last chunk, or ran to the document's end)
+
+__global__ void __launch_bounds__(128) chunk_meet_kernel(const StitchArgs A, uint32_t total_chunks,
+                                                         const ChunkItem* __restrict__ items) {
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < total_chunks; c += gridDim.x * blockDim.x) {
+    const ChunkOut co = A.c_out[c];
+    uint32_t ma = kMeetNone, mb = 0;
+    if ((items[c].flags & 1u) || (co.flags & 4u)) {
+      ma = kMeetEnd;
+    } else if ((co.flags & 3u) == 0) {
+      const ChunkOut cn = A.c_out[c + 1];
+      if ((cn.flags & 3u) == 0) {
+        const uint32_t* pos = A.c_pos + uint64_t(c) * A.c_cap;
+        const uint32_t* pn = A.c_pos + uint64_t(c + 1) * A.c_cap;
+        // the steps at or beyond the successor's start are at the tail of the log: walk back to the first
+        uint32_t a = co.cnt;
+        while (a > 0) {
+          const uint32_t p = pos[a - 1];
+          if (p != 0xFFFFFFFFu && (p & 0x7FFFFFFFu) < co.n_norm) break;
+          a--;
+        }
+        uint32_t b = 0;
+        while (a < co.cnt && b < cn.cnt) {   // two pointers over (position relative to the successor, fd)
+          const uint32_t pa = pos[a], pb = pn[b];
+          if (pa == 0xFFFFFFFFu) { a++; continue; }
+          if (pb == 0xFFFFFFFFu) { b++; continue; }
+          const uint32_t ra = (pa & 0x7FFFFFFFu) - co.n_norm, xb = pb & 0x7FFFFFFFu;
+          if (ra == xb && (pa >> 31) == (pb >> 31)) { ma = a; mb = b; break; }
+          if (ra < xb || (ra == xb && (pa >> 31) < (pb >> 31))) a++; else b++;
+        }
+      }
+    }
+    A.meet_a[c] = ma;
+    A.meet_b[c] = mb;
+  }
+}
+
+__global__ void __launch_bounds__(256) chunk_segment_kernel(const StitchArgs A, uint32_t total_chunks,
+                                                            const ChunkItem* __restrict__ items) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < total_chunks; c += warps) {
+    const ChunkOut co = A.c_out[c];
+    const uint32_t d = items[c].doc;
+    const bool first = (uint64_t(c) == A.chunk_base[d]);
+    const uint32_t ma = A.meet_a[c];
+    uint32_t flag = (co.flags & 1u) ? 1u : ((co.flags & 2u) ? 2u : 0u);   // 1 non-ASCII, 2 cannot stitch
+    uint32_t begin = 0, end = co.cnt;
+    if (!first) {
+      if (A.meet_a[c - 1] == kMeetNone) flag |= 2u; else begin = A.meet_b[c - 1];
+    }
+    if (ma == kMeetNone) flag |= 2u;
+    else if (ma != kMeetEnd) end = ma;
+    if (end < begin) flag |= 2u;
+    uint32_t dels = 0;
+    const uint32_t* pos = A.c_pos + uint64_t(c) * A.c_cap;
+    if (!(flag & 2u) && A.count_mode)
+      for (uint32_t t = begin + lane; t < end; t += 32) dels += (pos[t] == 0xFFFFFFFFu);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) dels += __shfl_xor_sync(0xFFFFFFFFu, dels, o);
+    if (lane == 0) {
+      const uint32_t* cm = A.c_miss + uint64_t(c) * A.c_cap;
+      uint32_t miss = 0;
+      if (!(flag & 2u)) miss = ((end < co.cnt) ? cm[end] : co.miss) - ((begin < co.cnt) ? cm[begin] : co.miss);
+      A.seg_begin[c] = begin;
+      A.seg_end[c] = (flag & 2u) ? begin : end;
+      A.seg_dels[c] = dels;
+      A.seg_miss[c] = miss;
+      A.seg_flag[c] = flag | (ma == kMeetEnd ? 4u : 0u);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) chunk_finish_kernel(const StitchArgs A) {
   for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d < A.n; d += gridDim.x * blockDim.x) {
     const uint32_t nc = A.n_chunks[d];
     if (nc == 0) continue;
     const uint64_t c0 = A.chunk_base[d];
-    bool fail = A.doc_fail[d] != 0, bad = false;
-    uint32_t begin = 0;            // first kept step of the current chunk
-    uint64_t total = 0, counted = 0, miss = 0;
-    for (uint32_t k = 0; k < nc && !fail; k++) {
-      const ChunkOut co = A.c_out[c0 + k];
-      const uint32_t* pos = A.c_pos + (c0 + k) * uint64_t(A.c_cap);
-      const uint32_t* cm = A.c_miss + (c0 + k) * uint64_t(A.c_cap);
-      if (co.flags & 1u) { bad = true; break; }
-      if (co.flags & 2u) { fail = true; break; }
-      uint32_t end = co.cnt, next_begin = 0;
-      bool done = (k + 1 == nc) || (co.flags & 4u);   // this chunk reached the end of the document
-      if (!done) {
-        const ChunkOut cn = A.c_out[c0 + k + 1];
-        const uint32_t* pn = A.c_pos + (c0 + k + 1) * uint64_t(A.c_cap);
-        if ((cn.flags & 3u) != 0) { if (cn.flags & 1u) bad = true; else fail = true; break; }
-        // two-pointer walk: a over this chunk's steps at or beyond the next chunk's start, b over the
-        // next chunk's steps; keys are (position relative to the next chunk's start, fd flag)
-        uint32_t a = begin, b = 0;
-        bool met = false;
-        while (a < co.cnt && b < cn.cnt) {
-          const uint32_t pa = pos[a], pb = pn[b];
-          if (pa == 0xFFFFFFFFu) { a++; continue; }
-          if (pb == 0xFFFFFFFFu) { b++; continue; }
-          const uint32_t xa = pa & 0x7FFFFFFFu, xb = pb & 0x7FFFFFFFu;
-          if (xa < co.n_norm) { a++; continue; }
-          const uint32_t ra = xa - co.n_norm;
-          if (ra == xb && (pa >> 31) == (pb >> 31)) { met = true; break; }
-          if (ra < xb || (ra == xb && (pa >> 31) < (pb >> 31))) a++; else b++;
-        }
-        if (!met) { fail = true; break; }
-        end = a;
-        next_begin = b;
-      }
-      A.seg_begin[c0 + k] = begin;
-      A.seg_end[c0 + k] = end;
-      A.seg_dst[c0 + k] = uint32_t(total);
-      total += end - begin;
-      if (A.count_mode) {
-        for (uint32_t t = begin; t < end; t++) counted += (pos[t] != 0xFFFFFFFFu);
-      }
-      // characters without a token inside the kept range: cumulative counter at its two ends
-      const uint32_t m_end = (end < co.cnt) ? cm[end] : co.miss;
-      const uint32_t m_begin = (begin < co.cnt) ? cm[begin] : co.miss;
-      miss += m_end - m_begin;
-      if (done) {
-        for (uint32_t r = k + 1; r < nc; r++) { A.seg_begin[c0 + r] = 0; A.seg_end[c0 + r] = 0; A.seg_dst[c0 + r] = 0; }
-        break;
-      }
-      begin = next_begin;
+    bool fail = A.doc_fail[d] != 0, bad = false, done = false;
+    uint64_t total = 0, dels = 0, miss = 0;
+    for (uint32_t k = 0; k < nc; k++) {
+      const uint64_t c = c0 + k;
+      if (done || fail || bad) { A.seg_end[c] = A.seg_begin[c]; continue; }   // dropped: nothing to gather
+      const uint32_t f = A.seg_flag[c];
+      if (f & 1u) { bad = true; A.seg_end[c] = A.seg_begin[c]; continue; }
+      if (f & 2u) { fail = true; A.seg_end[c] = A.seg_begin[c]; continue; }
+      A.seg_dst[c] = uint32_t(total);
+      total += A.seg_end[c] - A.seg_begin[c];
+      dels += A.seg_dels[c];
+      miss += A.seg_miss[c];
+      if (f & 4u) done = true;
     }
-    if (bad) {              // non-ASCII text: status 13 here, the non-ASCII pass picks it up
-      for (uint32_t r = 0; r < nc; r++) { A.seg_begin[c0 + r] = 0; A.seg_end[c0 + r] = 0; A.seg_dst[c0 + r] = 0; }
-      A.counts[d] = 0; A.need[d] = 0; A.missing[d] = 0; A.status[d] = 13;
-      A.doc_fail[d] = 0;
-      continue;
-    }
-    if (fail) {
-      for (uint32_t r = 0; r < nc; r++) { A.seg_begin[c0 + r] = 0; A.seg_end[c0 + r] = 0; A.seg_dst[c0 + r] = 0; }
-      A.doc_fail[d] = 1;
-      continue;
-    }
-    A.doc_fail[d] = 0;
     const int64_t len = (A.ends ? A.ends[d] : A.off[d + 1]) - A.off[d];
     const uint64_t cap = uint64_t(len) + A.slab_pad;
-    const uint64_t value = A.count_mode ? counted : total;
-    A.need[d] = uint32_t(value);
-    A.missing[d] = uint32_t(miss);
-    A.status[d] = 0;
-    if (!A.count_mode && total > cap) {      // more ids than the slab slot holds: exact-size re-run
-      for (uint32_t r = 0; r < nc; r++) { A.seg_begin[c0 + r] = 0; A.seg_end[c0 + r] = 0; A.seg_dst[c0 + r] = 0; }
-      A.counts[d] = uint32_t(cap);
-      atomicExch(A.overflow, 1u);
+    const bool too_big = !A.count_mode && total > cap;   // more ids than the slab slot holds: exact-size re-run
+    if (bad || fail || too_big) {
+      for (uint32_t k = 0; k < nc; k++) A.seg_end[c0 + k] = A.seg_begin[c0 + k];
+    }
+    if (bad) {              // non-ASCII text: status 13 here, the non-ASCII pass picks the document up
+      A.counts[d] = 0; A.need[d] = 0; A.missing[d] = 0; A.status[d] = 13;
+      A.doc_fail[d] = 0;
+    } else if (fail) {
+      A.doc_fail[d] = 1;
     } else {
-      A.counts[d] = uint32_t(value);
+      A.doc_fail[d] = 0;
+      const uint64_t value = A.count_mode ? total - dels : total;
+      A.need[d] = uint32_t(value);
+      A.missing[d] = uint32_t(miss);
+      A.status[d] = 0;
+      A.counts[d] = too_big ? uint32_t(cap) : uint32_t(value);
+      if (too_big) atomicExch(A.overflow, 1u);
     }
   }
 }

@@ -438,8 +438,11 @@ cudaError_t launch_tokenize_chunks(const TokenizeArgs& a, int sms, cudaStream_t 
   return cudaGetLastError();
 }
 
-cudaError_t launch_chunk_stitch(const StitchArgs& a, int sms, cudaStream_t st) {
-  chunk_stitch_kernel<<<sms, 128, 0, st>>>(a);
+cudaError_t launch_chunk_stitch(const StitchArgs& a, uint32_t total_chunks, const ChunkItem* items, int sms,
+                                cudaStream_t st) {
+  chunk_meet_kernel<<<sms * 2, 128, 0, st>>>(a, total_chunks, items);
+  chunk_segment_kernel<<<sms * 4, 256, 0, st>>>(a, total_chunks, items);
+  chunk_finish_kernel<<<sms, 128, 0, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -83,9 +83,14 @@ struct StitchArgs {
   uint32_t count_mode;           // Vocab.Count: the delete token of a two-id step is not counted
   uint8_t* doc_fail;             // in: planning failed; out: 1 = tokenize this document with one lane
   // per chunk: the kept range of its log and where it goes in the document's slab slot
+  uint32_t* meet_a;              // step of this chunk's log where it meets its successor's ...
+  uint32_t* meet_b;              // ... and the successor's step there
   uint32_t* seg_begin;
   uint32_t* seg_end;
   uint32_t* seg_dst;
+  uint32_t* seg_dels;            // delete-token entries in the kept range (not counted by Vocab.Count)
+  uint32_t* seg_miss;            // characters without a token in the kept range
+  uint32_t* seg_flag;            // 1 non-ASCII, 2 cannot stitch, 4 document ends with this chunk
   // per document
   uint32_t* counts;
   uint32_t* need;
@@ -102,7 +107,8 @@ cudaError_t launch_chunk_fill(const uint8_t* data, const int64_t* off, const int
                               const uint32_t* n_chunks, const uint64_t* chunk_base, uint32_t total, ChunkItem* items,
                               uint8_t* doc_fail, int sms, cudaStream_t st);
 cudaError_t launch_tokenize_chunks(const TokenizeArgs& a, int sms, cudaStream_t st);
-cudaError_t launch_chunk_stitch(const StitchArgs& a, int sms, cudaStream_t st);
+cudaError_t launch_chunk_stitch(const StitchArgs& a, uint32_t total_chunks, const ChunkItem* items, int sms,
+                                cudaStream_t st);
 cudaError_t launch_chunk_gather(const ChunkItem* items, uint32_t total, const uint32_t* c_ids, uint32_t c_cap,
                                 const uint32_t* seg_begin, const uint32_t* seg_end, const uint32_t* seg_dst,
                                 const int64_t* off, uint32_t slab_pad, uint32_t* slab, int sms, cudaStream_t st);
