@@ -123,6 +123,19 @@ void tmgpu_result_free(tmgpu_result* r);
 int tmgpu_count_batch(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off, uint32_t n,
                       uint64_t* counts, uint32_t* missing, uint8_t* status);
 
+/* ---- training worker loop (training/trainvocab.go:932-1170) ---------------------------------
+ * What `worker()` computes for one candidate vocabulary over its data strips: the same branch
+ * decisions as Vocab.tokenize (the two loops are textual copies), accumulated instead of emitted:
+ *   scores[id] += characters the chosen token covers (scores[deleteToken]++ for a retry branch,
+ *                 :1109-1162); n_reverse entries, overwritten
+ *   *tokens_in_text = tokens used (a retry branch counts 2, a byte without a token 1, :1164-1171)
+ *   miss_hist[b]    = how often byte value b had no token (the worker's missingList, as a
+ *                     histogram); 256 entries, may be NULL
+ * The candidate is passed as a vocabulary (tmgpu_vocab_create on the .vocab layout of its
+ * tokenInfo table); strings are the data strips.  status[] as for tmgpu_tokenize_batch (NULL ok). */
+int tmgpu_score_batch(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off, uint32_t n,
+                      uint64_t* scores, uint64_t* miss_hist, uint64_t* tokens_in_text, uint8_t* status);
+
 /* ---- batched Vocab.Decode / DecodeSerialized (go:788-811; server jobs 2-4, :420-433) -----
  * tokens: ids packed enc_len (2/3/4) bytes each, strings back to back; tok_off[n+1] in ids.
  * Out-of-range ids and nil reverse entries decode to nothing (go:813-834). */

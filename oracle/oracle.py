@@ -67,6 +67,8 @@ def _bind(path: str, p: str):
     if p == "tmr_":
         api["tokenize_batch"] = f("tokenize_batch", C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.POINTER(C.c_uint64)])
     else:
+        api["score"] = f("score", C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.POINTER(C.c_uint64)])
         api["longest_prefix"] = f("longest_prefix", C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32)])
         api["capcode_encode"] = f("capcode_encode", C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)])
         api["incomplete_utf8"] = f("incomplete_utf8", C.c_int, [C.c_char_p, C.c_size_t])
@@ -152,6 +154,19 @@ class OracleVocab:
         if mode == 0:
             return np.frombuffer(raw, dtype=np.uint32).copy(), miss.value
         return raw, miss.value
+
+    def score(self, texts, normalized: bool = False):
+        """The training worker's loop (training/trainvocab.go:932-1170) over a list of byte strings
+        -> (scores uint64[n_reverse], miss_hist uint64[256], tokens_in_text).  Port only."""
+        scores = np.zeros(max(int(self.n_reverse), 1), np.uint64)
+        hist = np.zeros(256, np.uint64)
+        total = C.c_uint64(0)
+        for t in texts:
+            st = self.api["score"](self.h, t, len(t), int(normalized), scores.ctypes.data, hist.ctypes.data,
+                                   C.byref(total))
+            if st:
+                raise OracleError(st, "score")
+        return scores, hist, int(total.value)
 
     def decode(self, tokens, enc_len: int = 0, raw: bool = False) -> bytes:
         keep, ptr, cnt = _as_tokens_arg(tokens, enc_len)

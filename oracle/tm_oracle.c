@@ -361,13 +361,21 @@ int tmo_normalize(const tmo_vocab* v, const uint8_t* in, size_t n, uint8_t** out
 /* ------------------------------------------------------------------ tokenize */
 
 typedef struct {
-  int mode; /* 0 ids, 1 count, 2/3/4 serialized */
+  int mode; /* 0 ids, 1 count, 2/3/4 serialized, 5 training scores (training/trainvocab.go:932-1170) */
   uint8_t* p;
   size_t n_ids, bytes, cap;
+  uint64_t* scores;    /* mode 5: characters covered per token id */
+  uint64_t* miss_hist; /* mode 5: occurrences of each byte value no token covers */
 } sink;
 
-static void emit(sink* s, uint32_t id) {
+/* adv = characters the step advances by: what the training worker adds to scores[id]
+ * (trainvocab.go:1109-1162; 1 for the delete token, :1134) */
+static void emit(sink* s, uint32_t id, int adv) {
   s->n_ids++;
+  if (s->mode == 5) {
+    if (id != TMO_DNE) s->scores[id] += (uint64_t)adv;
+    return;
+  }
   if (s->mode == 1) return;
   size_t w = s->mode == 0 ? 4 : (size_t)s->mode;
   if (s->bytes + 4 > s->cap) {
@@ -456,7 +464,12 @@ static void tokenize_core(const tmo_vocab* v, const uint8_t* data, int len_data,
     int room = len_data - i;
     int length = tmo_longest_prefix(v, data + i, (size_t)(room < v->max_len ? room : v->max_len), &index);
     if (length == 0) {
-      if (v->unk != TMO_DNE) emit(out, v->unk);
+      if (out->mode == 5) { /* trainvocab.go:1164-1171: counted, never scored */
+        out->n_ids++;
+        out->miss_hist[data[i]]++;
+      } else if (v->unk != TMO_DNE) {
+        emit(out, v->unk, 0);
+      }
       i++;
       missing++;
       fd = 0;
@@ -490,25 +503,25 @@ static void tokenize_core(const tmo_vocab* v, const uint8_t* data, int len_data,
         if (best != NEG) {
           advanced = 1;
           if (best == c1.score) {
-            emit(out, o->id); i += length; index = c1.idx; length = c1.len; fd = 0;
+            emit(out, o->id, length); i += length; index = c1.idx; length = c1.len; fd = 0;
           } else if (best == c2.score) {
-            emit(out, o->id1); i += o->alt_len - fd; index = c2.idx; length = c2.len; fd = 0;
+            emit(out, o->id1, o->alt_len - fd); i += o->alt_len - fd; index = c2.idx; length = c2.len; fd = 0;
           } else if (best == c3.score) {
-            emit(out, o->id2); i += o->alt_len2 - fd; index = c3.idx; length = c3.len; fd = 0;
+            emit(out, o->id2, o->alt_len2 - fd); i += o->alt_len2 - fd; index = c3.idx; length = c3.len; fd = 0;
           } else if (best == c1.score_b) {
-            emit(out, o->id); emit(out, v->delete_token); if (out->mode == 1) out->n_ids--;
+            emit(out, o->id, length); emit(out, v->delete_token, 1); if (out->mode == 1) out->n_ids--;
             i += length; index = c1.idx_b; length = c1.len_b; fd = 1;
           } else if (best == c2.score_b) {
-            emit(out, o->id1); emit(out, v->delete_token); if (out->mode == 1) out->n_ids--;
+            emit(out, o->id1, o->alt_len - fd); emit(out, v->delete_token, 1); if (out->mode == 1) out->n_ids--;
             i += o->alt_len - fd; index = c2.idx_b; length = c2.len_b; fd = 1;
           } else {
-            emit(out, o->id2); emit(out, v->delete_token); if (out->mode == 1) out->n_ids--;
+            emit(out, o->id2, o->alt_len2 - fd); emit(out, v->delete_token, 1); if (out->mode == 1) out->n_ids--;
             i += o->alt_len2 - fd; index = c3.idx_b; length = c3.len_b; fd = 1;
           }
         }
       }
       if (advanced) continue;
-      emit(out, o->id);
+      emit(out, o->id, length);
       i += length;
       fd = 0;
       break;
@@ -535,11 +548,38 @@ int tmo_tokenize(const tmo_vocab* v, const uint8_t* in, size_t n, int normalized
   }
   norm = (uint8_t*)realloc(norm, nn + 1);
   norm[nn] = 0; /* defined look-ahead byte */
-  sink s = {mode, NULL, 0, 0, 0};
+  sink s = {mode, NULL, 0, 0, 0, NULL, NULL};
   tokenize_core(v, norm, (int)nn, &s, missing);
   free(norm);
   *out = s.p;
   *n_tokens = s.n_ids;
+  return TMO_OK;
+}
+
+/* The training worker's tokenization loop (training/trainvocab.go:932-1170): the same branch
+ * decisions as Vocab.tokenize (the two loops are textual copies), but instead of ids it
+ * accumulates scores[id] += characters covered (1 for the delete token), tokensInText (a
+ * two-id step counts 2, a byte without a token counts 1) and the bytes without a token.
+ * scores has n_reverse entries, miss_hist 256; both are ADDED to. */
+int tmo_score(const tmo_vocab* v, const uint8_t* in, size_t n, int normalized, uint64_t* scores,
+              uint64_t* miss_hist, uint64_t* tokens_in_text) {
+  if (v->max_len == 0) return TMO_OK;
+  uint8_t* norm = NULL;
+  size_t nn = n;
+  if (!normalized) {
+    int st = tmo_normalize(v, in, n, &norm, &nn);
+    if (st != TMO_OK) return st;
+  } else {
+    norm = (uint8_t*)malloc(n + 1);
+    memcpy(norm, in, n);
+  }
+  norm = (uint8_t*)realloc(norm, nn + 1);
+  norm[nn] = 0;
+  sink s = {5, NULL, 0, 0, 0, scores, miss_hist};
+  int64_t missing = 0;
+  tokenize_core(v, norm, (int)nn, &s, &missing);
+  free(norm);
+  *tokens_in_text += s.n_ids;
   return TMO_OK;
 }
 

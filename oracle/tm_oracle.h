@@ -83,6 +83,11 @@ int tmo_tokenize(const tmo_vocab* v, const uint8_t* in, size_t n, int normalized
 
 /* ---- decode ---- */
 /* raw != 0 skips the capcode decode (Vocab.decode, go:813). enc_len 0 => u32 ids. */
+/* training worker loop (training/trainvocab.go:932-1170): scores[id] += characters covered,
+ * *tokens_in_text += tokens, miss_hist[byte] += bytes without a token; all three accumulate */
+int tmo_score(const tmo_vocab* v, const uint8_t* in, size_t n, int normalized, uint64_t* scores,
+              uint64_t* miss_hist, uint64_t* tokens_in_text);
+
 int tmo_decode(const tmo_vocab* v, const void* tokens, size_t n_tokens_or_bytes, int enc_len,
                int raw, uint8_t** out, size_t* out_n);
 

@@ -60,6 +60,8 @@ PROTOTYPES = {
     "tmgpu_result_free": (None, [C.POINTER(Result)]),
     "tmgpu_count_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),
+    "tmgpu_score_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                    C.POINTER(C.c_uint64), C.c_void_p]),
     "tmgpu_decode_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8,
                                      C.POINTER(C.POINTER(Bytes))]),
     "tmgpu_bytes_free": (None, [C.POINTER(Bytes)]),

@@ -104,6 +104,7 @@ struct tmgpu_workspace {
   uint64_t ck_chunks_cap = 0;
   std::vector<void*> ck_allocs;
   uint32_t last_chunked = 0, last_chunk_redo = 0;   // chunks launched / documents redone, last launch
+  unsigned long long* score_buf = nullptr;          // training scores: n_reverse ids, then 256 byte values
   // decode
   uint32_t* raw_len = nullptr;  // n + 1
   uint64_t* raw_off = nullptr;  // n + 1
@@ -435,6 +436,7 @@ extern "C" int tmgpu_workspace_create(tmgpu_vocab* v, uint32_t max_strings, uint
   A(&ws->ck_fb, n1);
   A(&ws->ck_fe, n1);
   A(&ws->ck_ctr, 2);
+  A(&ws->score_buf, size_t(v->host.n_reverse) + 256 + 8);
   A(&ws->raw_len, n1);
   A(&ws->raw_off, n1);
   A(&ws->out_len, n1);
@@ -507,7 +509,8 @@ static int chunk_plan(tmgpu_workspace* ws, const TokenizeArgs& a, cudaStream_t s
   ws->last_chunk_redo = 0;
   static const bool off = getenv("TMGPU_NO_CHUNKS") != nullptr;   // diagnostic: one lane per document always
   const HostTables& h = v->host;
-  if (off || a.n == 0 || a.n >= uint32_t(v->sms) * 512u || h.max_len == 0 || h.charset == 2 || a.slab_off) return TMGPU_OK;
+  if (off || a.n == 0 || a.n >= uint32_t(v->sms) * 512u || h.max_len == 0 || h.charset == 2 || a.slab_off || a.scores)
+    return TMGPU_OK;   // (overlapping chunks would be scored twice)
   CU(launch_chunk_count(a.off, a.ends, a.n, ws->ck_n, ws->ck_skip, v->sms, st));
   CU(cudaMemsetAsync(ws->ck_n + a.n, 0, 4, st));
   CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, ws->ck_n, ws->ck_base, a.n + 1, st));
@@ -695,6 +698,7 @@ static int unicode_pass(tmgpu_workspace* ws, const TokenizeArgs& first, bool sto
   b.raw_off = first.off;
   b.raw_ends = first.ends;
   b.prenorm = 1;
+  b.skip = nullptr;
   b.watermark = nullptr;
   b.work_counter = ws->work_counter + (tmgpu_workspace::kMaxChunks - 1);
   CU(cudaMemsetAsync(b.work_counter, 0, 4, st));
@@ -738,6 +742,21 @@ static int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const 
   a.status = ws->status;
   a.work_counter = ws->work_counter;
   a.overflow = ws->overflow;
+  if (mode == 2 && n > 0 && v->host.max_len != 0) {
+    // training scores (trainvocab.go:932-1170): a histogram cannot be rolled back, so strings the
+    // first pass would abandon at a non-ASCII byte are set aside before it starts
+    a.scores = ws->score_buf;
+    a.miss_hist = ws->score_buf + v->host.n_reverse;
+    CU(cudaMemsetAsync(ws->score_buf, 0, (size_t(v->host.n_reverse) + 256) * 8, st));
+    if (v->unicode) {
+      if (chunks)
+        for (const ChunkPlan& c : *chunks)
+          if (c.ready) CU(cudaStreamWaitEvent(st, c.ready, 0));
+      CU(launch_flag_non_ascii(d_data, d_off, d_ends, n, ws->ck_skip, ws->status, ws->counts, ws->missing, v->sms, st));
+      a.skip = ws->ck_skip;
+      ws->last_launches++;
+    }
+  }
   uint32_t ck_total = 0;   // long documents of a small batch are tokenized in chunks (chunking.cuh)
   if (n > 0 && (!chunks || chunks->size() == 1)) {
     if (chunks && (*chunks)[0].ready) CU(cudaStreamWaitEvent(st, (*chunks)[0].ready, 0));
@@ -757,6 +776,7 @@ static int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const 
       TokenizeArgs b = a;
       b.off = d_off + c.s0;
       if (d_ends) b.ends = d_ends + c.s0;
+      if (a.skip) b.skip = a.skip + c.s0;
       b.n = c.s1 - c.s0;
       b.slab = slab + c.slab_base;
       b.counts = ws->counts + c.s0;
@@ -1159,6 +1179,48 @@ extern "C" int tmgpu_count_batch(tmgpu_vocab* v, const uint8_t* data, const uint
     if (missing) missing[i] = m[i];
     if (status) status[i] = s[i];
   }
+  return TMGPU_OK;
+}
+
+// The tokenization loop of the training worker (training/trainvocab.go:932-1170) for one candidate
+// vocabulary over a batch of data strips.
+extern "C" int tmgpu_score_batch(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off, uint32_t n,
+                                 uint64_t* scores, uint64_t* miss_hist, uint64_t* tokens_in_text, uint8_t* status) {
+  if (!v || !off || !scores || !tokens_in_text) {
+    g_err = "tmgpu_score_batch: null argument";
+    return TMGPU_E_ARG;
+  }
+  std::lock_guard<std::mutex> lock(v->mu);
+  int rc = ensure_host_path(v, n, off[n] - off[0]);
+  if (rc) return rc;
+  uint64_t total = 0;
+  std::vector<ChunkPlan> plan;
+  if ((rc = stage_input(v, data, off, n, &total, &plan))) return rc;
+  tmgpu_workspace* ws = v->ws;
+  if ((rc = tokenize_on_stream(ws, v->d_in, v->d_off, n, 0, 2, v->stream, nullptr, ws->slab, ws->tokens, &plan)))
+    return rc;
+  const size_t nr = v->host.n_reverse;
+  std::vector<uint32_t> c(size_t(n) + 1);
+  std::vector<uint8_t> s(size_t(n) + 1);
+  std::vector<unsigned long long> hist(256);
+  if (v->host.max_len == 0) {
+    std::memset(scores, 0, nr * 8);
+    if (miss_hist) std::memset(miss_hist, 0, 256 * 8);
+  } else {
+    CU(cudaMemcpyAsync(scores, ws->score_buf, nr * 8, cudaMemcpyDeviceToHost, v->stream));
+    CU(cudaMemcpyAsync(hist.data(), ws->score_buf + nr, 256 * 8, cudaMemcpyDeviceToHost, v->stream));
+  }
+  CU(cudaMemcpyAsync(c.data(), ws->counts, size_t(n) * 4, cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaMemcpyAsync(s.data(), ws->status, size_t(n), cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaStreamSynchronize(v->stream));
+  uint64_t t = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    t += c[i];
+    if (status) status[i] = s[i];
+  }
+  *tokens_in_text = t;
+  if (miss_hist && v->host.max_len != 0)
+    for (int b = 0; b < 256; b++) miss_hist[b] = hist[b];
   return TMGPU_OK;
 }
 

@@ -365,9 +365,37 @@ static cudaError_t launch_thr(const TokenizeArgs& a, int sms, cudaStream_t st, i
   return cudaGetLastError();
 }
 
+// one warp per string: any byte >= 0x80?
+__global__ void __launch_bounds__(256) flag_non_ascii_kernel(const uint8_t* __restrict__ data,
+                                                             const int64_t* __restrict__ off,
+                                                             const int64_t* __restrict__ ends, uint32_t n,
+                                                             uint8_t* __restrict__ skip, uint8_t* __restrict__ status,
+                                                             uint32_t* __restrict__ counts,
+                                                             uint32_t* __restrict__ missing) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n; s += warps) {
+    const int64_t b0 = off[s], b1 = ends ? ends[s] : off[s + 1];
+    bool hi = false;
+    for (int64_t p = b0 + lane; p < b1; p += 32) hi |= (data[p] & 0x80u) != 0;
+    hi = __any_sync(0xFFFFFFFFu, hi);
+    if (lane == 0) {
+      skip[s] = hi ? 1 : 0;
+      if (hi) { status[s] = 13; counts[s] = 0; missing[s] = 0; }
+    }
+  }
+}
+
+cudaError_t launch_flag_non_ascii(const uint8_t* data, const int64_t* off, const int64_t* ends, uint32_t n,
+                                  uint8_t* skip, uint8_t* status, uint32_t* counts, uint32_t* missing, int sms,
+                                  cudaStream_t st) {
+  flag_non_ascii_kernel<<<sms * 8, 256, 0, st>>>(data, off, ends, n, skip, status, counts, missing);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_tokenize(const TokenizeArgs& a, int group, bool store, int sms, cudaStream_t st, int* grid_out) {
   const int cap = a.prenorm ? 0 : a.v.capcode;   // pre-normalized text is read verbatim
-  if (a.prenorm) group = 1;
+  if (a.prenorm || a.scores) group = 1;          // only the lane-per-string kernel carries these modes
   if (group == 1) {  // one thread per string; big CTAs share a big edge cache when the batch fills them
     static const int forced = getenv("TMGPU_CTA") ? atoi(getenv("TMGPU_CTA")) : 0;  // experiment hook
     int cta = forced ? forced : (a.n >= uint32_t(sms) * 768u ? 1024 : 256);

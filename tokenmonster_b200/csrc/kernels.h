@@ -47,6 +47,10 @@ struct TokenizeArgs {
   const int64_t* raw_ends;
   uint32_t prenorm;          // text is already normalized: no ASCII check, no case folding, CAP = 0
   const uint8_t* skip;       // optional: strings another launch handles (documents tokenized in chunks)
+  // training worker loop (training/trainvocab.go:932-1170), count kernels only: characters covered
+  // per token id, and occurrences of each byte value that no token covers
+  unsigned long long* scores;
+  unsigned long long* miss_hist;
   // chunk launch (tokenize_thread_kernel<.., CHUNK = true>): n = number of chunks
   const ChunkItem* chunks;
   uint32_t* c_pos;           // per logged id: normalized position | forward-delete << 31 of its step
@@ -115,6 +119,11 @@ cudaError_t launch_chunk_gather(const ChunkItem* items, uint32_t total, const ui
 cudaError_t launch_chunk_failed(const uint8_t* doc_fail, const uint32_t* n_chunks, const int64_t* off,
                                 const int64_t* ends, uint32_t n, uint32_t* list, int64_t* f_begin, int64_t* f_end,
                                 unsigned long long* ctr, int sms, cudaStream_t st);
+// strings with a byte >= 0x80: status 13, counts 0, skip 1 (so that a pass with side effects --
+// the score histogram -- never starts on them; the non-ASCII pass then takes them whole)
+cudaError_t launch_flag_non_ascii(const uint8_t* data, const int64_t* off, const int64_t* ends, uint32_t n,
+                                  uint8_t* skip, uint8_t* status, uint32_t* counts, uint32_t* missing, int sms,
+                                  cudaStream_t st);
 cudaError_t launch_select_refused(const uint8_t* status, const int64_t* off, const int64_t* ends, uint32_t n,
                                   uint32_t* list, int64_t* n_begin, unsigned long long* ctr, int sms,
                                   cudaStream_t st);

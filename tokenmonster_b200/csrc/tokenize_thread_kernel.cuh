@@ -139,7 +139,10 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
     if ((m0 | m1 | m2 | m3) & 0x80808080u) bad = true;
     if (to_lower) { w.x = lower4(w.x); w.y = lower4(w.y); w.z = lower4(w.z); w.w = lower4(w.w); }
   };
-  auto emit = [&](uint32_t id, uint32_t pos_code = 0) {
+  // adv = characters the step advances by (what the training worker adds to scores[id],
+  // training/trainvocab.go:1109-1162); only the count kernels carry the histogram
+  auto emit = [&](uint32_t id, uint32_t pos_code = 0, uint32_t adv = 0) {
+    if (!STORE && A.scores) atomicAdd(&A.scores[id], static_cast<unsigned long long>(adv));
     if (STORE && cnt < cap) {
       A.slab[slab_base + cnt] = id;
       if (CHUNK) {
@@ -499,7 +502,12 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
     // ============================ SCORE + PICK =================================================
     if (seek) {
       if (l0 == 0) {                                // no token covers this byte (go:1269-1276)
-        if (V.unk != 0xFFFFFFu) emit(V.unk, uint32_t(i));
+        if (!STORE && A.scores) {                   // trainvocab.go:1164-1171: counted, never scored
+          cnt++;
+          atomicAdd(&A.miss_hist[ring_byte(i + cshift)], 1ull);
+        } else if (V.unk != 0xFFFFFFu) {
+          emit(V.unk, uint32_t(i));
+        }
         i++;
         miss++;
         fd = 0;
@@ -554,7 +562,7 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
       }
       const uint32_t id0 = r0.y, id1 = r0.z, id2 = r0.w;
       if (pick < 0) {
-        emit(id0, uint32_t(i) | (uint32_t(fd) << 31));   // go:1265-1267
+        emit(id0, uint32_t(i) | (uint32_t(fd) << 31), uint32_t(len));   // go:1265-1267
         i += len;
         fd = 0;
         have = (l0 > 0);
@@ -562,8 +570,10 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
         len = l0;
       } else {
         const int br = pick >= 3 ? pick - 3 : pick;
-        emit(br == 0 ? id0 : (br == 1 ? id1 : id2), uint32_t(i) | (uint32_t(fd) << 31));
-        if (pick >= 3 && STORE) emit(V.delete_token, 0xFFFFFFFFu);   // Count() adds only 1 here (quirk Q2)
+        emit(br == 0 ? id0 : (br == 1 ? id1 : id2), uint32_t(i) | (uint32_t(fd) << 31),
+             uint32_t(br == 0 ? base0 : (br == 1 ? base1 : base2)));
+        // Count() adds only 1 here (quirk Q2); the training worker counts and scores the delete token
+        if (pick >= 3 && (STORE || A.scores)) emit(V.delete_token, 0xFFFFFFFFu, 1u);
         i += (br == 0 ? base0 : (br == 1 ? base1 : base2));
         if (pick >= 3) { idx = (br == 0 ? xb0 : (br == 1 ? xb1 : xb2)); len = (br == 0 ? lb0 : (br == 1 ? lb1 : lb2)); fd = 1; }
         else { idx = (br == 0 ? x0 : (br == 1 ? x1 : x2)); len = (br == 0 ? l0 : (br == 1 ? l1 : l2)); fd = 0; }

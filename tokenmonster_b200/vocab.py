@@ -236,6 +236,20 @@ class Vocab:
             lib().tmgpu_bytes_free(res)
         return data, boff
 
+    def score_batch(self, data, off):
+        """The training worker's loop (training/trainvocab.go:932-1170) over a batch of data strips:
+        returns (scores uint64[n_reverse], miss_hist uint64[256], tokens_in_text, status uint8[n])."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        n = len(off) - 1
+        scores = np.zeros(max(int(self.info.n_reverse), 1), np.uint64)
+        hist = np.zeros(256, np.uint64)
+        status = np.zeros(max(n, 1), np.uint8)
+        total = C.c_uint64(0)
+        check(lib().tmgpu_score_batch(self._h, data.ctypes.data if data.size else None, off.ctypes.data, n,
+                                      scores.ctypes.data, hist.ctypes.data, C.byref(total), status.ctypes.data))
+        return scores, hist, int(total.value), status[:n]
+
     def last_stats(self) -> dict:
         """What the latest tokenize / count call did: strings through the non-ASCII normalizer,
         chunks launched for long documents, chunked documents redone by one lane, kernel launches."""
