@@ -239,9 +239,10 @@ extern "C" int tmgpu_vocab_create(const uint8_t* file_bytes, size_t n, int devic
     return fail(TMGPU_E_NOMEM);
   }
   VocabDev& d = v->dev;
-  std::vector<uint8_t> image(1280);
+  std::vector<uint8_t> image(2304);
   std::memcpy(image.data(), h.root_child, 1024);
   std::memcpy(image.data() + 1024, h.begin_byte, 256);
+  std::memcpy(image.data() + 1280, h.sp_child, 1024);
   const uint64_t* edges64 = nullptr;
   if ((rc = upload(v, h.edges.data(), h.edges.size(), &edges64))) return fail(rc);
   d.edges = reinterpret_cast<const uint2*>(edges64);
@@ -251,6 +252,7 @@ extern "C" int tmgpu_vocab_create(const uint8_t* file_bytes, size_t n, int devic
   if ((rc = upload(v, h.rec.data(), h.rec.size(), &recs))) return fail(rc);
   d.rec = reinterpret_cast<const uint4*>(recs);
   if ((rc = upload(v, image.data(), image.size(), &d.smem_image))) return fail(rc);
+  if ((rc = upload(v, h.root2.data(), h.root2.size(), &d.root2))) return fail(rc);
   if ((rc = upload(v, h.rev_off.data(), h.rev_off.size(), &d.rev_off))) return fail(rc);
   if ((rc = upload(v, h.rev_len.data(), h.rev_len.size(), &d.rev_len))) return fail(rc);
   if ((rc = upload(v, h.rev_blob.data(), h.rev_blob.size(), &d.rev_blob))) return fail(rc);

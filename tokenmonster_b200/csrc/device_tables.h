@@ -22,7 +22,8 @@ struct VocabDev {
   uint32_t edge_mask;          // capacity - 1
   uint32_t edge_shift;         // 32 - log2(capacity)
   const uint4* rec;            // 2 x uint4 per dictionary index (TokenRecord)
-  const uint8_t* smem_image;   // 1280 B: root_child[256] (u32) then begin_byte[256]; staged by TMA
+  const uint8_t* smem_image;   // 2304 B: root_child[256] (u32), begin_byte[256], sp_child[256] (u32); staged by TMA
+  const uint32_t* root2;       // 65536: val of the node two bytes below the root (first two steps in one load)
   const uint32_t* rev_off;     // decode: reverse[id] offset into rev_blob
   const uint8_t* rev_len;      // 0xFF = nil
   const uint8_t* rev_blob;

@@ -36,8 +36,8 @@
 namespace tmgpu {
 
 constexpr int kBlockThreads = 256;
-constexpr int kSmemTableBytes = 1280;  // root_child[256] u32 + begin_byte[256]
-constexpr int kSmemRingBase = 1536;    // tables + mbarrier, 512-aligned ring area
+constexpr int kSmemTableBytes = 2304;  // root_child[256] u32 + begin_byte[256] + sp_child[256] u32
+constexpr int kSmemRingBase = 2560;    // tables + mbarrier + class table, 512-aligned ring area
 
 template <int G>
 struct GroupCfg {

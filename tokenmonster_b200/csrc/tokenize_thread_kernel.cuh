@@ -77,12 +77,12 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
   __syncthreads();
   const uint32_t* s_root = reinterpret_cast<const uint32_t*>(smem);
   const uint8_t* s_begin = smem + 1024;
+  const uint32_t* s_sp = reinterpret_cast<const uint32_t*>(smem + 1280);   // child of the " " state by byte
   const int lane = threadIdx.x & 31;
   uint8_t* wbase = smem + Cfg::WARP_BASE + (threadIdx.x >> 5) * Cfg::WARP_BYTES;
   uint32_t* ring = reinterpret_cast<uint32_t*>(wbase) + lane;          // word w of this lane: ring[(w & 31) * 32]
   uint2* task = reinterpret_cast<uint2*>(wbase + Cfg::TASK_OFF);
   uint32_t* res = reinterpret_cast<uint32_t*>(wbase + Cfg::RES_OFF);
-  int* next_task = reinterpret_cast<int*>(wbase + Cfg::CTR_OFF);
 
   const VocabDev& V = A.v;
   const int M = V.max_len;
@@ -409,63 +409,96 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
                                   uint32_t(lane) | (uint32_t(jj) << 5) | (uint32_t(max(0, min(len_data - p, maxd_cap))) << 8));
         }
       }
-      if (lane == 0) *next_task = 0;
       __syncwarp();
+      // The pool is handed out by rank among the idle lanes (one ballot, no atomics).  A lane that
+      // takes a task does the first steps right away, without the hash table: the plain walk reads
+      // the node two bytes below the root from a 64 K-entry table (the top of the trie is where
+      // every walk goes), the retry walk the child of the " " state from shared memory.
       bool walking = false, dry = false;
       int c = 0, d = 0, maxd = 0, best_len = 0, slot_out = 0;
       uint32_t node = 0, best = 0, sig = 0;
+      uint32_t next = 0;                            // tasks handed out so far (warp-uniform)
       const uint32_t* col = ring;                   // ring column of the task's owner
       for (;;) {
-        if (!walking && !dry) {                     // take the next task of the pool
-          const int t = atomicAdd(next_task, 1);
-          if (t < ntask) {
+        const bool idle = !walking && !dry;
+        const uint32_t im = __ballot_sync(FULL, idle);
+        if (idle) {
+          const uint32_t t = next + __popc(im & lt);
+          if (t < uint32_t(ntask)) {
             const uint2 tk = task[t];
             const int owner = int(tk.y & 31u);
             c = int(tk.x);
-            d = 0;
             maxd = int(tk.y >> 8);
             slot_out = int((tk.y >> 5) & 3u) * 32 + owner;
             col = ring - lane + owner;
-            node = (pass == 0) ? kRootStart : (V.space_start & 0xFFFFFFu);
-            sig = V.space_start >> 24;
             best = 0;
             best_len = 0;
-            walking = true;
+            d = 0;
+            uint32_t val = kNoVal;
+            if (maxd > 0) {
+              const uint32_t b0 = (col[((c >> 2) & (kRingWords - 1)) * 32] >> ((c & 3) * 8)) & 0xFFu;
+              if (pass == 0) {
+                const uint32_t v1 = s_root[b0];
+                if (v1 != kNoVal) {
+                  d = 1;
+                  val = v1;
+                  if ((v1 & 0xFFFFFFu) < V.n_info) { best = v1 & 0xFFFFFFu; best_len = 1; }
+                  if (maxd > 1) {
+                    const int c1 = c + 1;
+                    const uint32_t b1 = (col[((c1 >> 2) & (kRingWords - 1)) * 32] >> ((c1 & 3) * 8)) & 0xFFu;
+                    const uint32_t v2 = __ldg(&V.root2[(b0 << 8) | b1]);
+                    if (v2 != kNoVal) {
+                      d = 2;
+                      val = v2;
+                      if ((v2 & 0xFFFFFFu) < V.n_info) { best = v2 & 0xFFFFFFu; best_len = 2; }
+                    } else {
+                      val = kNoVal;                 // no node two bytes down: the walk ends at depth 1
+                    }
+                  }
+                }
+              } else {
+                const uint32_t v1 = s_sp[b0];
+                if (v1 != kNoVal) {
+                  d = 1;
+                  val = v1;
+                  if ((v1 & 0xFFFFFFu) < V.n_info) { best = v1 & 0xFFFFFFu; best_len = 1; }
+                }
+              }
+            }
+            node = val & 0xFFFFFFu;
+            sig = val >> 24;
+            walking = (val != kNoVal) && (d < maxd) && (sig != 0u);
+            if (!walking) res[slot_out] = best | (uint32_t(best_len) << 24);
           } else {
             dry = true;
           }
         }
-        if (!__any_sync(FULL, walking)) break;
+        next += __popc(im);
+        if (!__any_sync(FULL, walking)) {
+          if (next >= uint32_t(ntask)) break;
+          continue;
+        }
         if (walking) {
-          bool end = (d >= maxd);
-          if (!end) {
-            const int cc = c + d;
-            const uint32_t b = (col[((cc >> 2) & (kRingWords - 1)) * 32] >> ((cc & 3) * 8)) & 0xFFu;
-            uint32_t val;
-            if (node == kRootStart) {
-              val = s_root[b];
-            } else if (((sig >> sig_bit_of(b)) & 1u) == 0) {
-              val = kNoVal;                         // no child of this node starts with b
-            } else {
-              const uint32_t key = (node << 8) | b;
-              uint32_t h = (key * 0x9E3779B1u) >> V.edge_shift;
-              uint2 e = __ldg(&V.edges[h]);
-              while (e.x != key && e.x != kNoVal) {  // linear probing, load factor <= 1/4
-                h = (h + 1) & V.edge_mask;
-                e = __ldg(&V.edges[h]);
-              }
-              val = (e.x == key) ? e.y : kNoVal;
+          const int cc = c + d;
+          const uint32_t b = (col[((cc >> 2) & (kRingWords - 1)) * 32] >> ((cc & 3) * 8)) & 0xFFu;
+          uint32_t val = kNoVal;
+          if ((sig >> sig_bit_of(b)) & 1u) {        // else: no child of this node starts with b
+            const uint32_t key = (node << 8) | b;
+            uint32_t h = (key * 0x9E3779B1u) >> V.edge_shift;
+            uint2 e = __ldg(&V.edges[h]);
+            while (e.x != key && e.x != kNoVal) {    // linear probing, load factor <= 1/4
+              h = (h + 1) & V.edge_mask;
+              e = __ldg(&V.edges[h]);
             }
-            if (val == kNoVal) {
-              end = true;
-            } else {
-              node = val & 0xFFFFFFu;
-              sig = val >> 24;
-              d++;
-              if (node < V.n_info) { best = node; best_len = d; }
-            }
+            if (e.x == key) val = e.y;
           }
-          if (end) {
+          if (val != kNoVal) {
+            node = val & 0xFFFFFFu;
+            sig = val >> 24;
+            d++;
+            if (node < V.n_info) { best = node; best_len = d; }
+          }
+          if (val == kNoVal || d >= maxd || sig == 0u) {
             walking = false;
             res[slot_out] = best | (uint32_t(best_len) << 24);
           }

@@ -200,6 +200,22 @@ int parse_vocab(const uint8_t* file, size_t n, HostTables* t, std::string* err) 
       h = (h + 1) & mask;
     }
   }
+  auto child_of = [&](uint32_t node, uint32_t byte) -> uint32_t {
+    uint32_t key = (node << 8) | byte, h = edge_hash(key, bits);
+    while (t->edges[h] != ~0ull) {
+      if (uint32_t(t->edges[h]) == key) return uint32_t(t->edges[h] >> 32);
+      h = (h + 1) & mask;
+    }
+    return kNone;
+  };
+  t->root2.assign(65536, kNone);
+  for (uint32_t b0 = 0; b0 < 256; b0++) {
+    if (t->root_child[b0] == kNone) continue;
+    const uint32_t n1 = t->root_child[b0] & 0xFFFFFFu;
+    for (uint32_t b1 = 0; b1 < 256; b1++) t->root2[b0 * 256 + b1] = child_of(n1, b1);
+  }
+  for (uint32_t b = 0; b < 256; b++)
+    t->sp_child[b] = t->space_start == kNone ? kNone : child_of(t->space_start & 0xFFFFFFu, b);
   return TMGPU_OK;
 }
 

@@ -40,6 +40,9 @@ struct HostTables {
   uint32_t edge_bits = 0;        // log2(capacity)
   uint32_t root_child[256];      // val or kNone
   uint32_t space_start = kNone;  // trie state after the virtual " " (0x20 0x00 in UTF-16) prefix
+  // shortcuts for the first steps of a walk (the top of the trie is where every walk goes):
+  std::vector<uint32_t> root2;   // 65536: val of the node two bytes below the root, or kNone
+  uint32_t sp_child[256];        // val of space_start's child by byte, or kNone
   uint32_t n_nodes = 0;
 
   // reverse table for decode: reverse[id] = LAST record with that id (go:2715)
