@@ -44,10 +44,12 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--strings", type=int, default=0, help="strings per GPU (default: the config's 1,000,000)")
     ap.add_argument("--config", default=WORKLOAD)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=3, help="timed steps of the host-buffer (e2e) leg, >= 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--check", action="store_true", help="verify a sample of the GPU ids against the oracle")
-    return ap.parse_args()
+    args = ap.parse_args()
+    args.e2e_steps = max(1, args.e2e_steps)
+    return args
 
 
 def config_block(args, n_strings, total_bytes, world):
@@ -367,7 +369,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
-                     "kernel": "tokenize_kernel", "kernel_ms": k_ms, "kernel_share_of_step": (k_ms * args.steps / elapsed_ms) if k_ms else None,
+                     "kernel": "tokenize_thread_kernel<1024, capcode, store>", "kernel_ms": k_ms, "kernel_share_of_step": (k_ms * args.steps / elapsed_ms) if k_ms else None,
                      "algorithmic_bytes_per_launch": total_bytes, "peak_source": peak_src},
         "clocks": summarize_clocks(samples),
         "tokens_per_step": all_tokens, "chars_per_token": all_bytes / max(all_tokens, 1.0), "strings_failed": bad_status,
