@@ -91,9 +91,16 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
   const bool to_lower = !A.prenorm && (V.normflag & 2) != 0;
   const bool can_retry = (V.delete_token != 0xFFFFFFu) && (V.space_start != kNoVal);
 
-  auto ring_byte = [&](int c) -> uint32_t {
-    return (ring[((c >> 2) & (kRingWords - 1)) * 32] >> ((c & 3) * 8)) & 0xFFu;
+  // byte c of a ring column: word (c >> 2) & 31 of the column sits 128 bytes after the previous one
+  // (the 32 lanes' words are interleaved), so a single byte load does it
+  const uint32_t rb = smem_u32(ring);
+  auto col_byte = [](uint32_t colb, int c) -> uint32_t {
+    uint32_t v;
+    const uint32_t a = colb + ((uint32_t(c) << 5) & uint32_t((kRingWords - 1) << 7)) + (uint32_t(c) & 3u);
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
   };
+  auto ring_byte = [&](int c) -> uint32_t { return col_byte(rb, c); };
   auto cls_of = [&](uint32_t c) -> uint32_t { return s_cls[c & 127u]; };
 
   // ---- per-lane string state ------------------------------------------------------------------
@@ -418,7 +425,7 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
       int c = 0, d = 0, maxd = 0, best_len = 0, slot_out = 0;
       uint32_t node = 0, best = 0, sig = 0;
       uint32_t next = 0;                            // tasks handed out so far (warp-uniform)
-      const uint32_t* col = ring;                   // ring column of the task's owner
+      uint32_t colb = rb;                           // ring column of the task's owner (shared address)
       for (;;) {
         const bool idle = !walking && !dry;
         const uint32_t im = __ballot_sync(FULL, idle);
@@ -430,13 +437,13 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
             c = int(tk.x);
             maxd = int(tk.y >> 8);
             slot_out = int((tk.y >> 5) & 3u) * 32 + owner;
-            col = ring - lane + owner;
+            colb = rb + uint32_t(owner - lane) * 4u;
             best = 0;
             best_len = 0;
             d = 0;
             uint32_t val = kNoVal;
             if (maxd > 0) {
-              const uint32_t b0 = (col[((c >> 2) & (kRingWords - 1)) * 32] >> ((c & 3) * 8)) & 0xFFu;
+              const uint32_t b0 = col_byte(colb, c);
               if (pass == 0) {
                 const uint32_t v1 = s_root[b0];
                 if (v1 != kNoVal) {
@@ -444,8 +451,7 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
                   val = v1;
                   if ((v1 & 0xFFFFFFu) < V.n_info) { best = v1 & 0xFFFFFFu; best_len = 1; }
                   if (maxd > 1) {
-                    const int c1 = c + 1;
-                    const uint32_t b1 = (col[((c1 >> 2) & (kRingWords - 1)) * 32] >> ((c1 & 3) * 8)) & 0xFFu;
+                    const uint32_t b1 = col_byte(colb, c + 1);
                     const uint32_t v2 = __ldg(&V.root2[(b0 << 8) | b1]);
                     if (v2 != kNoVal) {
                       d = 2;
@@ -479,8 +485,7 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
           continue;
         }
         if (walking) {
-          const int cc = c + d;
-          const uint32_t b = (col[((cc >> 2) & (kRingWords - 1)) * 32] >> ((cc & 3) * 8)) & 0xFFu;
+          const uint32_t b = col_byte(colb, c + d);
           uint32_t val = kNoVal;
           if ((sig >> sig_bit_of(b)) & 1u) {        // else: no child of this node starts with b
             const uint32_t key = (node << 8) | b;
