@@ -97,9 +97,10 @@ def test_device_trie_equals_oracle_dictionary(built, name):
     for _ in range(4000):
         a = rng.randrange(len(text) - 64)
         w = text[a:a + rng.randrange(1, m + 1)]
-        assert v._trie_lookup(w) == o.longest_prefix(w)
+        assert v._trie_lookup(w) == o.longest_prefix(w) == v._trie_lookup(w, shortcut=True)
         wi, wl = o.longest_prefix((b" " + w)[:m])
         gi, gl = v._trie_lookup(w[:m - 1], spaced=True)
+        assert (gi, gl) == v._trie_lookup(w[:m - 1], spaced=True, shortcut=True)
         if wl <= 1:
             assert gl == 0 or gl + 1 == wl
         else:

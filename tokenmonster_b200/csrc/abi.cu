@@ -341,6 +341,8 @@ extern "C" int tmgpu_vocab_info_get(const tmgpu_vocab* v, tmgpu_vocab_info* o) {
 // Table self-check (host): walks the same prefix trie the kernels walk, for a single window.
 // Not a tokenizer and not a fallback -- it exists so that CPU-only CI can verify the table
 // builder against the oracle's dictionary.  Returns matched length in window bytes.
+// spaced: bit 0 = window sits behind the virtual space, bit 1 = first steps through the shortcut
+// tables (root2 / sp_child) the lane-per-string kernel uses.
 extern "C" int tmgpu_selftest_trie_lookup(const tmgpu_vocab* v, const uint8_t* window, int n, int spaced,
                                           uint32_t* index) {
   return host_trie_lookup(v->host, window, n, spaced, index);

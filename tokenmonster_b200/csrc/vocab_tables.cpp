@@ -219,11 +219,44 @@ int parse_vocab(const uint8_t* file, size_t n, HostTables* t, std::string* err) 
   return TMGPU_OK;
 }
 
+// spaced: 0 plain window, 1 window behind the virtual space; +2 = take the first steps from the
+// shortcut tables the lane-per-string kernel uses (root2 / sp_child) instead of the hashed edges
 int host_trie_lookup(const HostTables& h, const uint8_t* window, int n, int spaced, uint32_t* index) {
+  const bool shortcut = (spaced & 2) != 0;
+  spaced &= 1;
   uint32_t start = spaced ? h.space_start : kRootStart;
   if (spaced && start == kNoVal) return 0;
   const uint2* edges = reinterpret_cast<const uint2*>(h.edges.data());
   uint32_t idx = 0;
+  if (shortcut && n > 0) {   // mirrors the task fetch of tokenize_thread_kernel
+    uint32_t best = 0, val = kNoVal;
+    int best_len = 0, d = 0;
+    const uint32_t v1 = spaced ? h.sp_child[window[0]] : h.root_child[window[0]];
+    if (v1 != kNoVal) {
+      d = 1;
+      val = v1;
+      if ((v1 & 0xFFFFFFu) < h.n_info) { best = v1 & 0xFFFFFFu; best_len = 1; }
+      if (!spaced && n > 1) {
+        const uint32_t v2 = h.root2[size_t(window[0]) * 256 + window[1]];
+        if (v2 != kNoVal) {
+          d = 2;
+          val = v2;
+          if ((v2 & 0xFFFFFFu) < h.n_info) { best = v2 & 0xFFFFFFu; best_len = 2; }
+        } else {
+          val = kNoVal;
+        }
+      }
+    }
+    if (val != kNoVal && d < n) {   // the rest of the walk through the hashed edges
+      uint32_t sub = 0;
+      int l = trie_longest([&](int k) { return uint32_t(window[d + k]); }, [&](uint32_t) { return kNoVal; },
+                           [&](uint32_t s) { return edges[s]; }, uint32_t(h.edges.size() - 1), 32u - h.edge_bits,
+                           h.n_info, n - d, val, &sub);
+      if (l > 0) { best = sub; best_len = d + l; }
+    }
+    if (index) *index = best;
+    return best_len;
+  }
   int l = trie_longest([&](int d) { return uint32_t(window[d]); }, [&](uint32_t b) { return h.root_child[b]; },
                        [&](uint32_t s) { return edges[s]; }, uint32_t(h.edges.size() - 1), 32u - h.edge_bits,
                        h.n_info, n, start, &idx);

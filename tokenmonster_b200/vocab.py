@@ -319,9 +319,12 @@ class Vocab:
         return _widen24(raw)
 
     # ---- table self-check (host walk of the device trie; CPU-only CI) ---------------------
-    def _trie_lookup(self, window: bytes, spaced: bool = False):
+    def _trie_lookup(self, window: bytes, spaced: bool = False, shortcut: bool = False):
+        """Table self-check: host walk of the device trie; shortcut = first steps through the
+        root2 / sp_child tables, the way the lane-per-string kernel starts a walk."""
         idx = C.c_uint32()
-        l = lib().tmgpu_selftest_trie_lookup(self._h, window, len(window), int(spaced), C.byref(idx))
+        l = lib().tmgpu_selftest_trie_lookup(self._h, window, len(window), int(spaced) | (2 if shortcut else 0),
+                                             C.byref(idx))
         return (int(idx.value), l) if l else (None, 0)
 
 
