@@ -561,7 +561,7 @@ static int chunk_run(tmgpu_workspace* ws, const TokenizeArgs& first, uint32_t to
   TokenizeArgs c = first;
   c.n = total;
   c.slab = ws->ck_ids;
-  c.skip = nullptr;
+  c.skip = ws->ck_fail;      // per document: planning found no safe boundary, its chunks do nothing
   c.watermark = nullptr;
   c.chunks = ws->ck_items;
   c.c_pos = ws->ck_pos;

@@ -171,6 +171,11 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
         // the normalizer refused this string: its status 13 from the first pass stands
       } else if (!CHUNK && A.skip && A.skip[item]) {
         // a long document that is tokenized in chunks by another launch
+      } else if (CHUNK && A.skip[A.chunks[item].doc]) {
+        // no safe chunk boundaries in this document (planning failed): it goes to the one-lane path
+        ChunkOut co;
+        co.cnt = 0; co.n_norm = 0; co.miss = 0; co.flags = 2u;
+        A.c_out[item] = co;
       } else {
         s = A.list ? A.list[item] : item;
         int64_t o0 = A.off[CHUNK ? 0 : item];
@@ -357,7 +362,10 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
     const bool exhausted = (CAP == 0) ? true : (rc >= total_c);
     const int len_data = (CAP == 0) ? slen : (exhausted ? filled : 0x3FFFFFFF);
     const bool past = CHUNK && !last_chunk && n_norm >= 0 && i >= n_norm + int(A.c_ov);
-    const bool finished = running && (bad || i >= len_data || past);
+    // the encoder went past the next chunk's start without landing on it: cannot happen behind a
+    // safe boundary; stop rather than tokenize the rest of the document
+    const bool lost = CHUNK && CAP != 0 && !last_chunk && n_norm < 0 && rc > cross_c;
+    const bool finished = running && (bad || i >= len_data || past || lost);
     const bool stepping = running && !finished;
     const bool seek = stepping && !have;           // this iteration only finds the current token
     uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
@@ -623,7 +631,7 @@ __global__ void __launch_bounds__(BLOCK, 1) tokenize_thread_kernel(const Tokeniz
       co.cnt = min(cnt, cap);
       co.n_norm = uint32_t(n_norm < 0 ? 0 : n_norm);
       co.miss = miss;
-      co.flags = (bad ? 1u : 0u) | (cnt > cap ? 2u : 0u) | ((i >= len_data && !bad) ? 4u : 0u);
+      co.flags = (bad ? 1u : 0u) | ((cnt > cap || lost) ? 2u : 0u) | ((i >= len_data && !bad && !lost) ? 4u : 0u);
       A.c_out[s] = co;
       running = false;
     } else if (finished) {
