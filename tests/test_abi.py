@@ -34,7 +34,9 @@ def test_host_only_vocab_and_no_cpu_path(built):
     v = Vocab(vb, device=-1)
     assert len(v) == 50238 and v.charset() == "UTF-8" and v.capcode() == 0 and v.max_token_length() == 40
     assert v.highest_token_id() == 50256 and v.unk_token_id() is None and v.default_encoding_length() == 2
-    for call in (lambda: v.tokenize("hello"), lambda: v.tokenize_count("hello"), lambda: v.decode([1, 2, 3])):
+    one = (np.frombuffer(b"hello", np.uint8), np.array([0, 5], np.uint64))
+    for call in (lambda: v.tokenize("hello"), lambda: v.tokenize_count("hello"), lambda: v.decode([1, 2, 3]),
+                 lambda: v.score_batch(*one), lambda: v.decoder(1)):
         with pytest.raises(TmgpuError) as e:
             call()
         assert e.value.code == 2 and "no CPU path" in str(e.value)
