@@ -67,3 +67,41 @@ def test_shard_by_bytes_is_balanced_and_ordered():
         assert all(ranges[k][1] == ranges[k + 1][0] for k in range(world - 1))
         sizes = [int(off[b] - off[a]) for a, b in ranges]
         assert max(sizes) - min(sizes) <= 2 * 2000
+
+
+def _score_worker(rank, world, port, q):
+    """Each rank scores its own shard with the oracle's worker loop (the stand-in for the CUDA
+    path, which tests/test_training_scores.py covers); the all-reduce must give both ranks the
+    totals of the whole set."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle
+        from tokenmonster_b200.dist import score_sharded
+        from workloads import corpus
+        with open(os.path.join(os.path.dirname(__file__), "golden", "small_cap2.vocab"), "rb") as f:
+            chk = oracle.OracleVocab(f.read(), "port")
+        base = bytes(corpus.base_text(8, 1 << 16, 0.4))
+        strips = [base[k * 500:(k + 1) * 500 - (k % 7)] for k in range(60)]
+        mine = strips[rank::world]
+        s, h, t = chk.score(mine)
+        gs, gh, gt = score_sharded(torch.from_numpy(s.astype(np.int64)), torch.from_numpy(h.astype(np.int64)), t,
+                                   device=torch.device("cpu"))
+        ws, wh, wt = chk.score(strips)
+        q.put(bool(np.array_equal(gs.numpy(), ws.astype(np.int64)) and np.array_equal(gh.numpy(), wh.astype(np.int64))
+                   and gt == wt and wt > 0))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_training_scores_all_reduce_two_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_score_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True and q.get(timeout=5) is True

@@ -133,3 +133,30 @@ def gpu_compute(workspace, enc_len: int = 2):
         res = workspace.results()
         return res["tokens_u8"], res["counts"].to(torch.int32), res["enc_len"]
     return run
+
+
+def score_sharded(local_scores: torch.Tensor, local_hist: torch.Tensor, local_tokens: int, device=None, group=None):
+    """Training scores over a dataset sharded across ranks (training/trainvocab.go:932-1170 per shard).
+
+    Every rank scores its resident data strips for the same candidate vocabulary
+    (`Vocab.score_batch`); the per-token histograms, the histogram of uncovered byte values and
+    tokensInText are sums over strings, so ONE all-reduce (n_reverse + 257 int64 values; NCCL over
+    NVLink on GPU ranks) gives every rank the totals the master's pruning step needs.
+    Returns (scores int64[n_reverse], hist int64[256], tokens_in_text)."""
+    dev = device if device is not None else local_scores.device
+    n = local_scores.numel()
+    vec = torch.empty(n + 257, dtype=torch.int64, device=dev)
+    vec[:n] = local_scores.to(device=dev, dtype=torch.int64)
+    vec[n:n + 256] = local_hist.to(device=dev, dtype=torch.int64)
+    vec[n + 256] = int(local_tokens)
+    dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+    return vec[:n], vec[n:n + 256], int(vec[n + 256])
+
+
+def gpu_score(vocab, data, off, device=None, group=None):
+    """score_sharded() for a GPU rank: scores this rank's strips with the CUDA path, then reduces."""
+    import numpy as np
+    scores, hist, tokens, _ = vocab.score_batch(data, off)
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    return score_sharded(torch.from_numpy(scores.astype(np.int64)), torch.from_numpy(hist.astype(np.int64)), tokens,
+                         device=dev, group=group)
