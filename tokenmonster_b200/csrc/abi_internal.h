@@ -1,0 +1,201 @@
+// abi_internal.h -- what the translation units behind include/tmgpu.h share: the vocabulary and
+// workspace objects, the error string, allocation helpers and the internal entry points that one
+// unit offers to the others (abi.cu: library / vocabulary / workspace; abi_tokenize.cu: tokenize,
+// count, score; abi_decode.cu: decode and the streaming decoder; abi_wire.cu: server payloads).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/tmgpu.h"
+#include "kernels.h"
+#include "unicode_dev.h"
+#include "unicode_tables.h"
+#include "vocab_tables.h"
+
+using namespace tmgpu;
+
+extern thread_local std::string g_err;   // message behind tmgpu_last_error()
+
+#define CU(expr)                                                                          \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      g_err = std::string(#expr) + ": " + cudaGetErrorString(e__);                        \
+      return TMGPU_E_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+struct tmgpu_vocab {
+  HostTables host;
+  int device = -1;  // -1: host tables only (parser / table self-tests without a GPU)
+  int sms = 0;
+  int group = 1;    // 1 = lane-per-string kernel (default); 4/8/16/32 = lanes-over-branches kernel
+  VocabDev dev{};
+  bool unicode = false;           // non-ASCII strings go through the device normalizer (else status 13)
+  UnicodeDev uni{};
+  std::vector<void*> allocs;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  tmgpu_workspace* ws = nullptr;  // internal workspace of the host-buffer calls
+  uint8_t* d_in = nullptr;        // staging of host inputs
+  size_t d_in_cap = 0;
+  int64_t* d_off = nullptr;       // d_off_cap begin offsets, then d_off_cap end offsets (wire payloads)
+  size_t d_off_cap = 0;
+  int64_t* h_off = nullptr;       // pinned, same layout
+  size_t h_off_cap = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaStream_t d2h_stream = nullptr;
+  cudaEvent_t chunk_ev[32] = {};
+  cudaEvent_t done_ev[32] = {};
+  uint64_t* d_run = nullptr;      // device: running id total + per-chunk {base, total}
+  uint64_t* h_info = nullptr;     // pinned mirror of the per-chunk {base, total}
+  // pinned host blocks handed out as results and taken back by tmgpu_result_free / bytes_free
+  struct PinnedBlock { void* p; size_t bytes; bool used; };
+  std::vector<PinnedBlock> pinned;
+  std::mutex pin_mu;
+};
+
+struct tmgpu_workspace {
+  tmgpu_vocab* v = nullptr;
+  uint32_t max_strings = 0;
+  uint64_t max_bytes = 0;
+  uint32_t slab_pad = 16;
+  uint32_t* slab = nullptr;
+  uint64_t slab_ids = 0;
+  uint32_t* counts = nullptr;   // n + 1 (last = 0 for the scan)
+  uint32_t* need = nullptr;     // n + 1: uncapped counts (overflow re-run)
+  uint32_t* missing = nullptr;
+  uint8_t* status = nullptr;
+  uint64_t* tok_off = nullptr;  // n + 1
+  uint8_t* tokens = nullptr;    // dense serialized ids
+  uint32_t* work_counter = nullptr;
+  uint32_t* overflow = nullptr;
+  void* scan_temp = nullptr;
+  size_t scan_bytes = 0;
+  // device normalizer (non-ASCII strings): work list, placement, scratch text
+  uint32_t* uni_list = nullptr;          // n
+  int64_t* uni_begin = nullptr;          // n
+  int64_t* uni_end = nullptr;            // n
+  unsigned long long* uni_ctr = nullptr; // {strings, scratch bytes}
+  uint8_t* uni_text = nullptr;
+  uint64_t uni_text_cap = 0;
+  uint32_t last_unicode = 0;             // strings the normalizer handled in the most recent launch
+  // long documents tokenized in chunks (chunking.cuh): per document ...
+  uint32_t* ck_n = nullptr;              // n + 1: chunks of the document (0 = not chunked)
+  uint64_t* ck_base = nullptr;           // n + 1: exclusive scan
+  uint8_t* ck_skip = nullptr;            // n
+  uint8_t* ck_fail = nullptr;            // n
+  uint32_t* ck_list = nullptr;           // n: documents to redo with one lane
+  int64_t* ck_fb = nullptr;              // n
+  int64_t* ck_fe = nullptr;              // n
+  unsigned long long* ck_ctr = nullptr;
+  // ... and per chunk (grown on demand)
+  ChunkItem* ck_items = nullptr;
+  ChunkOut* ck_out = nullptr;
+  uint32_t *ck_ids = nullptr, *ck_pos = nullptr, *ck_miss = nullptr;   // chunks x log capacity
+  uint32_t *ck_sb = nullptr, *ck_se = nullptr, *ck_sd = nullptr;
+  uint32_t *ck_ma = nullptr, *ck_mb = nullptr, *ck_dl = nullptr, *ck_sm = nullptr, *ck_fl = nullptr;
+  uint64_t ck_chunks_cap = 0;
+  std::vector<void*> ck_allocs;
+  uint32_t last_chunked = 0, last_chunk_redo = 0;   // chunks launched / documents redone, last launch
+  unsigned long long* score_buf = nullptr;          // training scores: n_reverse ids, then 256 byte values
+  // decode
+  uint32_t* raw_len = nullptr;  // n + 1
+  uint64_t* raw_off = nullptr;  // n + 1
+  uint32_t* out_len = nullptr;  // n + 1
+  uint64_t* out_off = nullptr;  // n + 1
+  uint8_t* raw = nullptr;
+  uint8_t* dec = nullptr;
+  uint8_t* dense = nullptr;
+  uint64_t dec_cap = 0;
+  std::vector<void*> allocs;
+  int last_launches = 0;
+  // CUDA events around the dominant kernel (tokenize) of the most recent launches
+  static constexpr int kMaxChunks = 32;
+  static constexpr int kEv = 64;
+  cudaEvent_t ev0[kEv] = {}, ev1[kEv] = {};
+  int ev_head = 0, ev_count = 0;
+};
+
+template <class T>
+inline int dev_alloc(std::vector<void*>& pool, T** out, size_t count) {
+  void* p = nullptr;
+  size_t bytes = count * sizeof(T);
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(&p, bytes + 16);
+  if (e != cudaSuccess) {
+    g_err = std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e);
+    return TMGPU_E_NOMEM;
+  }
+  pool.push_back(p);
+  *out = static_cast<T*>(p);
+  return TMGPU_OK;
+}
+
+// A host-buffer batch is tokenized in chunks of strings so that the H2D copy of chunk k+1 overlaps
+// the kernel of chunk k: `ready` is recorded on the copy stream after the chunk's bytes landed.
+struct ChunkPlan {
+  uint32_t s0, s1;       // strings [s0, s1)
+  uint64_t slab_base;    // (off[s0] - off[0]) + slab_pad * s0
+  cudaEvent_t ready;     // may be null
+};
+
+struct ResultPriv {
+  tmgpu_vocab* v = nullptr;
+  std::vector<void*> blocks;
+};
+
+// pinned host memory from the vocabulary's pool (cudaMallocHost is far too slow to pay per call)
+template <class T>
+inline int pinned_alloc(ResultPriv* p, T** out, size_t count) {
+  size_t bytes = count * sizeof(T);
+  if (bytes < 64) bytes = 64;
+  tmgpu_vocab* v = p->v;
+  std::lock_guard<std::mutex> lock(v->pin_mu);
+  int best = -1;
+  for (size_t i = 0; i < v->pinned.size(); i++) {
+    auto& b = v->pinned[i];
+    if (!b.used && b.bytes >= bytes && (best < 0 || b.bytes < v->pinned[best].bytes)) best = int(i);
+  }
+  if (best < 0) {
+    void* q = nullptr;
+    size_t cap = bytes + bytes / 4 + 4096;
+    cudaError_t e = cudaMallocHost(&q, cap);
+    if (e != cudaSuccess) {
+      g_err = std::string("cudaMallocHost: ") + cudaGetErrorString(e);
+      return TMGPU_E_NOMEM;
+    }
+    v->pinned.push_back({q, cap, false});
+    best = int(v->pinned.size()) - 1;
+  }
+  v->pinned[best].used = true;
+  p->blocks.push_back(v->pinned[best].p);
+  *out = static_cast<T*>(v->pinned[best].p);
+  return TMGPU_OK;
+}
+
+// ---- internal entry points shared between the units -----------------------------------------
+void release_priv(ResultPriv* p);
+int ensure_host_path(tmgpu_vocab* v, uint32_t n, uint64_t bytes);
+int stage_input(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off, uint32_t n, uint64_t* total,
+                std::vector<ChunkPlan>* plan);
+int stage_copy(tmgpu_vocab* v, const uint8_t* src, uint32_t n, uint64_t total, bool gapped,
+               std::vector<ChunkPlan>* plan);
+int rerun_if_overflow(tmgpu_vocab* v, uint32_t n, uint8_t enc_len, std::vector<void*>* temp, uint8_t** dense,
+                      const int64_t* d_ends = nullptr);
+int tokenize_streamed(tmgpu_vocab* v, uint32_t n, uint8_t enc_len, cudaEvent_t offsets_ready,
+                      const int64_t* d_ends = nullptr);
+int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t* d_off, uint32_t n,
+                       uint8_t enc_len, int mode, cudaStream_t st, const uint64_t* slab_off, uint32_t* slab,
+                       uint8_t* dense, const std::vector<ChunkPlan>* chunks = nullptr,
+                       const int64_t* d_ends = nullptr);
+int ensure_decode_cap(tmgpu_workspace* ws, uint64_t bytes);
+int decode_on_stream(tmgpu_workspace* ws, const uint8_t* d_tokens, const int64_t* d_tok_off, uint32_t n, int enc,
+                     cudaStream_t st, const uint8_t** d_bytes, const uint64_t** d_off, uint64_t* total_out);

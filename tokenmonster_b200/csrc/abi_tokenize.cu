@@ -1,0 +1,692 @@
+// abi_tokenize.cu -- tokenize / count / score entry points of libtmgpu.so: the device-resident
+// path, the host-buffer path (chunked upload chased by one kernel launch), the passes for long
+// documents (chunking.cuh) and non-ASCII strings (unicode_normalize.cuh), the overflow re-run.
+#include "abi_internal.h"
+
+// ---- long documents in chunks (chunking.cuh) -----------------------------------------------------
+// Phase 1 (before the main launch): decide which documents are chunked.  Returns the number of
+// chunks (0 = nothing to do); the main launch then skips those documents via ws->ck_skip.
+static int chunk_plan(tmgpu_workspace* ws, const TokenizeArgs& a, cudaStream_t st, uint32_t* total_out) {
+  tmgpu_vocab* v = ws->v;
+  *total_out = 0;
+  ws->last_chunked = 0;
+  ws->last_chunk_redo = 0;
+  static const bool off = getenv("TMGPU_NO_CHUNKS") != nullptr;   // diagnostic: one lane per document always
+  const HostTables& h = v->host;
+  if (off || a.n == 0 || a.n >= uint32_t(v->sms) * 512u || h.max_len == 0 || h.charset == 2 || a.slab_off || a.scores)
+    return TMGPU_OK;   // (overlapping chunks would be scored twice)
+  CU(launch_chunk_count(a.off, a.ends, a.n, ws->ck_n, ws->ck_skip, v->sms, st));
+  CU(cudaMemsetAsync(ws->ck_n + a.n, 0, 4, st));
+  CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, ws->ck_n, ws->ck_base, a.n + 1, st));
+  uint64_t total = 0;
+  CU(cudaMemcpyAsync(&total, ws->ck_base + a.n, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (total == 0 || total > (1ull << 19)) return TMGPU_OK;   // nothing long, or far too much for the logs
+  if (ws->ck_chunks_cap < total) {
+    for (void* p : ws->ck_allocs) cudaFree(p);
+    ws->ck_allocs.clear();
+    ws->ck_chunks_cap = 0;
+    const uint64_t cap = total + total / 4 + 64, log = cap * chunk_log_capacity();
+    int rc = 0;
+    auto A = [&](auto** p, size_t count) {
+      if (!rc) rc = dev_alloc(ws->ck_allocs, p, count);
+    };
+    A(&ws->ck_items, cap);
+    A(&ws->ck_out, cap);
+    A(&ws->ck_ids, log);
+    A(&ws->ck_pos, log);
+    A(&ws->ck_miss, log);
+    A(&ws->ck_sb, cap);
+    A(&ws->ck_se, cap);
+    A(&ws->ck_sd, cap);
+    A(&ws->ck_ma, cap);
+    A(&ws->ck_mb, cap);
+    A(&ws->ck_dl, cap);
+    A(&ws->ck_sm, cap);
+    A(&ws->ck_fl, cap);
+    if (rc) return rc;
+    ws->ck_chunks_cap = cap;
+  }
+  *total_out = uint32_t(total);
+  return TMGPU_OK;
+}
+
+// Phase 2 (after the main launch): tokenize the chunks, stitch, gather; documents whose chunks do
+// not meet are tokenized again by one lane each.
+static int chunk_run(tmgpu_workspace* ws, const TokenizeArgs& first, uint32_t total, int mode, cudaStream_t st) {
+  tmgpu_vocab* v = ws->v;
+  CU(cudaMemsetAsync(ws->ck_fail, 0, first.n, st));
+  CU(launch_chunk_fill(first.data, first.off, first.ends, first.n, ws->ck_n, ws->ck_base, total, ws->ck_items,
+                       ws->ck_fail, v->sms, st));
+  TokenizeArgs c = first;
+  c.n = total;
+  c.slab = ws->ck_ids;
+  c.skip = ws->ck_fail;      // per document: planning found no safe boundary, its chunks do nothing
+  c.watermark = nullptr;
+  c.chunks = ws->ck_items;
+  c.c_pos = ws->ck_pos;
+  c.c_miss = ws->ck_miss;
+  c.c_out = ws->ck_out;
+  c.c_cap = chunk_log_capacity();
+  c.c_ov = chunk_overlap();
+  c.work_counter = ws->work_counter + (tmgpu_workspace::kMaxChunks - 2);
+  CU(cudaMemsetAsync(c.work_counter, 0, 4, st));
+  static const bool trace = getenv("TMGPU_TRACE") != nullptr;   // diagnostic: phase times on stderr
+  cudaEvent_t te[4] = {};
+  if (trace) {
+    for (auto& e : te) cudaEventCreate(&e);
+    cudaEventRecord(te[0], st);
+  }
+  CU(launch_tokenize_chunks(c, v->sms, st));
+  if (trace) cudaEventRecord(te[1], st);
+  StitchArgs sa{};
+  sa.off = first.off;
+  sa.ends = first.ends;
+  sa.n = first.n;
+  sa.n_chunks = ws->ck_n;
+  sa.chunk_base = ws->ck_base;
+  sa.c_out = ws->ck_out;
+  sa.c_pos = ws->ck_pos;
+  sa.c_miss = ws->ck_miss;
+  sa.c_cap = c.c_cap;
+  sa.slab_pad = first.slab_pad;
+  sa.count_mode = mode == 1;
+  sa.doc_fail = ws->ck_fail;
+  sa.seg_begin = ws->ck_sb;
+  sa.seg_end = ws->ck_se;
+  sa.seg_dst = ws->ck_sd;
+  sa.meet_a = ws->ck_ma;
+  sa.meet_b = ws->ck_mb;
+  sa.seg_dels = ws->ck_dl;
+  sa.seg_miss = ws->ck_sm;
+  sa.seg_flag = ws->ck_fl;
+  sa.counts = first.counts;
+  sa.need = first.need;
+  sa.missing = first.missing;
+  sa.status = first.status;
+  sa.overflow = first.overflow;
+  CU(launch_chunk_stitch(sa, total, ws->ck_items, v->sms, st));
+  if (trace) cudaEventRecord(te[2], st);
+  if (mode == 0)
+    CU(launch_chunk_gather(ws->ck_items, total, ws->ck_ids, c.c_cap, ws->ck_sb, ws->ck_se, ws->ck_sd, first.off,
+                           first.slab_pad, first.slab, v->sms, st));
+  if (trace) {
+    cudaEventRecord(te[3], st);
+    cudaEventSynchronize(te[3]);
+    float t0 = 0, t1 = 0, t2 = 0;
+    cudaEventElapsedTime(&t0, te[0], te[1]);
+    cudaEventElapsedTime(&t1, te[1], te[2]);
+    cudaEventElapsedTime(&t2, te[2], te[3]);
+    fprintf(stderr, "[tmgpu] chunks: %u, tokenize %.3f ms, stitch %.3f ms, gather %.3f ms\n", total, t0, t1, t2);
+    for (auto& e : te) cudaEventDestroy(e);
+  }
+  CU(cudaMemsetAsync(ws->ck_ctr, 0, 8, st));
+  CU(launch_chunk_failed(ws->ck_fail, ws->ck_n, first.off, first.ends, first.n, ws->ck_list, ws->ck_fb, ws->ck_fe,
+                         ws->ck_ctr, v->sms, st));
+  unsigned long long redo = 0;
+  CU(cudaMemcpyAsync(&redo, ws->ck_ctr, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  ws->last_launches += 7 + (mode == 0 ? 1 : 0);
+  ws->last_chunked = total;
+  ws->last_chunk_redo = uint32_t(redo);
+  if (redo) {   // one lane per document, the ordinary way
+    TokenizeArgs b = first;
+    b.off = ws->ck_fb;
+    b.ends = ws->ck_fe;
+    b.n = uint32_t(redo);
+    b.list = ws->ck_list;
+    b.raw_off = first.off;
+    b.raw_ends = first.ends;
+    b.skip = nullptr;
+    b.watermark = nullptr;
+    b.work_counter = ws->work_counter + (tmgpu_workspace::kMaxChunks - 2);
+    CU(cudaMemsetAsync(b.work_counter, 0, 4, st));
+    CU(launch_tokenize(b, 1, mode == 0, v->sms, st, nullptr));
+    ws->last_launches++;
+  }
+  return TMGPU_OK;
+}
+
+// Strings the tokenize kernel gave up on (first byte >= 0x80 under a normalizing vocabulary) are
+// normalized by the device normalizer and tokenized by a second launch that reads the normalized
+// text verbatim.  One small D2H tells the host whether there are any; ASCII batches pay only that.
+static int unicode_pass(tmgpu_workspace* ws, const TokenizeArgs& first, bool store, cudaStream_t st) {
+  tmgpu_vocab* v = ws->v;
+  ws->last_unicode = 0;
+  if (!v->unicode || first.n == 0 || v->host.max_len == 0) return TMGPU_OK;
+  CU(cudaMemsetAsync(ws->uni_ctr, 0, 16, st));
+  CU(launch_select_refused(first.status, first.off, first.ends, first.n, ws->uni_list, ws->uni_begin, ws->uni_ctr,
+                           v->sms, st));
+  unsigned long long h[2] = {0, 0};
+  CU(cudaMemcpyAsync(h, ws->uni_ctr, 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  ws->last_launches++;
+  if (h[0] == 0) return TMGPU_OK;
+  if (ws->uni_text_cap < h[1] + 64) {
+    if (ws->uni_text) cudaFree(ws->uni_text);
+    ws->uni_text = nullptr;
+    ws->uni_text_cap = h[1] + h[1] / 4 + 4096;
+    cudaError_t e = cudaMalloc(&ws->uni_text, ws->uni_text_cap);
+    if (e != cudaSuccess) {
+      ws->uni_text_cap = 0;
+      g_err = std::string("cudaMalloc(normalizer scratch): ") + cudaGetErrorString(e);
+      return TMGPU_E_NOMEM;
+    }
+  }
+  NormalizeArgs na{};
+  na.U = v->uni;
+  na.data = first.data;
+  na.off = first.off;
+  na.ends = first.ends;
+  na.list = ws->uni_list;
+  na.n_list = reinterpret_cast<const uint32_t*>(ws->uni_ctr);
+  na.scratch = ws->uni_text;
+  na.n_begin = ws->uni_begin;
+  na.n_end = ws->uni_end;
+  na.normflag = v->host.normflag;
+  na.capcode = v->host.capcode;
+  static const bool trace = getenv("TMGPU_TRACE") != nullptr;   // diagnostic: phase times on stderr
+  cudaEvent_t te[3] = {};
+  if (trace) {
+    for (auto& e : te) cudaEventCreate(&e);
+    cudaEventRecord(te[0], st);
+  }
+  CU(launch_unicode_normalize(na, v->sms, st));
+  if (trace) cudaEventRecord(te[1], st);
+  TokenizeArgs b = first;
+  b.data = ws->uni_text;
+  b.off = ws->uni_begin;
+  b.ends = ws->uni_end;
+  b.n = uint32_t(h[0]);
+  b.list = ws->uni_list;
+  b.raw_off = first.off;
+  b.raw_ends = first.ends;
+  b.prenorm = 1;
+  b.skip = nullptr;
+  b.watermark = nullptr;
+  b.work_counter = ws->work_counter + (tmgpu_workspace::kMaxChunks - 1);
+  CU(cudaMemsetAsync(b.work_counter, 0, 4, st));
+  CU(launch_tokenize(b, 1, store, v->sms, st, nullptr));
+  if (trace) {
+    cudaEventRecord(te[2], st);
+    cudaEventSynchronize(te[2]);
+    float a = 0, c = 0;
+    cudaEventElapsedTime(&a, te[0], te[1]);
+    cudaEventElapsedTime(&c, te[1], te[2]);
+    fprintf(stderr, "[tmgpu] non-ASCII pass: %llu strings, scratch %llu B, normalize %.3f ms, tokenize %.3f ms\n", h[0],
+            h[1], a, c);
+    for (auto& e : te) cudaEventDestroy(e);
+  }
+  ws->last_launches += 2;
+  ws->last_unicode = uint32_t(h[0]);
+  return TMGPU_OK;
+}
+
+int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t* d_off, uint32_t n,
+                              uint8_t enc_len, int mode, cudaStream_t st, const uint64_t* slab_off,
+                              uint32_t* slab, uint8_t* dense, const std::vector<ChunkPlan>* chunks,
+                              const int64_t* d_ends) {
+  tmgpu_vocab* v = ws->v;
+  ws->last_launches = 0;
+  CU(cudaMemsetAsync(ws->work_counter, 0, 4 * tmgpu_workspace::kMaxChunks, st));
+  CU(cudaMemsetAsync(ws->overflow, 0, 4, st));
+  CU(cudaMemsetAsync(ws->counts + n, 0, 4, st));
+  TokenizeArgs a{};
+  a.v = v->dev;
+  a.data = d_data;
+  a.off = d_off;
+  a.ends = d_ends;
+  a.n = n;
+  a.slab = slab;
+  a.slab_pad = ws->slab_pad;
+  a.slab_off = slab_off;
+  a.counts = ws->counts;
+  a.need = ws->need;
+  a.missing = ws->missing;
+  a.status = ws->status;
+  a.work_counter = ws->work_counter;
+  a.overflow = ws->overflow;
+  if (mode == 2 && n > 0 && v->host.max_len != 0) {
+    // training scores (trainvocab.go:932-1170): a histogram cannot be rolled back, so strings the
+    // first pass would abandon at a non-ASCII byte are set aside before it starts
+    a.scores = ws->score_buf;
+    a.miss_hist = ws->score_buf + v->host.n_reverse;
+    CU(cudaMemsetAsync(ws->score_buf, 0, (size_t(v->host.n_reverse) + 256) * 8, st));
+    if (v->unicode) {
+      if (chunks)
+        for (const ChunkPlan& c : *chunks)
+          if (c.ready) CU(cudaStreamWaitEvent(st, c.ready, 0));
+      CU(launch_flag_non_ascii(d_data, d_off, d_ends, n, ws->ck_skip, ws->status, ws->counts, ws->missing, v->sms, st));
+      a.skip = ws->ck_skip;
+      ws->last_launches++;
+    }
+  }
+  uint32_t ck_total = 0;   // long documents of a small batch are tokenized in chunks (chunking.cuh)
+  if (n > 0 && (!chunks || chunks->size() == 1)) {
+    if (chunks && (*chunks)[0].ready) CU(cudaStreamWaitEvent(st, (*chunks)[0].ready, 0));
+    int rc = chunk_plan(ws, a, st, &ck_total);
+    if (rc) return rc;
+    if (ck_total) a.skip = ws->ck_skip;
+  }
+  if (v->host.max_len == 0) {  // empty vocabulary: empty result, not an error (go:960-962)
+    CU(cudaMemsetAsync(ws->counts, 0, (size_t(n) + 1) * 4, st));
+    CU(cudaMemsetAsync(ws->missing, 0, size_t(n) * 4, st));
+    CU(cudaMemsetAsync(ws->status, 0, n, st));
+  } else if (n > 0 && chunks && !slab_off) {
+    int ci = 0;
+    for (const ChunkPlan& c : *chunks) {
+      if (c.s1 <= c.s0) continue;
+      if (c.ready) CU(cudaStreamWaitEvent(st, c.ready, 0));
+      TokenizeArgs b = a;
+      b.off = d_off + c.s0;
+      if (d_ends) b.ends = d_ends + c.s0;
+      if (a.skip) b.skip = a.skip + c.s0;
+      b.n = c.s1 - c.s0;
+      b.slab = slab + c.slab_base;
+      b.counts = ws->counts + c.s0;
+      b.need = ws->need + c.s0;
+      b.missing = ws->missing + c.s0;
+      b.status = ws->status + c.s0;
+      b.work_counter = ws->work_counter + (ci++ % tmgpu_workspace::kMaxChunks);
+      CU(launch_tokenize(b, v->group, mode == 0, v->sms, st, nullptr));
+      ws->last_launches++;
+    }
+  } else if (n > 0) {
+    const int e = ws->ev_head;
+    CU(cudaEventRecord(ws->ev0[e], st));
+    CU(launch_tokenize(a, v->group, mode == 0, v->sms, st, nullptr));
+    CU(cudaEventRecord(ws->ev1[e], st));
+    ws->ev_head = (e + 1) % tmgpu_workspace::kEv;
+    if (ws->ev_count < tmgpu_workspace::kEv) ws->ev_count++;
+    ws->last_launches++;
+  }
+  if (ck_total) {
+    int rc = chunk_run(ws, a, ck_total, mode, st);
+    if (rc) return rc;
+    a.skip = nullptr;
+  }
+  {
+    int rc = unicode_pass(ws, a, mode == 0, st);
+    if (rc) return rc;
+  }
+  if (mode == 0) {
+    CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, ws->counts, ws->tok_off, n + 1, st));
+    ws->last_launches += 2;  // cub::DeviceScan = init kernel + scan kernel
+    if (n > 0) {
+      CU(launch_pack(a.slab, d_off, ws->slab_pad, slab_off, ws->counts, ws->tok_off, dense, n, enc_len, v->sms, st));
+      ws->last_launches++;
+    }
+  }
+  return TMGPU_OK;
+}
+
+extern "C" int tmgpu_tokenize_device(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t* d_off, uint32_t n,
+                                     uint8_t enc_len, int mode, void* stream, tmgpu_device_view* view) {
+  if (!ws || !d_off || (!d_data && n) || !(mode == 0 || mode == 1)) {
+    g_err = "tmgpu_tokenize_device: bad argument";
+    return TMGPU_E_ARG;
+  }
+  if (enc_len == 0) enc_len = ws->v->host.n_reverse <= 65536 ? 2 : 3;  // go:990-996
+  if (mode == 0 && !(enc_len == 2 || enc_len == 3 || enc_len == 4)) {
+    g_err = "invalid encoding length";  // go:1012
+    return TMGPU_E_ARG;
+  }
+  if (n > ws->max_strings) {
+    g_err = "batch has more strings than the workspace was created for";
+    return TMGPU_E_ARG;
+  }
+  if (reinterpret_cast<uintptr_t>(d_data) & 15) {
+    g_err = "d_data must be 16-byte aligned";
+    return TMGPU_E_ARG;
+  }
+  CU(cudaSetDevice(ws->v->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);  // NULL = the CUDA default stream
+  int rc = tokenize_on_stream(ws, d_data, d_off, n, enc_len, mode, st, nullptr, ws->slab, ws->tokens);
+  if (rc) return rc;
+  if (view) {
+    view->tokens = ws->tokens;
+    view->tok_off = ws->tok_off;
+    view->missing = ws->missing;
+    view->status = ws->status;
+    view->n_tokens = ws->tok_off + n;
+    view->counts = ws->counts;
+  }
+  return TMGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer calls
+// ------------------------------------------------------------------------------------------
+int ensure_host_path(tmgpu_vocab* v, uint32_t n, uint64_t bytes) {
+  if (v->device < 0) {
+    g_err = "vocabulary was created without a device (this library has no CPU path)";
+    return TMGPU_E_CUDA;
+  }
+  CU(cudaSetDevice(v->device));
+  if (!v->ws || v->ws->max_strings < n || v->ws->max_bytes < bytes) {
+    if (v->ws) {
+      CU(cudaStreamSynchronize(v->stream));
+      tmgpu_workspace_destroy(v->ws);
+      v->ws = nullptr;
+    }
+    uint32_t ms = n < 1024 ? 1024 : n + n / 8;
+    uint64_t mb = bytes < (1u << 20) ? (1u << 20) : bytes + bytes / 8;
+    int rc = tmgpu_workspace_create(v, ms, mb, &v->ws);
+    if (rc) return rc;
+  }
+  if (v->d_in_cap < bytes + 64) {
+    if (v->d_in) cudaFree(v->d_in);
+    v->d_in = nullptr;
+    v->d_in_cap = bytes + bytes / 8 + 4096;
+    CU(cudaMalloc(&v->d_in, v->d_in_cap));
+  }
+  if (v->d_off_cap < size_t(n) + 1) {
+    if (v->d_off) cudaFree(v->d_off);
+    if (v->h_off) cudaFreeHost(v->h_off);
+    v->d_off = nullptr;
+    v->h_off = nullptr;
+    v->d_off_cap = size_t(n) + n / 8 + 1024;
+    CU(cudaMalloc(&v->d_off, v->d_off_cap * 16));
+    CU(cudaMallocHost(&v->h_off, v->d_off_cap * 16));
+  }
+  return TMGPU_OK;
+}
+
+void release_priv(ResultPriv* p) {
+  if (!p) return;
+  if (p->v) {
+    std::lock_guard<std::mutex> lock(p->v->pin_mu);
+    for (void* q : p->blocks)
+      for (auto& b : p->v->pinned)
+        if (b.p == q) b.used = false;
+  }
+  delete p;
+}
+
+extern "C" void tmgpu_result_free(tmgpu_result* r) {
+  if (!r) return;
+  release_priv(static_cast<ResultPriv*>(r->priv));
+  delete r;
+}
+
+extern "C" void tmgpu_bytes_free(tmgpu_bytes* b) {
+  if (!b) return;
+  release_priv(static_cast<ResultPriv*>(b->priv));
+  delete b;
+}
+
+// stage host strings: offsets rebased to 0 go first, then the bytes in chunks on the copy stream;
+// each chunk records an event the compute stream waits on, so copy k+1 overlaps kernel k.
+int stage_input(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off, uint32_t n, uint64_t* total,
+                       std::vector<ChunkPlan>* plan) {
+  const uint64_t base = off[0];
+  for (uint32_t i = 0; i <= n; i++) {
+    if (off[i] < base || (i && off[i] < off[i - 1])) {
+      g_err = "offsets must be non-decreasing";
+      return TMGPU_E_ARG;
+    }
+    if (i && off[i] - off[i - 1] > 0x3FFFFFFFull) {
+      g_err = "a single string may not exceed 1 GiB";
+      return TMGPU_E_ARG;
+    }
+    v->h_off[i] = int64_t(off[i] - base);
+  }
+  *total = off[n] - base;
+  return stage_copy(v, data + base, n, *total, false, plan);
+}
+
+// h_off[0..n] (and, if gapped, the end offsets behind them) are filled in; `src` holds `total`
+// bytes that go to d_in verbatim.
+int stage_copy(tmgpu_vocab* v, const uint8_t* src, uint32_t n, uint64_t total_bytes, bool gapped,
+                      std::vector<ChunkPlan>* plan) {
+  const uint64_t* total = &total_bytes;
+  // watermark = 0, then the offsets; the compute stream may start once both are on the device
+  v->h_info[40] = 0;
+  CU(cudaMemcpyAsync(v->d_run + 4, v->h_info + 40, 8, cudaMemcpyHostToDevice, v->copy_stream));
+  CU(cudaMemcpyAsync(v->d_off, v->h_off, (size_t(n) + 1) * 8, cudaMemcpyHostToDevice, v->copy_stream));
+  if (gapped && n)
+    CU(cudaMemcpyAsync(v->d_off + v->d_off_cap, v->h_off + v->d_off_cap, size_t(n) * 8, cudaMemcpyHostToDevice,
+                       v->copy_stream));
+  CU(cudaEventRecord(v->chunk_ev[31], v->copy_stream));
+  // chunks of ~equal bytes; after each one the watermark (bytes landed) moves forward
+  int want = int(*total / (16ull << 20)) + 1;
+  if (want > 24) want = 24;
+  if (n < uint32_t(v->sms) * 800u) want = 1;   // small batches: one copy, then the plain path
+  if (plan) plan->clear();
+  uint32_t s0 = 0;
+  const uint32_t pad = v->ws->slab_pad;
+  for (int c = 0; c < want && s0 < n; c++) {
+    uint32_t s1 = n;
+    if (c + 1 < want) {
+      const uint64_t target = *total * uint64_t(c + 1) / uint64_t(want);
+      uint32_t lo = s0, hi = n;  // first string whose end offset passes the target
+      while (lo < hi) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (uint64_t(v->h_off[mid + 1]) < target) lo = mid + 1; else hi = mid;
+      }
+      s1 = lo + 1 > n ? n : lo + 1;
+    }
+    const uint64_t b0 = uint64_t(v->h_off[s0]), b1 = uint64_t(v->h_off[s1]);
+    if (b1 > b0) CU(cudaMemcpyAsync(v->d_in + b0, src + b0, b1 - b0, cudaMemcpyHostToDevice, v->copy_stream));
+    v->h_info[41 + c] = b1;
+    CU(cudaMemcpyAsync(v->d_run + 4, v->h_info + 41 + c, 8, cudaMemcpyHostToDevice, v->copy_stream));
+    CU(cudaEventRecord(v->chunk_ev[c], v->copy_stream));
+    if (plan) plan->push_back({s0, s1, (b0 - uint64_t(v->h_off[0])) + uint64_t(pad) * s0, v->chunk_ev[c]});
+    s0 = s1;
+  }
+  if (!plan) CU(cudaStreamSynchronize(v->copy_stream));
+  return TMGPU_OK;
+}
+
+// If a string produced more ids than its slab share (len + 16), run again with exact sizes.
+// On success *dense points at the serialized ids to copy out; temp holds what to cudaFree.
+int rerun_if_overflow(tmgpu_vocab* v, uint32_t n, uint8_t enc_len, std::vector<void*>* temp,
+                             uint8_t** dense, const int64_t* d_ends) {
+  tmgpu_workspace* ws = v->ws;
+  uint32_t flag = 0;
+  CU(cudaMemcpyAsync(&flag, ws->overflow, 4, cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaStreamSynchronize(v->stream));
+  if (!flag) return TMGPU_OK;
+  CU(cudaMemsetAsync(ws->need + n, 0, 4, v->stream));
+  uint64_t* slab_off = nullptr;
+  int rc = dev_alloc(*temp, &slab_off, size_t(n) + 1);
+  if (rc) return rc;
+  CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, ws->need, slab_off, n + 1, v->stream));
+  uint64_t total = 0;
+  CU(cudaMemcpyAsync(&total, slab_off + n, 8, cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaStreamSynchronize(v->stream));
+  uint32_t* big = nullptr;
+  if ((rc = dev_alloc(*temp, &big, total + 16))) return rc;
+  uint8_t* d = nullptr;
+  if ((rc = dev_alloc(*temp, &d, (total + 16) * 4))) return rc;
+  if ((rc = tokenize_on_stream(ws, v->d_in, v->d_off, n, enc_len, 0, v->stream, slab_off, big, d, nullptr, d_ends)))
+    return rc;
+  *dense = d;
+  return TMGPU_OK;
+}
+
+// Large host batches: ONE launch of the tokenize kernel runs while the strings are still being
+// copied in.  stage_input() issues the H2D copies in chunks on the copy stream and, after each,
+// an 8-byte copy that advances a device "watermark" (bytes landed); a lane that pulls a string
+// beyond the watermark sleeps until its bytes are there.  No SM is needed to move the watermark
+// (it is a DMA write), so the persistent kernel can own the whole GPU.
+int tokenize_streamed(tmgpu_vocab* v, uint32_t n, uint8_t enc_len, cudaEvent_t offsets_ready,
+                             const int64_t* d_ends) {
+  tmgpu_workspace* ws = v->ws;
+  cudaStream_t st = v->stream;
+  ws->last_launches = 0;
+  CU(cudaMemsetAsync(ws->work_counter, 0, 4 * tmgpu_workspace::kMaxChunks, st));
+  CU(cudaMemsetAsync(ws->overflow, 0, 4, st));
+  CU(cudaMemsetAsync(ws->counts + n, 0, 4, st));
+  CU(cudaStreamWaitEvent(st, offsets_ready, 0));
+  TokenizeArgs a{};
+  a.v = v->dev;
+  a.data = v->d_in;
+  a.off = v->d_off;
+  a.ends = d_ends;
+  a.n = n;
+  a.slab = ws->slab;
+  a.slab_pad = ws->slab_pad;
+  a.counts = ws->counts;
+  a.need = ws->need;
+  a.missing = ws->missing;
+  a.status = ws->status;
+  a.work_counter = ws->work_counter;
+  a.overflow = ws->overflow;
+  a.watermark = reinterpret_cast<const unsigned long long*>(v->d_run + 4);
+  CU(launch_tokenize(a, v->group, true, v->sms, st, nullptr));
+  {
+    TokenizeArgs whole = a;
+    whole.watermark = nullptr;
+    int rc = unicode_pass(ws, whole, true, st);
+    if (rc) return rc;
+  }
+  CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, ws->counts, ws->tok_off, n + 1, st));
+  CU(launch_pack(ws->slab, v->d_off, ws->slab_pad, nullptr, ws->counts, ws->tok_off, ws->tokens, n, enc_len, v->sms, st));
+  ws->last_launches = 4;
+  return TMGPU_OK;
+}
+
+extern "C" int tmgpu_tokenize_batch(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off, uint32_t n,
+                                    uint8_t enc_len, tmgpu_result** out) {
+  if (!v || !off || !out || (!data && n && off[n] != off[0])) {
+    g_err = "tmgpu_tokenize_batch: null argument";
+    return TMGPU_E_ARG;
+  }
+  if (enc_len == 0) enc_len = v->host.n_reverse <= 65536 ? 2 : 3;
+  if (!(enc_len == 2 || enc_len == 3 || enc_len == 4)) {
+    g_err = "invalid encoding length";
+    return TMGPU_E_ARG;
+  }
+  std::lock_guard<std::mutex> lock(v->mu);
+  int rc = ensure_host_path(v, n, off[n] - off[0]);
+  if (rc) return rc;
+  uint64_t total = 0;
+  std::vector<ChunkPlan> plan;
+  if ((rc = stage_input(v, data, off, n, &total, &plan))) return rc;
+  tmgpu_workspace* ws = v->ws;
+  if (plan.size() > 1 && v->host.max_len != 0) {
+    // streamed: the kernel is already chasing the copies (stage_input armed the watermark)
+    if ((rc = tokenize_streamed(v, n, enc_len, v->chunk_ev[31]))) return rc;
+  } else
+  if ((rc = tokenize_on_stream(ws, v->d_in, v->d_off, n, enc_len, 0, v->stream, nullptr, ws->slab, ws->tokens, &plan)))
+    return rc;
+  std::vector<void*> temp;
+  uint8_t* dense = ws->tokens;
+  auto cleanup = [&]() {
+    for (void* p : temp) cudaFree(p);
+    temp.clear();
+  };
+  if ((rc = rerun_if_overflow(v, n, enc_len, &temp, &dense))) {
+    cleanup();
+    return rc;
+  }
+  auto* priv = new ResultPriv();
+  priv->v = v;
+  auto* r = new tmgpu_result();
+  std::memset(r, 0, sizeof(*r));
+  r->priv = priv;
+  r->n = n;
+  r->enc_len = enc_len;
+  auto bail = [&](int code) {
+    cleanup();
+    tmgpu_result_free(r);
+    return code;
+  };
+  if ((rc = pinned_alloc(priv, &r->tok_off, size_t(n) + 1))) return bail(rc);
+  if ((rc = pinned_alloc(priv, &r->missing, size_t(n) + 1))) return bail(rc);
+  if ((rc = pinned_alloc(priv, &r->status, size_t(n) + 1))) return bail(rc);
+  cudaError_t e;
+  e = cudaMemcpyAsync(r->tok_off, ws->tok_off, (size_t(n) + 1) * 8, cudaMemcpyDeviceToHost, v->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(r->missing, ws->missing, size_t(n) * 4, cudaMemcpyDeviceToHost, v->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(r->status, ws->status, size_t(n), cudaMemcpyDeviceToHost, v->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(v->stream);
+  if (e != cudaSuccess) {
+    g_err = std::string("tokenize: ") + cudaGetErrorString(e);
+    return bail(TMGPU_E_CUDA);
+  }
+  r->n_tokens = r->tok_off[n];
+  if ((rc = pinned_alloc(priv, &r->tokens, r->n_tokens * enc_len + 8))) return bail(rc);
+  if (r->n_tokens) {
+    e = cudaMemcpyAsync(r->tokens, dense, r->n_tokens * enc_len, cudaMemcpyDeviceToHost, v->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(v->stream);
+    if (e != cudaSuccess) {
+      g_err = std::string("tokenize D2H: ") + cudaGetErrorString(e);
+      return bail(TMGPU_E_CUDA);
+    }
+  }
+  cleanup();
+  *out = r;
+  return TMGPU_OK;
+}
+
+extern "C" int tmgpu_count_batch(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off, uint32_t n,
+                                 uint64_t* counts, uint32_t* missing, uint8_t* status) {
+  if (!v || !off || !counts) {
+    g_err = "tmgpu_count_batch: null argument";
+    return TMGPU_E_ARG;
+  }
+  std::lock_guard<std::mutex> lock(v->mu);
+  int rc = ensure_host_path(v, n, off[n] - off[0]);
+  if (rc) return rc;
+  uint64_t total = 0;
+  std::vector<ChunkPlan> plan;
+  if ((rc = stage_input(v, data, off, n, &total, &plan))) return rc;
+  tmgpu_workspace* ws = v->ws;
+  if ((rc = tokenize_on_stream(ws, v->d_in, v->d_off, n, 0, 1, v->stream, nullptr, ws->slab, ws->tokens, &plan)))
+    return rc;
+  std::vector<uint32_t> c(n + 1), m(n + 1);
+  std::vector<uint8_t> s(n + 1);
+  CU(cudaMemcpyAsync(c.data(), ws->counts, size_t(n) * 4, cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaMemcpyAsync(m.data(), ws->missing, size_t(n) * 4, cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaMemcpyAsync(s.data(), ws->status, size_t(n), cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaStreamSynchronize(v->stream));
+  for (uint32_t i = 0; i < n; i++) {
+    counts[i] = c[i];
+    if (missing) missing[i] = m[i];
+    if (status) status[i] = s[i];
+  }
+  return TMGPU_OK;
+}
+
+// The tokenization loop of the training worker (training/trainvocab.go:932-1170) for one candidate
+// vocabulary over a batch of data strips.
+extern "C" int tmgpu_score_batch(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off, uint32_t n,
+                                 uint64_t* scores, uint64_t* miss_hist, uint64_t* tokens_in_text, uint8_t* status) {
+  if (!v || !off || !scores || !tokens_in_text) {
+    g_err = "tmgpu_score_batch: null argument";
+    return TMGPU_E_ARG;
+  }
+  std::lock_guard<std::mutex> lock(v->mu);
+  int rc = ensure_host_path(v, n, off[n] - off[0]);
+  if (rc) return rc;
+  uint64_t total = 0;
+  std::vector<ChunkPlan> plan;
+  if ((rc = stage_input(v, data, off, n, &total, &plan))) return rc;
+  tmgpu_workspace* ws = v->ws;
+  if ((rc = tokenize_on_stream(ws, v->d_in, v->d_off, n, 0, 2, v->stream, nullptr, ws->slab, ws->tokens, &plan)))
+    return rc;
+  const size_t nr = v->host.n_reverse;
+  std::vector<uint32_t> c(size_t(n) + 1);
+  std::vector<uint8_t> s(size_t(n) + 1);
+  std::vector<unsigned long long> hist(256);
+  if (v->host.max_len == 0) {
+    std::memset(scores, 0, nr * 8);
+    if (miss_hist) std::memset(miss_hist, 0, 256 * 8);
+  } else {
+    CU(cudaMemcpyAsync(scores, ws->score_buf, nr * 8, cudaMemcpyDeviceToHost, v->stream));
+    CU(cudaMemcpyAsync(hist.data(), ws->score_buf + nr, 256 * 8, cudaMemcpyDeviceToHost, v->stream));
+  }
+  CU(cudaMemcpyAsync(c.data(), ws->counts, size_t(n) * 4, cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaMemcpyAsync(s.data(), ws->status, size_t(n), cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaStreamSynchronize(v->stream));
+  uint64_t t = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    t += c[i];
+    if (status) status[i] = s[i];
+  }
+  *tokens_in_text = t;
+  if (miss_hist && v->host.max_len != 0)
+    for (int b = 0; b < 256; b++) miss_hist[b] = hist[b];
+  return TMGPU_OK;
+}

@@ -1,4 +1,4 @@
-// kernels.h -- launcher interface between the C-ABI host code (abi.cu) and the device code.
+// kernels.h -- launcher interface between the C-ABI host code (abi*.cu) and the device code.
 #pragma once
 #include <cuda_runtime.h>
 

@@ -1,5 +1,5 @@
 // unicode_dev.h -- device-side view of the Unicode character data and the normalizer's arguments
-// (shared by the host code in abi.cu and the kernels in unicode_normalize.cuh).
+// (shared by the host code in abi*.cu and the kernels in unicode_normalize.cuh).
 #pragma once
 #include <cstdint>
 
