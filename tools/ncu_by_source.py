@@ -1,3 +1,10 @@
+"""Executed warp instructions and active lanes per source region of one kernel.
+
+    cuobjdump -xelf all libtmgpu.so; nvdisasm -g -c *.cubin > /tmp/all.sass      # SASS with line info
+    ncu -i report.ncu-rep --page source --csv > src.csv
+    python tools/ncu_by_source.py <mangled kernel name> src.csv
+Joins the n-th SASS instruction of the kernel (nvdisasm order) with the n-th row of the source
+page; prints 10-line source buckets that hold >= 0.4 % of the warp instructions."""
 import re,csv,sys
 kname=sys.argv[1]; srccsv=sys.argv[2]
 lines=open('/tmp/all.sass').read().split('\n')
@@ -24,7 +31,7 @@ for k in range(min(len(ins),len(data))):
 tot=sum(v[0] for v in agg.values())
 import glob,os
 files={}
-for f in glob.glob('/root/repo/tokenmonster_b200/csrc/*'):
+for f in glob.glob(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tokenmonster_b200', 'csrc', '*')):
     files[os.path.basename(f)]=open(f).read().split('\n')
 # group by ranges of source lines (per file) in buckets
 rng=defaultdict(lambda:[0,0])

@@ -1,3 +1,4 @@
+"""Selected lines of `ncu --page raw` for one report:  python tools/ncu_summary.py report.ncu-rep"""
 import csv,sys,subprocess
 rep=sys.argv[1]
 out=subprocess.run(['ncu','-i',rep,'--page','raw','--csv'],capture_output=True,text=True).stdout
