@@ -230,3 +230,63 @@ def test_non_ascii_decode_and_round_trip(built, capcode, normflag):
         assert outs[k] + tail[k] == back[int(boff[s]):int(boff[s + 1])].tobytes(), (k, texts[s])
     dec.close()
     v.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# committed fixtures (tests/golden/unicode_cases.json, frozen oracle answers on Unicode 15.0)
+# ---------------------------------------------------------------------------------------------
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _unicode_fixture():
+    import json
+    with open(os.path.join(GOLD, "unicode_cases.json")) as f:
+        cases = json.load(f)
+    with open(os.path.join(GOLD, "unicode_cap2.vocab"), "rb") as f:
+        vb = f.read()
+    return cases, vb
+
+
+def test_oracle_reproduces_committed_unicode_fixtures():
+    cases, vb = _unicode_fixture()
+    assert cases["unicode"] == "15.0.0" and make_unicode_vocab(2, 1) == vb     # the stand-in is deterministic
+    chk = oracle.OracleVocab(vb, "port")
+    for row in cases["rows"]:
+        t = bytes.fromhex(row["in"])
+        ids, miss, st = expect(chk, t, 1, 2)
+        assert st == row["status"]
+        if st == 0:
+            assert uo.normalize(t, 1, 2).hex() == row["norm"]
+            assert ids.tolist() == row["ids"] and miss == row["missing"]
+
+
+@pytest.mark.gpu
+def test_device_matches_committed_unicode_fixtures(built):
+    from tokenmonster_b200 import Vocab
+    os.environ["TMGPU_GROUP"] = "1"
+    cases, vb = _unicode_fixture()
+    rows = cases["rows"]
+    texts = [bytes.fromhex(r["in"]) for r in rows]
+    off = np.zeros(len(texts) + 1, np.uint64)
+    off[1:] = np.cumsum([len(t) for t in texts])
+    data = np.frombuffer(b"".join(texts), np.uint8)
+    v = Vocab(vb, device=0)
+    r = v.tokenize_batch(data, off, 4)
+    counts, _, _ = v.count_batch(data, off)
+    back, boff = v.decode_batch(r.raw, r.tok_off, 4)
+    scores, hist, tit, status = v.score_batch(data, off)
+    want_scores = np.zeros_like(scores)
+    want_tit = 0
+    for s, row in enumerate(rows):
+        assert int(r.status[s]) == row["status"] == int(status[s]), s
+        if row["status"]:
+            assert len(r[s]) == 0
+            continue
+        assert r[s].astype(np.uint32).tolist() == row["ids"], s
+        assert int(r.missing[s]) == row["missing"] and int(counts[s]) == row["count"], s
+        assert back[int(boff[s]):int(boff[s + 1])].tobytes().hex() == row["decoded"], s
+        for k, val in row["scores"].items():
+            want_scores[int(k)] += val
+        want_tit += row["tokens_in_text"]
+    assert np.array_equal(scores, want_scores) and tit == want_tit
+    v.close()
