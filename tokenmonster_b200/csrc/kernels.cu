@@ -1,9 +1,18 @@
 // kernels.cu -- device code of libtmgpu.so (sm_100a only) and its launchers.
-//   K1/K3 tokenize_kernel        (tokenize_kernel.cuh)
-//   pack_tokens_kernel           slab of u32 ids -> dense 2/3/4-byte serialized ids
-//                                (the emit variants go/tokenmonster.go:1545/:1817/:2089)
-//   K2 decode_size / decode_copy reverse[id] gather (go/tokenmonster.go:813-948)
-//   capcode_decode_kernel        capcode level-2 decoder (javascript/tokenmonster.js:1007-1065)
+//   K1/K3 tokenize_thread_kernel  one lane per string, the default (tokenize_thread_kernel.cuh);
+//                                 also the chunk launch for long documents (CHUNK = true), the
+//                                 second pass over normalized non-ASCII text ("prenorm") and the
+//                                 training-score histogram (count kernels with A.scores set)
+//   K1/K3 tokenize_kernel         G lanes per string, alternative mapping (tokenize_kernel.cuh)
+//   unicode_normalize_kernel      NFD / accents / lowercase / capcode per code point
+//                                 (unicode_normalize.cuh)
+//   chunk_* kernels               plan, stitch and gather for long documents (chunking.cuh)
+//   pack_tokens_kernel            slab of u32 ids -> dense 2/3/4-byte serialized ids
+//                                 (the emit variants go/tokenmonster.go:1545/:1817/:2089)
+//   wire_frame_kernel             reply framing of the server protocol
+//   K2 decode_size / decode_copy  reverse[id] gather (go/tokenmonster.go:813-948)
+//   capcode_decode_kernel         capcode level-2 decoder (javascript/tokenmonster.js:1007-1065)
+//   stream_tail / copy_tail       the streaming decoder's incomplete-sequence remainder
 #include "kernels.h"
 
 #include <cstdlib>

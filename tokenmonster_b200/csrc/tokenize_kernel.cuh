@@ -1,4 +1,10 @@
-// tokenize_kernel.cuh -- K1/K3: batched normalize -> capcode -> 6-branch ungreedy match.
+// tokenize_kernel.cuh -- K1/K3, mapping 1 (G lanes per string): batched normalize -> capcode ->
+// 6-branch ungreedy match.  This is the mapping the north star describes and the first one
+// built; the default since is mapping 2 (tokenize_thread_kernel.cuh, one lane per string), which
+// is 2x faster on large batches.  This one stays selectable (TMGPU_GROUP=4|8|16|32) and under
+// test as an independent implementation of the same semantics; it does ASCII text only (the
+// non-ASCII pass, chunking and scores always use mapping 2) and shares the TMA table staging,
+// the ring constants and lower4() with it.
 //
 // Replaces, for a whole batch of strings at once,
 //   /root/reference go/tokenmonster.go:242-253  normalize + applyCapcode
