@@ -413,11 +413,25 @@ typedef struct {
 /* Evaluate the continuation that starts at data position p after a first token with
  * (aflag, nw).  base = bytes the first token consumes; ref_len < 0 for the primary branch,
  * otherwise the primary length used for the alt penalties (go:1132-1133). */
+/* Diagnostics for the design notes (tools/walk_reuse.py): how many look-ahead searches the loop
+ * performs and how many of the plain ones repeat a position searched during the previous steps. */
+static uint64_t g_dbg[4];        /* plain searches, retry searches, plain repeats, steps */
+static int g_recent[8], g_recent_n;
+void tmo_debug_walk_stats(uint64_t out[4], int reset) {
+  for (int k = 0; k < 4; k++) out[k] = g_dbg[k];
+  if (reset) { memset(g_dbg, 0, sizeof g_dbg); g_recent_n = 0; }
+}
+
 static void eval_branch(const tmo_vocab* v, const uint8_t* data, int len_data, int p, int base,
                         uint8_t aflag, int nw, int ref_len, int off, cand* c) {
   c->score = c->score_b = NEG;
   int room = len_data - p;
   if (room < 0) return;
+  g_dbg[0]++;
+  for (int k = 0; k < g_recent_n; k++)
+    if (g_recent[k] == p) { g_dbg[2]++; break; }
+  if (g_recent_n < 8) g_recent[g_recent_n++] = p;
+  else { memmove(g_recent, g_recent + 1, 7 * sizeof(int)); g_recent[7] = p; }
   uint32_t x;
   int l = tmo_longest_prefix(v, data + p, (size_t)(room < v->max_len ? room : v->max_len), &x);
   if (l == 0) return;
@@ -438,6 +452,7 @@ static void eval_branch(const tmo_vocab* v, const uint8_t* data, int len_data, i
     lil[1] = 0;
     memcpy(lil + off, data + p, (size_t)take);
     uint32_t xb = 0;
+    g_dbg[1]++;
     int lb = tmo_longest_prefix(v, lil, (size_t)(take + off), &xb);
     if (lb > l + 1) {
       lb -= off;
@@ -476,6 +491,7 @@ static void tokenize_core(const tmo_vocab* v, const uint8_t* data, int len_data,
       continue;
     }
     for (;;) { /* "checkpoint" */
+      g_dbg[3]++;
       const tmo_rec* o = &v->rec[index];
       int i1 = i + length;
       int advanced = 0;

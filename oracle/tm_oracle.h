@@ -88,6 +88,10 @@ int tmo_tokenize(const tmo_vocab* v, const uint8_t* in, size_t n, int normalized
 int tmo_score(const tmo_vocab* v, const uint8_t* in, size_t n, int normalized, uint64_t* scores,
               uint64_t* miss_hist, uint64_t* tokens_in_text);
 
+/* diagnostics (not thread safe): look-ahead searches {plain, retry, plain repeats of one of the
+ * previous 8 positions, steps} since the last reset */
+void tmo_debug_walk_stats(uint64_t out[4], int reset);
+
 int tmo_decode(const tmo_vocab* v, const void* tokens, size_t n_tokens_or_bytes, int enc_len,
                int raw, uint8_t** out, size_t* out_n);
 
