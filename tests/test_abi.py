@@ -27,6 +27,15 @@ def test_library_exports_every_declared_symbol(built):
     assert b"sm_100a" in lib.tmgpu_version()
 
 
+def test_header_is_plain_c(tmp_path):
+    """cgo (and any C FFI) compiles include/tmgpu.h as C, not C++."""
+    import subprocess
+    src = tmp_path / "h.c"
+    src.write_text('#include "tmgpu.h"\nint main(void) { tmgpu_vocab* v = 0; (void)v; return 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    "-c", str(src), "-o", str(tmp_path / "h.o")], check=True)
+
+
 def test_host_only_vocab_and_no_cpu_path(built):
     from tokenmonster_b200 import TmgpuError, Vocab
     with open(os.path.join(GOLD, "gpt2.vocab"), "rb") as f:
