@@ -16,6 +16,46 @@ constexpr uint32_t kNoVal = 0xFFFFFFFFu;   // "no child" / empty edge key
 constexpr uint32_t kRootStart = 0xFFFFFFFEu;  // walk starts at the trie root
 constexpr int kNegScore = -1000000;        // go/tokenmonster.go:1059-1065 sentinel
 
+// ---- reversed-key automaton (vocab_tables.h has the table description) ------------------------
+constexpr uint32_t kDfaStateBits = 20;
+constexpr uint32_t kDfaStateMask = (1u << kDfaStateBits) - 1u;
+constexpr uint32_t kDfaEmpty = 0x7FFFFFFFu;
+constexpr uint32_t kDfaOverflow = 0x80000000u;
+TM_HD uint32_t dfa_len(uint32_t packed) { return (packed >> 20) & 63u; }
+TM_HD uint32_t dfa_splen(uint32_t packed) { return packed >> 26; }
+TM_HD uint32_t dfa_hash(uint32_t key, uint32_t shift) { return (key * 0x9E3779B1u) >> shift; }
+
+struct DfaDev {
+  const uint4* buckets;      // 2 x uint4 per bucket: keys, values
+  const uint32_t* d2;        // 65536
+  const uint4* hot;          // per state
+  uint32_t shift;            // 32 - log2(buckets)
+  uint32_t mask;             // buckets - 1
+  uint32_t n_states;
+};
+
+// One transition: the packed state after consuming byte b (previous text byte `prev`) from the
+// state in `packed`.  load4(i) reads uint4 number i of the bucket array, d2(i) entry i of dfa_d2.
+template <class Load4, class LoadD2>
+TM_HD uint32_t dfa_next(uint32_t packed, uint32_t prev, uint32_t b, uint32_t shift, uint32_t mask, Load4 load4,
+                        LoadD2 d2) {
+  const uint32_t s = packed & kDfaStateMask;
+  if (s != 0) {   // the root has no transition to depth >= 3
+    const uint32_t key = (s << 8) | b;
+    uint32_t h = dfa_hash(key, shift);
+    for (;;) {
+      const uint4 k = load4(2 * h), v = load4(2 * h + 1);
+      if ((k.x & ~kDfaOverflow) == key) return v.x;
+      if (k.y == key) return v.y;
+      if (k.z == key) return v.z;
+      if (k.w == key) return v.w;
+      if (!(k.x & kDfaOverflow)) break;
+      h = (h + 1) & mask;
+    }
+  }
+  return d2((prev << 8) | b);
+}
+
 // Everything a kernel needs about one vocabulary (device pointers + scalars).
 struct VocabDev {
   const uint2* edges;          // hashed trie edges {key = parent<<8|byte, val = child|sig<<24}
@@ -33,6 +73,8 @@ struct VocabDev {
   int max_len;                 // maxTokenLength
   int off;                     // 1, or 2 for UTF-16 (lilbufOffset, go:1031-1034)
   uint8_t capcode, normflag, charset, pad;
+  DfaDev dfa;
+  const uint8_t* pipe_image;   // 1536 B staged per CTA: dfa_d1[256] (u32), begin_byte[256], class_code[256]
 };
 
 TM_HD uint32_t sig_bit_of(uint32_t b) { return (b ^ (b >> 3)) & 7u; }

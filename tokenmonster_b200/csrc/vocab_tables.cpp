@@ -3,6 +3,7 @@
 // worked example tokenmonster-cpp/tests/unit.cpp:12-79.
 #include "vocab_tables.h"
 
+#include <algorithm>
 #include <cstring>
 #include <string_view>
 #include <unordered_map>
@@ -31,6 +32,196 @@ struct Cursor {
 };
 }  // namespace
 
+struct KeyRef {
+  uint32_t off;
+  uint8_t len;
+};
+
+// Reversed-key Aho-Corasick automaton in DFA form (vocab_tables.h describes the tables).
+static int build_dfa(HostTables* t, const std::vector<KeyRef>& keys, const std::vector<uint8_t>& blob,
+                     const std::vector<uint8_t>& flag, const std::vector<uint8_t>& nwords, std::string* err) {
+  for (int b = 0; b < 256; b++) {
+    const uint8_t v = t->begin_byte[b];   // go:3780-3787 writes only these four values
+    if (v == 0) t->class_code[b] = 0;
+    else if (v == 1) t->class_code[b] = 1;
+    else if (v == 10) t->class_code[b] = 2;
+    else if (v == 12) t->class_code[b] = 3;
+    else {
+      *err = "beginByte table holds a value other than 0, 1, 10, 12";
+      return TMGPU_E_UNSUPPORTED;
+    }
+  }
+  // ---- trie of the reversed keys ---------------------------------------------------------
+  struct Node {
+    uint32_t fail = 0, term = kNone, child_begin = 0, child_end = 0;
+    uint8_t depth = 0;
+  };
+  std::vector<Node> nodes(1);
+  std::unordered_map<uint32_t, uint32_t> child_of;   // node<<8 | byte -> child
+  child_of.reserve(size_t(t->n_info) * 4);
+  struct Edge {
+    uint32_t parent, child;
+    uint8_t byte;
+  };
+  std::vector<Edge> edges;
+  for (uint32_t i = 0; i < t->n_info; i++) {
+    uint32_t at = 0;
+    for (int k = int(keys[i].len) - 1; k >= 0; k--) {
+      const uint8_t b = blob[keys[i].off + k];
+      if (nodes.size() >= (1u << kDfaStateBits)) {
+        *err = "vocabulary too large for the 20-bit automaton state space";
+        return TMGPU_E_UNSUPPORTED;
+      }
+      auto ins = child_of.emplace((at << 8) | b, uint32_t(nodes.size()));
+      if (ins.second) {
+        Node nd;
+        nd.depth = uint8_t(nodes[at].depth + 1);
+        nodes.push_back(nd);
+        edges.push_back({at, ins.first->second, b});
+      }
+      at = ins.first->second;
+    }
+    nodes[at].term = i;
+  }
+  const uint32_t N = uint32_t(nodes.size());
+  t->dfa_states = N;
+  std::sort(edges.begin(), edges.end(), [](const Edge& a, const Edge& b) {
+    return a.parent != b.parent ? a.parent < b.parent : a.byte < b.byte;
+  });
+  for (size_t e = 0; e < edges.size(); e++) {
+    Node& p = nodes[edges[e].parent];
+    if (p.child_end == 0) p.child_begin = uint32_t(e);
+    p.child_end = uint32_t(e) + 1;
+  }
+  // ---- failure links, rows of the DFA restricted to targets at depth >= 2 ------------------
+  // row entry: byte << 24 | target, sorted by byte; row(s) = row(fail(s)) overridden by s's children
+  std::vector<std::vector<uint32_t>> row(N);
+  uint32_t d1[256];
+  for (int b = 0; b < 256; b++) {
+    auto it = child_of.find(uint32_t(b));
+    d1[b] = it == child_of.end() ? 0u : it->second;
+  }
+  auto delta = [&](uint32_t s, uint32_t b) -> uint32_t {
+    const std::vector<uint32_t>& r = row[s];
+    size_t lo = 0, hi = r.size();
+    while (lo < hi) {
+      const size_t mid = (lo + hi) / 2;
+      if ((r[mid] >> 24) < b) lo = mid + 1; else hi = mid;
+    }
+    if (lo < r.size() && (r[lo] >> 24) == b) return r[lo] & 0xFFFFFFu;
+    return d1[b];
+  };
+  std::vector<uint32_t> order;
+  order.reserve(N);
+  order.push_back(0);
+  std::vector<uint32_t> best_idx(N, kNone);
+  std::vector<uint8_t> best_len(N, 0);
+  for (size_t q = 0; q < order.size(); q++) {
+    const uint32_t s = order[q];
+    Node& nd = nodes[s];
+    if (s != 0) {
+      const std::vector<uint32_t>& base = row[nd.fail];
+      std::vector<uint32_t>& r = row[s];
+      r.reserve(base.size() + (nd.child_end - nd.child_begin));
+      size_t a = 0;
+      uint32_t e = nd.child_begin;
+      while (a < base.size() || e < nd.child_end) {
+        const uint32_t ba = a < base.size() ? (base[a] >> 24) : 256u;
+        const uint32_t be = e < nd.child_end ? edges[e].byte : 256u;
+        if (be <= ba) {
+          r.push_back((be << 24) | edges[e].child);
+          e++;
+          if (be == ba) a++;
+        } else {
+          r.push_back(base[a++]);
+        }
+      }
+      if (nd.term != kNone) { best_idx[s] = nd.term; best_len[s] = nd.depth; }
+      else { best_idx[s] = best_idx[nd.fail]; best_len[s] = best_len[nd.fail]; }
+    }
+    for (uint32_t e = nd.child_begin; e < nd.child_end; e++) {
+      const uint32_t c = edges[e].child;
+      nodes[c].fail = (s == 0) ? 0u : delta(nd.fail, edges[e].byte);
+      order.push_back(c);
+    }
+  }
+  // ---- the space-prefixed retry: best key ending at the virtual space ----------------------
+  std::vector<uint32_t> sp_idx(N, kNone);
+  std::vector<uint8_t> sp_len(N, 0);
+  for (uint32_t s = 0; s < N; s++) {
+    uint32_t x = s;
+    if (t->charset == 2) x = delta(x, 0x00);   // the virtual space is 0x20 0x00, consumed back to front
+    x = delta(x, 0x20);
+    sp_idx[s] = best_idx[x];
+    sp_len[s] = best_len[x];
+  }
+  auto pack = [&](uint32_t s) { return s | (uint32_t(best_len[s]) << 20) | (uint32_t(sp_len[s]) << 26); };
+  for (int b = 0; b < 256; b++) t->dfa_d1[b] = pack(d1[b]);
+  t->dfa_d2.assign(65536, 0);
+  for (uint32_t prev = 0; prev < 256; prev++)
+    for (uint32_t b = 0; b < 256; b++) t->dfa_d2[(prev << 8) | b] = pack(delta(d1[prev], b));
+  t->dfa_hot.assign(size_t(N) * 4, 0);
+  for (uint32_t s = 0; s < N; s++) {
+    uint32_t* h = &t->dfa_hot[size_t(s) * 4];
+    const uint32_t bi = best_len[s] ? best_idx[s] : 0u, si = sp_len[s] ? sp_idx[s] : 0u;
+    h[0] = bi | (uint32_t(best_len[s]) << 24);
+    h[1] = si | (uint32_t(sp_len[s]) << 24);
+    h[2] = (best_len[s] ? (uint32_t(flag[bi]) | (uint32_t(nwords[bi]) << 8)) : 0u) |
+           (sp_len[s] ? ((uint32_t(flag[si]) << 16) | (uint32_t(nwords[si]) << 24)) : 0u);
+  }
+  // ---- hashed transitions to depth >= 3 ----------------------------------------------------
+  size_t n_deep = 0;
+  for (uint32_t s = 1; s < N; s++)
+    for (uint32_t e : row[s])
+      if (nodes[e & 0xFFFFFFu].depth >= 3) n_deep++;
+  uint32_t bits = 4;
+  while ((size_t(1) << bits) * 2 < n_deep) bits++;   // on average <= 2 of 4 slots used
+  t->dfa_bits = bits;
+  const uint32_t mask = (1u << bits) - 1u, shift = 32u - bits;
+  t->dfa_buckets.assign((size_t(1) << bits) * 8, 0);
+  for (size_t b = 0; b < (size_t(1) << bits); b++)
+    for (int k = 0; k < 4; k++) t->dfa_buckets[b * 8 + k] = kDfaEmpty;
+  for (uint32_t s = 1; s < N; s++) {
+    for (uint32_t e : row[s]) {
+      const uint32_t tgt = e & 0xFFFFFFu;
+      if (nodes[tgt].depth < 3) continue;
+      const uint32_t key = (s << 8) | (e >> 24);
+      uint32_t h = dfa_hash(key, shift);
+      for (;;) {
+        uint32_t* bk = &t->dfa_buckets[size_t(h) * 8];
+        int slot = -1;
+        for (int k = 0; k < 4; k++)
+          if ((bk[k] & ~kDfaOverflow) == kDfaEmpty) { slot = k; break; }
+        if (slot >= 0) {
+          bk[slot] = (bk[slot] & kDfaOverflow) | key;
+          bk[4 + slot] = pack(tgt);
+          break;
+        }
+        bk[0] |= kDfaOverflow;
+        h = (h + 1) & mask;
+      }
+    }
+  }
+  return TMGPU_OK;
+}
+
+int host_dfa_lookup(const HostTables& h, const uint8_t* window, int n, uint32_t* index, uint32_t* sp_index,
+                    int* sp_len) {
+  const uint4* bk = reinterpret_cast<const uint4*>(h.dfa_buckets.data());
+  uint32_t w = 0;
+  for (int p = n - 1; p >= 0; p--) {
+    if (p == n - 1) w = h.dfa_d1[window[p]];
+    else
+      w = dfa_next(w, window[p + 1], window[p], 32u - h.dfa_bits, (1u << h.dfa_bits) - 1u,
+                   [&](uint32_t i) { return bk[i]; }, [&](uint32_t i) { return h.dfa_d2[i]; });
+  }
+  const uint32_t* hot = &h.dfa_hot[size_t(w & kDfaStateMask) * 4];
+  if (index) *index = hot[0] & 0xFFFFFFu;
+  if (sp_index) *sp_index = hot[1] & 0xFFFFFFu;
+  if (sp_len) *sp_len = int(dfa_splen(w));
+  return n > 0 ? int(dfa_len(w)) : 0;
+}
+
 int parse_vocab(const uint8_t* file, size_t n, HostTables* t, std::string* err) {
   Cursor c{file, n};
   if (n < 24) {
@@ -54,10 +245,7 @@ int parse_vocab(const uint8_t* file, size_t n, HostTables* t, std::string* err) 
   t->delete_token = c.u24();
   t->max_len = (int)c.u8();
 
-  struct Key {
-    uint32_t off;
-    uint8_t len;
-  };
+  using Key = KeyRef;
   std::vector<Key> keys(t->n_info);
   std::vector<uint8_t> blob;
   blob.reserve(size_t(t->n_info) * 8);
@@ -216,7 +404,7 @@ int parse_vocab(const uint8_t* file, size_t n, HostTables* t, std::string* err) 
   }
   for (uint32_t b = 0; b < 256; b++)
     t->sp_child[b] = t->space_start == kNone ? kNone : child_of(t->space_start & 0xFFFFFFu, b);
-  return TMGPU_OK;
+  return build_dfa(t, keys, blob, flag, nwords, err);
 }
 
 // spaced: 0 plain window, 1 window behind the virtual space; +2 = take the first steps from the

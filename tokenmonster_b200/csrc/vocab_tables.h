@@ -45,6 +45,33 @@ struct HostTables {
   uint32_t sp_child[256];        // val of space_start's child by byte, or kNone
   uint32_t n_nodes = 0;
 
+  // ---- reversed-key automaton (position-table pipeline, stage 2) -------------------------------
+  // Aho-Corasick over the REVERSED keys, run right to left over the normalized text: after the byte
+  // at position p has been consumed the state names the longest suffix-of-a-key that starts at p,
+  // and its first terminal on the failure chain is the longest KEY that starts at p -- the result
+  // of pansearch.Fast.LongestSubstring for the window at p (call sites go/tokenmonster.go:1049,
+  // 1068,...) with ONE transition per byte instead of one trie walk per window.
+  //   transition value ("packed state"): state | best_len << 20 | sp_len << 26
+  //     best_len = length of the longest key starting here (0 = none)
+  //     sp_len   = length of the longest key that prefixes  virtual space + text from here
+  //                (the lilbuf retry of go:1088-1107; includes the `off` prefix bytes; 0 = none)
+  //   dfa_d1[b]            first byte of a string (no previous byte)
+  //   dfa_d2[prev<<8 | b]  default: every transition whose target is at depth <= 2 depends only
+  //                        on the previous text byte and this one
+  //   dfa_buckets          hashed (state<<8|b) -> packed target for targets at depth >= 3;
+  //                        32-byte buckets of 4 keys + 4 values, bit 31 of key 0 = "overflowed
+  //                        into the next bucket", empty key = kDfaEmpty
+  //   dfa_hot[state]       what the chain stage reads per look-ahead position (4 x u32):
+  //                        w0 = best index | best_len<<24, w1 = sp index | sp_len<<24,
+  //                        w2 = best.flag | best.nWords<<8 | sp.flag<<16 | sp.nWords<<24, w3 = 0
+  uint32_t dfa_states = 0;
+  uint32_t dfa_bits = 0;
+  std::vector<uint32_t> dfa_buckets;
+  std::vector<uint32_t> dfa_d2;
+  uint32_t dfa_d1[256];
+  std::vector<uint32_t> dfa_hot;
+  uint8_t class_code[256];       // begin_byte as a 2-bit code: 0 -> 0, 1 -> 1, 10 -> 2, 12 -> 3
+
   // reverse table for decode: reverse[id] = LAST record with that id (go:2715)
   std::vector<uint32_t> rev_off; // n_reverse, offset into rev_blob
   std::vector<uint8_t> rev_len;  // n_reverse, 0xFF = nil
@@ -56,6 +83,10 @@ int parse_vocab(const uint8_t* file, size_t n, HostTables* out, std::string* err
 
 // host walk of the device trie for one window (table self-check; see tmgpu_selftest_trie_lookup)
 int host_trie_lookup(const HostTables& h, const uint8_t* window, int n, int spaced, uint32_t* index);
+
+// host run of the reversed automaton over a window: best match at window[0] (table self-check)
+int host_dfa_lookup(const HostTables& h, const uint8_t* window, int n, uint32_t* index, uint32_t* sp_index,
+                    int* sp_len);
 
 inline uint32_t sig_bit(uint32_t b) { return (b ^ (b >> 3)) & 7u; }
 inline uint32_t edge_hash(uint32_t key, uint32_t bits) { return (key * 0x9E3779B1u) >> (32u - bits); }
