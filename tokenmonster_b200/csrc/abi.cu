@@ -123,6 +123,22 @@ extern "C" int tmgpu_vocab_create(const uint8_t* file_bytes, size_t n, int devic
   if ((rc = upload(v, h.rev_off.data(), h.rev_off.size(), &d.rev_off))) return fail(rc);
   if ((rc = upload(v, h.rev_len.data(), h.rev_len.size(), &d.rev_len))) return fail(rc);
   if ((rc = upload(v, h.rev_blob.data(), h.rev_blob.size(), &d.rev_blob))) return fail(rc);
+  {
+    const uint32_t* bk = nullptr;
+    const uint32_t* hot = nullptr;
+    if ((rc = upload(v, h.dfa_buckets.data(), h.dfa_buckets.size(), &bk))) return fail(rc);
+    if ((rc = upload(v, h.dfa_d2.data(), h.dfa_d2.size(), &d.dfa.d2))) return fail(rc);
+    if ((rc = upload(v, h.dfa_hot.data(), h.dfa_hot.size(), &hot))) return fail(rc);
+    d.dfa.buckets = reinterpret_cast<const uint4*>(bk);
+    d.dfa.hot = reinterpret_cast<const uint4*>(hot);
+    d.dfa.shift = 32u - h.dfa_bits;
+    d.dfa.mask = (1u << h.dfa_bits) - 1u;
+    d.dfa.n_states = h.dfa_states;
+    std::vector<uint8_t> pimg(1536, 0);
+    std::memcpy(pimg.data(), h.dfa_d1, 1024);
+    std::memcpy(pimg.data() + 1024, h.class_code, 256);
+    if ((rc = upload(v, pimg.data(), pimg.size(), &d.pipe_image))) return fail(rc);
+  }
   d.n_info = h.n_info;
   d.n_reverse = h.n_reverse;
   d.unk = h.unk;
@@ -253,6 +269,8 @@ extern "C" void tmgpu_workspace_destroy(tmgpu_workspace* ws) {
   if (ws->v && ws->v->device >= 0) cudaSetDevice(ws->v->device);
   for (void* p : ws->allocs) cudaFree(p);
   if (ws->uni_text) cudaFree(ws->uni_text);
+  if (ws->p_text) cudaFree(ws->p_text);
+  if (ws->p_words) cudaFree(ws->p_words);
   for (void* p : ws->ck_allocs) cudaFree(p);
   for (int i = 0; i < tmgpu_workspace::kEv; i++) {
     if (ws->ev0[i]) cudaEventDestroy(ws->ev0[i]);
@@ -290,6 +308,12 @@ extern "C" int tmgpu_workspace_create(tmgpu_vocab* v, uint32_t max_strings, uint
   A(&ws->tok_off, n1);
   A(&ws->tokens, ws->slab_ids * 4);
   A(&ws->work_counter, tmgpu_workspace::kMaxChunks);
+  A(&ws->p_nlen, n1);
+  A(&ws->p_npad, n1);
+  A(&ws->p_toff, n1);
+  A(&ws->p_wbase, n1);
+  A(&ws->p_flag, n1);
+  A(&ws->p_counters, 4);
   A(&ws->overflow, 4);
   ws->scan_bytes = scan_temp_bytes(uint32_t(n1)) + 256;
   A(reinterpret_cast<uint8_t**>(&ws->scan_temp), ws->scan_bytes);

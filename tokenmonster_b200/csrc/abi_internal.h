@@ -79,6 +79,18 @@ struct tmgpu_workspace {
   uint32_t* overflow = nullptr;
   void* scan_temp = nullptr;
   size_t scan_bytes = 0;
+  // position-table pipeline (pipeline_kernels.cuh): normalized text, one word per position, and
+  // per work item: normalized length, slot size, slot offset, first word, verdict
+  uint8_t* p_text = nullptr;
+  uint64_t p_text_cap = 0;
+  uint32_t* p_words = nullptr;
+  uint64_t p_words_cap = 0;              // entries
+  uint32_t* p_nlen = nullptr;            // n + 1
+  uint32_t* p_npad = nullptr;            // n + 1
+  uint64_t* p_toff = nullptr;            // n + 1
+  uint64_t* p_wbase = nullptr;           // n + 1
+  uint8_t* p_flag = nullptr;             // n + 1
+  uint32_t* p_counters = nullptr;        // 4
   // device normalizer (non-ASCII strings): work list, placement, scratch text
   uint32_t* uni_list = nullptr;          // n
   int64_t* uni_begin = nullptr;          // n
@@ -189,8 +201,6 @@ int stage_input(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off, uint32
 int stage_copy(tmgpu_vocab* v, const uint8_t* src, uint32_t n, uint64_t total, bool gapped,
                std::vector<ChunkPlan>* plan);
 int rerun_if_overflow(tmgpu_vocab* v, uint32_t n, uint8_t enc_len, std::vector<void*>* temp, uint8_t** dense,
-                      const int64_t* d_ends = nullptr);
-int tokenize_streamed(tmgpu_vocab* v, uint32_t n, uint8_t enc_len, cudaEvent_t offsets_ready,
                       const int64_t* d_ends = nullptr);
 int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t* d_off, uint32_t n,
                        uint8_t enc_len, int mode, cudaStream_t st, const uint64_t* slab_off, uint32_t* slab,

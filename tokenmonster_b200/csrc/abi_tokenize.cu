@@ -3,6 +3,63 @@
 // documents (chunking.cuh) and non-ASCII strings (unicode_normalize.cuh), the overflow re-run.
 #include "abi_internal.h"
 
+// ---- the position-table pipeline (pipeline_kernels.cuh) ------------------------------------------
+static int grow_device(void** p, uint64_t* cap, uint64_t want, size_t unit, const char* what) {
+  if (*cap >= want) return TMGPU_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  const uint64_t c = want + want / 8 + 4096;
+  cudaError_t e = cudaMalloc(p, c * unit);
+  if (e != cudaSuccess) {
+    g_err = std::string("cudaMalloc(") + what + ", " + std::to_string(c * unit) + "): " + cudaGetErrorString(e);
+    return TMGPU_E_NOMEM;
+  }
+  *cap = c;
+  return TMGPU_OK;
+}
+
+// Runs the stages for the work items of `a` (a.n <= ws->max_strings).  `extent` = bytes spanned by
+// the items' text when it is read in place (capcode 0, or text the device normalizer produced).
+// Capcode-2 text is written to ws->p_text first: lengths, scan, ONE 8-byte D2H for the total (the
+// text and word buffers grow on demand), then the text itself.
+static int run_pipeline(tmgpu_workspace* ws, TokenizeArgs a, bool store, cudaStream_t st, uint64_t extent) {
+  tmgpu_vocab* v = ws->v;
+  if (a.n == 0) return TMGPU_OK;
+  const bool enc = !a.prenorm && v->host.capcode == 2;
+  a.nlen = ws->p_nlen;
+  a.npad = ws->p_npad;
+  a.toff = ws->p_toff;
+  a.wbase = ws->p_wbase;
+  a.pflag = ws->p_flag;
+  a.pipe_counters = ws->p_counters;
+  CU(cudaMemsetAsync(ws->p_counters, 0, 16, st));
+  if (enc) {
+    CU(launch_encode(a, false, v->sms, st));
+    CU(cudaMemsetAsync(a.npad + a.n, 0, 4, st));
+    CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, a.npad, a.toff, a.n + 1, st));
+    uint64_t total = 0;
+    CU(cudaMemcpyAsync(&total, a.toff + a.n, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    int rc = grow_device(reinterpret_cast<void**>(&ws->p_text), &ws->p_text_cap, total + 64, 1, "normalized text");
+    if (!rc) rc = grow_device(reinterpret_cast<void**>(&ws->p_words), &ws->p_words_cap, total + 64, 4, "position words");
+    if (rc) return rc;
+    a.text = ws->p_text;
+    a.words = ws->p_words;
+    CU(launch_encode(a, true, v->sms, st));
+    ws->last_launches += 4;
+  } else {
+    int rc = grow_device(reinterpret_cast<void**>(&ws->p_words), &ws->p_words_cap, extent + 4ull * ws->max_strings + 64, 4,
+                         "position words");
+    if (rc) return rc;
+    a.words = ws->p_words;
+  }
+  CU(launch_table(a, enc, v->sms, st));
+  CU(launch_chain(a, enc, store, v->sms, st));
+  ws->last_launches += 2;
+  return TMGPU_OK;
+}
+
 // ---- long documents in chunks (chunking.cuh) -----------------------------------------------------
 // Phase 1 (before the main launch): decide which documents are chunked.  Returns the number of
 // chunks (0 = nothing to do); the main launch then skips those documents via ws->ck_skip.
@@ -139,10 +196,8 @@ static int chunk_run(tmgpu_workspace* ws, const TokenizeArgs& first, uint32_t to
     b.raw_ends = first.ends;
     b.skip = nullptr;
     b.watermark = nullptr;
-    b.work_counter = ws->work_counter + (tmgpu_workspace::kMaxChunks - 2);
-    CU(cudaMemsetAsync(b.work_counter, 0, 4, st));
-    CU(launch_tokenize(b, 1, mode == 0, v->sms, st, nullptr));
-    ws->last_launches++;
+    int rc = run_pipeline(ws, b, mode == 0, st, ws->max_bytes);
+    if (rc) return rc;
   }
   return TMGPU_OK;
 }
@@ -204,9 +259,10 @@ static int unicode_pass(tmgpu_workspace* ws, const TokenizeArgs& first, bool sto
   b.prenorm = 1;
   b.skip = nullptr;
   b.watermark = nullptr;
-  b.work_counter = ws->work_counter + (tmgpu_workspace::kMaxChunks - 1);
-  CU(cudaMemsetAsync(b.work_counter, 0, 4, st));
-  CU(launch_tokenize(b, 1, store, v->sms, st, nullptr));
+  {
+    int rc = run_pipeline(ws, b, store, st, h[1] + 64);
+    if (rc) return rc;
+  }
   if (trace) {
     cudaEventRecord(te[2], st);
     cudaEventSynchronize(te[2]);
@@ -217,7 +273,7 @@ static int unicode_pass(tmgpu_workspace* ws, const TokenizeArgs& first, bool sto
             h[1], a, c);
     for (auto& e : te) cudaEventDestroy(e);
   }
-  ws->last_launches += 2;
+  ws->last_launches += 1;
   ws->last_unicode = uint32_t(h[0]);
   return TMGPU_OK;
 }
@@ -287,18 +343,20 @@ int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t
       b.need = ws->need + c.s0;
       b.missing = ws->missing + c.s0;
       b.status = ws->status + c.s0;
-      b.work_counter = ws->work_counter + (ci++ % tmgpu_workspace::kMaxChunks);
-      CU(launch_tokenize(b, v->group, mode == 0, v->sms, st, nullptr));
-      ws->last_launches++;
+      (void)ci;
+      int rc = run_pipeline(ws, b, mode == 0, st, ws->max_bytes);
+      if (rc) return rc;
     }
   } else if (n > 0) {
     const int e = ws->ev_head;
     CU(cudaEventRecord(ws->ev0[e], st));
-    CU(launch_tokenize(a, v->group, mode == 0, v->sms, st, nullptr));
+    {
+      int rc = run_pipeline(ws, a, mode == 0, st, ws->max_bytes);
+      if (rc) return rc;
+    }
     CU(cudaEventRecord(ws->ev1[e], st));
     ws->ev_head = (e + 1) % tmgpu_workspace::kEv;
     if (ws->ev_count < tmgpu_workspace::kEv) ws->ev_count++;
-    ws->last_launches++;
   }
   if (ck_total) {
     int rc = chunk_run(ws, a, ck_total, mode, st);
@@ -505,48 +563,6 @@ int rerun_if_overflow(tmgpu_vocab* v, uint32_t n, uint8_t enc_len, std::vector<v
   return TMGPU_OK;
 }
 
-// Large host batches: ONE launch of the tokenize kernel runs while the strings are still being
-// copied in.  stage_input() issues the H2D copies in chunks on the copy stream and, after each,
-// an 8-byte copy that advances a device "watermark" (bytes landed); a lane that pulls a string
-// beyond the watermark sleeps until its bytes are there.  No SM is needed to move the watermark
-// (it is a DMA write), so the persistent kernel can own the whole GPU.
-int tokenize_streamed(tmgpu_vocab* v, uint32_t n, uint8_t enc_len, cudaEvent_t offsets_ready,
-                             const int64_t* d_ends) {
-  tmgpu_workspace* ws = v->ws;
-  cudaStream_t st = v->stream;
-  ws->last_launches = 0;
-  CU(cudaMemsetAsync(ws->work_counter, 0, 4 * tmgpu_workspace::kMaxChunks, st));
-  CU(cudaMemsetAsync(ws->overflow, 0, 4, st));
-  CU(cudaMemsetAsync(ws->counts + n, 0, 4, st));
-  CU(cudaStreamWaitEvent(st, offsets_ready, 0));
-  TokenizeArgs a{};
-  a.v = v->dev;
-  a.data = v->d_in;
-  a.off = v->d_off;
-  a.ends = d_ends;
-  a.n = n;
-  a.slab = ws->slab;
-  a.slab_pad = ws->slab_pad;
-  a.counts = ws->counts;
-  a.need = ws->need;
-  a.missing = ws->missing;
-  a.status = ws->status;
-  a.work_counter = ws->work_counter;
-  a.overflow = ws->overflow;
-  a.watermark = reinterpret_cast<const unsigned long long*>(v->d_run + 4);
-  CU(launch_tokenize(a, v->group, true, v->sms, st, nullptr));
-  {
-    TokenizeArgs whole = a;
-    whole.watermark = nullptr;
-    int rc = unicode_pass(ws, whole, true, st);
-    if (rc) return rc;
-  }
-  CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, ws->counts, ws->tok_off, n + 1, st));
-  CU(launch_pack(ws->slab, v->d_off, ws->slab_pad, nullptr, ws->counts, ws->tok_off, ws->tokens, n, enc_len, v->sms, st));
-  ws->last_launches = 4;
-  return TMGPU_OK;
-}
-
 extern "C" int tmgpu_tokenize_batch(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off, uint32_t n,
                                     uint8_t enc_len, tmgpu_result** out) {
   if (!v || !off || !out || (!data && n && off[n] != off[0])) {
@@ -565,10 +581,6 @@ extern "C" int tmgpu_tokenize_batch(tmgpu_vocab* v, const uint8_t* data, const u
   std::vector<ChunkPlan> plan;
   if ((rc = stage_input(v, data, off, n, &total, &plan))) return rc;
   tmgpu_workspace* ws = v->ws;
-  if (plan.size() > 1 && v->host.max_len != 0) {
-    // streamed: the kernel is already chasing the copies (stage_input armed the watermark)
-    if ((rc = tokenize_streamed(v, n, enc_len, v->chunk_ev[31]))) return rc;
-  } else
   if ((rc = tokenize_on_stream(ws, v->d_in, v->d_off, n, enc_len, 0, v->stream, nullptr, ws->slab, ws->tokens, &plan)))
     return rc;
   std::vector<void*> temp;

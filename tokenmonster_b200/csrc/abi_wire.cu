@@ -96,9 +96,7 @@ static int wire_tokenize_impl(tmgpu_vocab* v, const uint8_t* payload, uint64_t l
   if ((rc = wire_stage(v, payload, len, n, &plan))) return rc;
   tmgpu_workspace* ws = v->ws;
   const int64_t* d_ends = v->d_off + v->d_off_cap;
-  if (!count_only && plan.size() > 1 && v->host.max_len != 0) {
-    if ((rc = tokenize_streamed(v, n, enc, v->chunk_ev[31], d_ends))) return rc;
-  } else if ((rc = tokenize_on_stream(ws, v->d_in, v->d_off, n, enc, count_only ? 1 : 0, v->stream, nullptr,
+  if ((rc = tokenize_on_stream(ws, v->d_in, v->d_off, n, enc, count_only ? 1 : 0, v->stream, nullptr,
                                       ws->slab, ws->tokens, &plan, d_ends))) {
     return rc;
   }

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cub/device/device_scan.cuh>
 
+#include "pipeline_kernels.cuh"
 #include "tokenize_kernel.cuh"
 #include "tokenize_thread_kernel.cuh"
 #include "unicode_normalize.cuh"
@@ -329,51 +330,6 @@ cudaError_t exclusive_scan_u32_to_u64(void* temp, size_t temp_bytes, const uint3
   return cub::DeviceScan::ExclusiveScan(temp, temp_bytes, in, out, ::cuda::std::plus<>{}, uint64_t(0), int(n_items), st);
 }
 
-template <int G, int CAP, bool STORE>
-static cudaError_t launch_tok(const TokenizeArgs& a, int sms, cudaStream_t st, int* grid_out) {
-  auto k = tokenize_kernel<G, CAP, STORE>;
-  constexpr int smem = GroupCfg<G>::SMEM;
-  static bool configured = false;
-  static int per_sm = 0;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kBlockThreads, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    configured = true;
-  }
-  // persistent grid: every SM gets its resident share of CTAs; strings are pulled from a counter
-  long long want = (static_cast<long long>(a.n) + GroupCfg<G>::GROUPS - 1) / GroupCfg<G>::GROUPS;
-  long long full = static_cast<long long>(sms) * per_sm;
-  int grid = int(want < full ? (want < 1 ? 1 : want) : full);
-  if (grid_out) *grid_out = grid;
-  k<<<grid, kBlockThreads, smem, st>>>(a);
-  return cudaGetLastError();
-}
-
-template <int BLOCK, int CAP, bool STORE>
-static cudaError_t launch_thr(const TokenizeArgs& a, int sms, cudaStream_t st, int* grid_out) {
-  auto k = tokenize_thread_kernel<BLOCK, CAP, STORE>;
-  constexpr int smem = ThreadCfg<BLOCK>::SMEM;
-  static bool configured = false;
-  static int per_sm = 0;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, BLOCK, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    configured = true;
-  }
-  long long want = (static_cast<long long>(a.n) + BLOCK - 1) / BLOCK;
-  long long full = static_cast<long long>(sms) * per_sm;
-  int grid = int(want < full ? (want < 1 ? 1 : want) : full);
-  if (grid_out) *grid_out = grid;
-  k<<<grid, BLOCK, smem, st>>>(a);
-  return cudaGetLastError();
-}
-
 // one warp per string: any byte >= 0x80?
 __global__ void __launch_bounds__(256) flag_non_ascii_kernel(const uint8_t* __restrict__ data,
                                                              const int64_t* __restrict__ off,
@@ -402,36 +358,37 @@ cudaError_t launch_flag_non_ascii(const uint8_t* data, const int64_t* off, const
   return cudaGetLastError();
 }
 
-cudaError_t launch_tokenize(const TokenizeArgs& a, int group, bool store, int sms, cudaStream_t st, int* grid_out) {
-  const int cap = a.prenorm ? 0 : a.v.capcode;   // pre-normalized text is read verbatim
-  if (a.prenorm || a.scores) group = 1;          // only the lane-per-string kernel carries these modes
-  if (group == 1) {  // one thread per string; big CTAs share a big edge cache when the batch fills them
-    static const int forced = getenv("TMGPU_CTA") ? atoi(getenv("TMGPU_CTA")) : 0;  // experiment hook
-    int cta = forced ? forced : (a.n >= uint32_t(sms) * 768u ? 1024 : 256);
-#define TM_THR(B_)                                                                         \
-    if (cap == 0) return store ? launch_thr<B_, 0, true>(a, sms, st, grid_out)             \
-                               : launch_thr<B_, 0, false>(a, sms, st, grid_out);           \
-    return store ? launch_thr<B_, 2, true>(a, sms, st, grid_out)                           \
-                 : launch_thr<B_, 2, false>(a, sms, st, grid_out);
-    if (cta >= 1024) { TM_THR(1024) }
-    if (cta >= 768) { TM_THR(768) }
-    if (cta >= 512) { TM_THR(512) }
-    TM_THR(256)
-#undef TM_THR
+// persistent grid for a one-lane-per-string kernel: every SM gets its resident share of CTAs
+template <class K>
+static int pipe_grid(K kernel, uint32_t n, int sms) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPipeBlock, 0) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
   }
-#define TM_CASE(G_)                                                                      \
-  if (group == G_) {                                                                     \
-    if (cap == 0) return store ? launch_tok<G_, 0, true>(a, sms, st, grid_out)           \
-                               : launch_tok<G_, 0, false>(a, sms, st, grid_out);         \
-    return store ? launch_tok<G_, 2, true>(a, sms, st, grid_out)                         \
-                 : launch_tok<G_, 2, false>(a, sms, st, grid_out);                       \
-  }
-  TM_CASE(32)
-  TM_CASE(16)
-  TM_CASE(8)
-  TM_CASE(4)
-#undef TM_CASE
-  return cudaErrorInvalidValue;
+  const long long want = (static_cast<long long>(n) + kPipeBlock - 1) / kPipeBlock;
+  const long long full = static_cast<long long>(sms) * per_sm;
+  return int(want < full ? (want < 1 ? 1 : want) : full);
+}
+
+cudaError_t launch_encode(const TokenizeArgs& a, bool write, int sms, cudaStream_t st) {
+  if (write) encode_kernel<true><<<pipe_grid(encode_kernel<true>, a.n, sms), kPipeBlock, 0, st>>>(a);
+  else encode_kernel<false><<<pipe_grid(encode_kernel<false>, a.n, sms), kPipeBlock, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_table(const TokenizeArgs& a, bool enc, int sms, cudaStream_t st) {
+  if (enc) table_kernel<true><<<pipe_grid(table_kernel<true>, a.n, sms), kPipeBlock, 0, st>>>(a);
+  else table_kernel<false><<<pipe_grid(table_kernel<false>, a.n, sms), kPipeBlock, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chain(const TokenizeArgs& a, bool enc, bool store, int sms, cudaStream_t st) {
+#define TM_CHAIN(S_, E_) chain_kernel<S_, E_><<<pipe_grid(chain_kernel<S_, E_>, a.n, sms), kPipeBlock, 0, st>>>(a)
+  if (store) { if (enc) TM_CHAIN(true, true); else TM_CHAIN(true, false); }
+  else { if (enc) TM_CHAIN(false, true); else TM_CHAIN(false, false); }
+#undef TM_CHAIN
+  return cudaGetLastError();
 }
 
 uint32_t chunk_log_capacity() { return kChunkLogCap; }
@@ -456,15 +413,14 @@ cudaError_t launch_tokenize_chunks(const TokenizeArgs& a, int sms, cudaStream_t 
   constexpr int smem = ThreadCfg<B>::SMEM;
   auto k0 = tokenize_thread_kernel<B, 0, true, true>;
   auto k2 = tokenize_thread_kernel<B, 2, true, true>;
-  static bool configured = false;
-  static int per_sm0 = 1, per_sm2 = 1;
-  if (!configured) {
+  // function attributes are per device: set them on every launch (a process may hold several GPUs)
+  int per_sm0 = 1, per_sm2 = 1;
+  {
     cudaError_t e = cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm0, k0, B, smem);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k2, B, smem);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const bool cap2 = a.v.capcode == 2;
   const long long want = (static_cast<long long>(a.n) + B - 1) / B;

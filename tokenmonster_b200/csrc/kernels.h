@@ -57,15 +57,26 @@ struct TokenizeArgs {
   uint32_t* c_miss;          // per logged id: characters without a token before its step
   ChunkOut* c_out;
   uint32_t c_cap, c_ov;      // log capacity per chunk; how far a chunk runs past the next one's start
-  const unsigned long long* watermark;  // optional: input bytes that have landed in `data` so far (host path
-                             // streams the batch in while the kernel runs); NULL = everything is there
+  const unsigned long long* watermark;  // (chunk kernel only) unused
+  // position-table pipeline scratch, per launch, indexed by work item
+  uint8_t* text;             // normalized text of capcode-2 vocabularies: 16-byte aligned slots at toff[item]
+  uint32_t* words;           // one word per normalized position (pipeline_core.h)
+  uint32_t* nlen;            // normalized length
+  uint32_t* npad;            // n + 1: slot size (0 for refused / skipped items)
+  uint64_t* toff;            // n + 1: exclusive scan of npad
+  uint64_t* wbase;           // first word of the item when the text is read in place
+  uint8_t* pflag;            // 0 run, 1 refused (status 13), 2 nothing to do
+  uint32_t* pipe_counters;   // 4 zeroed work counters: encode lengths, encode, table, chain
 };
 
 size_t scan_temp_bytes(uint32_t n_items);
 cudaError_t exclusive_scan_u32_to_u64(void* temp, size_t temp_bytes, const uint32_t* in, uint64_t* out,
                                       uint32_t n_items, cudaStream_t st);
-// group = lanes per string (32, 16 or 8); store = ids (K1) vs count only (K3)
-cudaError_t launch_tokenize(const TokenizeArgs& a, int group, bool store, int sms, cudaStream_t st, int* grid_out);
+// the position-table pipeline (pipeline_kernels.cuh); enc = the vocabulary uses capcode 2 and the
+// text is raw (not pre-normalized); store = ids (K1) vs count only (K3)
+cudaError_t launch_encode(const TokenizeArgs& a, bool write, int sms, cudaStream_t st);
+cudaError_t launch_table(const TokenizeArgs& a, bool enc, int sms, cudaStream_t st);
+cudaError_t launch_chain(const TokenizeArgs& a, bool enc, bool store, int sms, cudaStream_t st);
 cudaError_t launch_pack(const uint32_t* slab, const int64_t* off, uint32_t slab_pad, const uint64_t* slab_off,
                         const uint32_t* counts, const uint64_t* tok_off, uint8_t* out, uint32_t n, int enc,
                         int sms, cudaStream_t st);
