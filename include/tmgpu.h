@@ -186,7 +186,8 @@ void tmgpu_wire_reply_free(tmgpu_wire_reply* r);
 /* ---- device-resident path (inputs already in HBM; used for the kernel roofline figure and
  *      by the sharded multi-GPU host) -------------------------------------------------------
  * A workspace owns the device output buffers for batches up to (max_strings, max_bytes).
- * d_data must be 16-byte aligned (any cudaMalloc / torch allocation is). */
+ * d_data needs no particular alignment, but the 16-byte block around its first byte must be
+ * readable (true for any pointer into a cudaMalloc / torch allocation). */
 typedef struct tmgpu_workspace tmgpu_workspace;
 
 typedef struct tmgpu_device_view {

@@ -195,7 +195,15 @@ extern "C" void tmgpu_vocab_destroy(tmgpu_vocab* v) {
     if (e) cudaEventDestroy(e);
   if (v->d_run) cudaFree(v->d_run);
   if (v->h_info) cudaFreeHost(v->h_info);
-  for (auto& b : v->pinned) cudaFreeHost(b.p);
+  {  // results cut from the pool may still be alive: free what is idle, leave the rest to them
+    std::lock_guard<std::mutex> lock(v->pool->mu);
+    v->pool->orphaned = true;
+    for (auto& b : v->pool->blocks)
+      if (b.p && !b.used) {
+        cudaFreeHost(b.p);
+        b.p = nullptr;
+      }
+  }
   delete v;
 }
 

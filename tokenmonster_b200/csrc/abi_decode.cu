@@ -101,16 +101,16 @@ extern "C" int tmgpu_decode_batch(tmgpu_vocab* v, const uint8_t* tokens, const u
     return TMGPU_E_ARG;
   }
   std::lock_guard<std::mutex> lock(v->mu);
-  const uint64_t n_ids = tok_off[n] - tok_off[0];
-  int rc = ensure_host_path(v, n, n_ids * enc_len + 64);
-  if (rc) return rc;
-  for (uint32_t i = 0; i <= n; i++) {
-    if (tok_off[i] < tok_off[0] || (i && tok_off[i] < tok_off[i - 1])) {
+  for (uint32_t i = 1; i <= n; i++) {   // before any buffer is sized from them
+    if (tok_off[i] < tok_off[i - 1]) {
       g_err = "token offsets must be non-decreasing";
       return TMGPU_E_ARG;
     }
-    v->h_off[i] = int64_t(tok_off[i] - tok_off[0]);
   }
+  const uint64_t n_ids = tok_off[n] - tok_off[0];
+  int rc = ensure_host_path(v, n, n_ids * enc_len + 64);
+  if (rc) return rc;
+  for (uint32_t i = 0; i <= n; i++) v->h_off[i] = int64_t(tok_off[i] - tok_off[0]);
   if (n_ids)
     CU(cudaMemcpyAsync(v->d_in, tokens + tok_off[0] * enc_len, n_ids * enc_len, cudaMemcpyHostToDevice, v->stream));
   CU(cudaMemcpyAsync(v->d_off, v->h_off, (size_t(n) + 1) * 8, cudaMemcpyHostToDevice, v->stream));
@@ -119,7 +119,7 @@ extern "C" int tmgpu_decode_batch(tmgpu_vocab* v, const uint8_t* tokens, const u
   uint64_t total = 0;
   if ((rc = decode_on_stream(v->ws, v->d_in, v->d_off, n, enc_len, v->stream, &d_bytes, &d_off, &total))) return rc;
   auto* priv = new ResultPriv();
-  priv->v = v;
+  priv->pool = v->pool;
   auto* b = new tmgpu_bytes();
   std::memset(b, 0, sizeof(*b));
   b->priv = priv;
@@ -191,8 +191,10 @@ extern "C" int tmgpu_decoder_create(tmgpu_vocab* v, uint32_t n_streams, tmgpu_de
     tmgpu_decoder_destroy(d);
     return rc;
   }
-  CU(cudaMemset(d->rem_off, 0, n1 * 8));
-  CU(cudaMemset(d->cc_state, 0, n1));
+  // the decoder's kernels run on v->stream (non-blocking: not ordered against the legacy stream)
+  CU(cudaMemsetAsync(d->rem_off, 0, n1 * 8, v->stream));
+  CU(cudaMemsetAsync(d->cc_state, 0, n1, v->stream));
+  CU(cudaStreamSynchronize(v->stream));
   *out = d;
   return TMGPU_OK;
 }
@@ -222,18 +224,18 @@ extern "C" int tmgpu_decoder_decode(tmgpu_decoder* d, const uint8_t* tokens, con
     return TMGPU_E_ARG;
   }
   std::lock_guard<std::mutex> lock(v->mu);
+  for (uint32_t i = 1; i <= n; i++) {   // before any buffer is sized from them
+    if (tok_off[i] < tok_off[i - 1]) {
+      g_err = "token offsets must be non-decreasing";
+      return TMGPU_E_ARG;
+    }
+  }
   const uint64_t n_ids = tok_off[n] - tok_off[0];
   int rc = ensure_host_path(v, n, n_ids * enc_len + 64);
   if (rc) return rc;
   tmgpu_workspace* ws = v->ws;
   cudaStream_t st = v->stream;
-  for (uint32_t i = 0; i <= n; i++) {
-    if (tok_off[i] < tok_off[0] || (i && tok_off[i] < tok_off[i - 1])) {
-      g_err = "token offsets must be non-decreasing";
-      return TMGPU_E_ARG;
-    }
-    v->h_off[i] = int64_t(tok_off[i] - tok_off[0]);
-  }
+  for (uint32_t i = 0; i <= n; i++) v->h_off[i] = int64_t(tok_off[i] - tok_off[0]);
   if (n_ids) CU(cudaMemcpyAsync(v->d_in, tokens + tok_off[0] * enc_len, n_ids * enc_len, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(v->d_off, v->h_off, (size_t(n) + 1) * 8, cudaMemcpyHostToDevice, st));
   const bool stateful = v->host.charset != 0;  // charset 0 returns before remainder / capcode handling (quirk Q6)
@@ -281,7 +283,7 @@ extern "C" int tmgpu_decoder_decode(tmgpu_decoder* d, const uint8_t* tokens, con
     std::swap(d->rem_off, d->new_off);
   }
   auto* priv = new ResultPriv();
-  priv->v = v;
+  priv->pool = v->pool;
   auto* b = new tmgpu_bytes();
   std::memset(b, 0, sizeof(*b));
   b->priv = priv;
@@ -314,7 +316,7 @@ extern "C" int tmgpu_decoder_flush(tmgpu_decoder* d, tmgpu_bytes** out) {
   CU(cudaSetDevice(v->device));
   const uint32_t n = d->n;
   auto* priv = new ResultPriv();
-  priv->v = v;
+  priv->pool = v->pool;
   auto* b = new tmgpu_bytes();
   std::memset(b, 0, sizeof(*b));
   b->priv = priv;
@@ -324,18 +326,23 @@ extern "C" int tmgpu_decoder_flush(tmgpu_decoder* d, tmgpu_bytes** out) {
     tmgpu_bytes_free(b);
     return rc;
   }
-  cudaError_t e = cudaMemcpy(b->off, d->rem_off, (size_t(n) + 1) * 8, cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaMemcpyAsync(b->off, d->rem_off, (size_t(n) + 1) * 8, cudaMemcpyDeviceToHost, v->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(v->stream);
   if (e == cudaSuccess) {
     b->n_bytes = b->off[n];
     rc = pinned_alloc(priv, &b->bytes, b->n_bytes + 8);
-    if (!rc && b->n_bytes) e = cudaMemcpy(b->bytes, d->rem, b->n_bytes, cudaMemcpyDeviceToHost);
+    if (!rc && b->n_bytes) {
+      e = cudaMemcpyAsync(b->bytes, d->rem, b->n_bytes, cudaMemcpyDeviceToHost, v->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(v->stream);
+    }
   }
   if (rc || e != cudaSuccess) {
     if (e != cudaSuccess) g_err = std::string("decoder flush: ") + cudaGetErrorString(e);
     tmgpu_bytes_free(b);
     return rc ? rc : TMGPU_E_CUDA;
   }
-  CU(cudaMemset(d->rem_off, 0, (size_t(n) + 1) * 8));
+  CU(cudaMemsetAsync(d->rem_off, 0, (size_t(n) + 1) * 8, v->stream));
+  CU(cudaStreamSynchronize(v->stream));
   *out = b;
   return TMGPU_OK;
 }

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -31,6 +32,20 @@ extern thread_local std::string g_err;   // message behind tmgpu_last_error()
       return TMGPU_E_CUDA;                                                                \
     }                                                                                     \
   } while (0)
+
+// Pinned host blocks handed out as results (cudaMallocHost per call is far too slow).  The pool is
+// shared between the vocabulary and every result / bytes / reply object cut from it, so a result
+// may outlive its vocabulary: the blocks are freed when the last owner goes.
+struct PinnedPool {
+  struct Block { void* p; size_t bytes; bool used; };
+  std::vector<Block> blocks;
+  std::mutex mu;
+  bool orphaned = false;   // the vocabulary is gone: blocks are freed as soon as they come back
+  ~PinnedPool() {
+    for (auto& b : blocks)
+      if (b.p) cudaFreeHost(b.p);
+  }
+};
 
 struct tmgpu_vocab {
   HostTables host;
@@ -56,10 +71,7 @@ struct tmgpu_vocab {
   cudaEvent_t done_ev[32] = {};
   uint64_t* d_run = nullptr;      // device: running id total + per-chunk {base, total}
   uint64_t* h_info = nullptr;     // pinned mirror of the per-chunk {base, total}
-  // pinned host blocks handed out as results and taken back by tmgpu_result_free / bytes_free
-  struct PinnedBlock { void* p; size_t bytes; bool used; };
-  std::vector<PinnedBlock> pinned;
-  std::mutex pin_mu;
+  std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
 };
 
 struct tmgpu_workspace {
@@ -160,7 +172,7 @@ struct ChunkPlan {
 };
 
 struct ResultPriv {
-  tmgpu_vocab* v = nullptr;
+  std::shared_ptr<PinnedPool> pool;
   std::vector<void*> blocks;
 };
 
@@ -169,12 +181,13 @@ template <class T>
 inline int pinned_alloc(ResultPriv* p, T** out, size_t count) {
   size_t bytes = count * sizeof(T);
   if (bytes < 64) bytes = 64;
-  tmgpu_vocab* v = p->v;
-  std::lock_guard<std::mutex> lock(v->pin_mu);
+  PinnedPool* v = p->pool.get();
+  std::lock_guard<std::mutex> lock(v->mu);
+  auto& pinned = v->blocks;
   int best = -1;
-  for (size_t i = 0; i < v->pinned.size(); i++) {
-    auto& b = v->pinned[i];
-    if (!b.used && b.bytes >= bytes && (best < 0 || b.bytes < v->pinned[best].bytes)) best = int(i);
+  for (size_t i = 0; i < pinned.size(); i++) {
+    auto& b = pinned[i];
+    if (b.p && !b.used && b.bytes >= bytes && (best < 0 || b.bytes < pinned[best].bytes)) best = int(i);
   }
   if (best < 0) {
     void* q = nullptr;
@@ -184,12 +197,12 @@ inline int pinned_alloc(ResultPriv* p, T** out, size_t count) {
       g_err = std::string("cudaMallocHost: ") + cudaGetErrorString(e);
       return TMGPU_E_NOMEM;
     }
-    v->pinned.push_back({q, cap, false});
-    best = int(v->pinned.size()) - 1;
+    pinned.push_back({q, cap, false});
+    best = int(pinned.size()) - 1;
   }
-  v->pinned[best].used = true;
-  p->blocks.push_back(v->pinned[best].p);
-  *out = static_cast<T*>(v->pinned[best].p);
+  pinned[best].used = true;
+  p->blocks.push_back(pinned[best].p);
+  *out = static_cast<T*>(pinned[best].p);
   return TMGPU_OK;
 }
 

@@ -329,7 +329,6 @@ int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t
     CU(cudaMemsetAsync(ws->missing, 0, size_t(n) * 4, st));
     CU(cudaMemsetAsync(ws->status, 0, n, st));
   } else if (n > 0 && chunks && !slab_off) {
-    int ci = 0;
     for (const ChunkPlan& c : *chunks) {
       if (c.s1 <= c.s0) continue;
       if (c.ready) CU(cudaStreamWaitEvent(st, c.ready, 0));
@@ -343,7 +342,6 @@ int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t
       b.need = ws->need + c.s0;
       b.missing = ws->missing + c.s0;
       b.status = ws->status + c.s0;
-      (void)ci;
       int rc = run_pipeline(ws, b, mode == 0, st, ws->max_bytes);
       if (rc) return rc;
     }
@@ -391,10 +389,6 @@ extern "C" int tmgpu_tokenize_device(tmgpu_workspace* ws, const uint8_t* d_data,
   }
   if (n > ws->max_strings) {
     g_err = "batch has more strings than the workspace was created for";
-    return TMGPU_E_ARG;
-  }
-  if (reinterpret_cast<uintptr_t>(d_data) & 15) {
-    g_err = "d_data must be 16-byte aligned";
     return TMGPU_E_ARG;
   }
   CU(cudaSetDevice(ws->v->device));
@@ -452,11 +446,17 @@ int ensure_host_path(tmgpu_vocab* v, uint32_t n, uint64_t bytes) {
 
 void release_priv(ResultPriv* p) {
   if (!p) return;
-  if (p->v) {
-    std::lock_guard<std::mutex> lock(p->v->pin_mu);
+  if (p->pool) {
+    std::lock_guard<std::mutex> lock(p->pool->mu);
     for (void* q : p->blocks)
-      for (auto& b : p->v->pinned)
-        if (b.p == q) b.used = false;
+      for (auto& b : p->pool->blocks)
+        if (b.p == q) {
+          b.used = false;
+          if (p->pool->orphaned) {   // nobody will ask for it again
+            cudaFreeHost(b.p);
+            b.p = nullptr;
+          }
+        }
   }
   delete p;
 }
@@ -594,7 +594,7 @@ extern "C" int tmgpu_tokenize_batch(tmgpu_vocab* v, const uint8_t* data, const u
     return rc;
   }
   auto* priv = new ResultPriv();
-  priv->v = v;
+  priv->pool = v->pool;
   auto* r = new tmgpu_result();
   std::memset(r, 0, sizeof(*r));
   r->priv = priv;

@@ -45,7 +45,7 @@ static int wire_scan(const uint8_t* payload, uint64_t len, uint32_t* n_out, uint
 
 static tmgpu_wire_reply* new_reply(tmgpu_vocab* v) {
   auto* priv = new ResultPriv();
-  priv->v = v;
+  priv->pool = v->pool;
   auto* r = new tmgpu_wire_reply();
   std::memset(r, 0, sizeof(*r));
   r->priv = priv;
