@@ -73,6 +73,7 @@ def _bind(path: str, p: str):
         api["capcode_encode"] = f("capcode_encode", C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)])
         api["incomplete_utf8"] = f("incomplete_utf8", C.c_int, [C.c_char_p, C.c_size_t])
         api["incomplete_utf16"] = f("incomplete_utf16", C.c_int, [C.c_char_p, C.c_size_t])
+        api["ids_checksum"] = f("ids_checksum", C.c_uint64, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32])
     return api
 
 
@@ -228,6 +229,13 @@ def capcode_encode(data: bytes) -> bytes:
     out = C.string_at(p.value, n.value) if n.value else b""
     api["free"](p.value)
     return out
+
+
+def ids_checksum(tokens_u8: np.ndarray, enc_len: int, tok_off: np.ndarray, n: int) -> int:
+    """Checksum of the first n strings of a batch result, comparable with OracleVocab.tokenize_batch_timed()."""
+    t = np.ascontiguousarray(tokens_u8).view(np.uint8)
+    o = np.ascontiguousarray(tok_off, dtype=np.uint64)
+    return int(_api("port")["ids_checksum"](t.ctypes.data, enc_len, o.ctypes.data, n))
 
 
 def incomplete_utf8(b: bytes) -> int:

@@ -195,16 +195,18 @@ int64_t tmr_tokenize_batch(const tmr_vocab* v, const uint8_t* data, const uint64
         auto r = v->v.tokenize({data + off[s], static_cast<size_t>(off[s + 1] - off[s])});
         tot[t] += static_cast<int64_t>(r.tokens.size());
         if (counts) counts[s] = static_cast<uint32_t>(r.tokens.size());
-        uint64_t h = chk[t];
+        // per-string FNV-1a over the ids (fold of tokenmonster-cpp/tests/bench.cpp:30-37), mixed with
+        // the string index and SUMMED: the same value whatever the thread count or the order
+        uint64_t h = 14695981039346656037ULL;
         for (auto id : r.tokens) h = (h ^ id) * 1099511628211ULL;
-        chk[t] = h;
+        chk[t] += h ^ (static_cast<uint64_t>(s) * 0x9E3779B97F4A7C15ULL);
       }
     });
   }
   for (auto& th : pool) th.join();
   int64_t total = 0;
   uint64_t c = 0;
-  for (int t = 0; t < threads; t++) { total += tot[t]; c ^= chk[t]; }
+  for (int t = 0; t < threads; t++) { total += tot[t]; c += chk[t]; }
   if (checksum) *checksum = c;
   return total;
 }

@@ -739,3 +739,22 @@ int tmo_decoder_flush(tmo_decoder* d, uint8_t** out, size_t* out_n) {
   d->remainder_len = 0;
   return TMO_OK;
 }
+
+/* Checksum of a batch result: per-string FNV-1a over the ids, mixed with the string index, summed
+ * (the fold oracle/ref_driver.cpp's tmr_tokenize_batch applies to the reference's own output, after
+ * tokenmonster-cpp/tests/bench.cpp:30-37).  tokens = dense ids of enc_len (2, 3, 4) bytes each. */
+uint64_t tmo_ids_checksum(const uint8_t* tokens, int enc_len, const uint64_t* tok_off, uint32_t n) {
+  uint64_t c = 0;
+  for (uint32_t s = 0; s < n; s++) {
+    uint64_t h = 14695981039346656037ULL;
+    for (uint64_t k = tok_off[s]; k < tok_off[s + 1]; k++) {
+      const uint8_t* p = tokens + k * (uint64_t)enc_len;
+      uint32_t id = p[0] | ((uint32_t)p[1] << 8);
+      if (enc_len > 2) id |= (uint32_t)p[2] << 16;
+      if (enc_len > 3) id |= (uint32_t)p[3] << 24;
+      h = (h ^ id) * 1099511628211ULL;
+    }
+    c += h ^ ((uint64_t)s * 0x9E3779B97F4A7C15ULL);
+  }
+  return c;
+}

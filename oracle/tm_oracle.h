@@ -110,6 +110,9 @@ int tmo_incomplete_utf16(const uint8_t* b, size_t n);
  * returns length (0 = not found), *index = dictionary index */
 int tmo_longest_prefix(const tmo_vocab* v, const uint8_t* w, size_t n, uint32_t* index);
 
+/* checksum of a batch result (same fold as oracle/ref_driver.cpp tmr_tokenize_batch) */
+uint64_t tmo_ids_checksum(const uint8_t* tokens, int enc_len, const uint64_t* tok_off, uint32_t n);
+
 #ifdef __cplusplus
 }
 #endif

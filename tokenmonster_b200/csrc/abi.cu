@@ -284,6 +284,8 @@ extern "C" void tmgpu_workspace_destroy(tmgpu_workspace* ws) {
     if (ws->ev0[i]) cudaEventDestroy(ws->ev0[i]);
     if (ws->ev1[i]) cudaEventDestroy(ws->ev1[i]);
   }
+  for (auto& e : ws->stage_ev)
+    if (e) cudaEventDestroy(e);
   delete ws;
 }
 
@@ -352,6 +354,7 @@ extern "C" int tmgpu_workspace_create(tmgpu_vocab* v, uint32_t max_strings, uint
     CU(cudaEventCreate(&ws->ev0[i]));
     CU(cudaEventCreate(&ws->ev1[i]));
   }
+  for (auto& e : ws->stage_ev) CU(cudaEventCreate(&e));
   *out = ws;
   return TMGPU_OK;
 }
@@ -373,6 +376,27 @@ extern "C" int tmgpu_workspace_kernel_times(tmgpu_workspace* ws, float* ms_out, 
   }
   ws->ev_count = 0;
   return n;
+}
+
+// Durations (ms) of the stages of the most recent tokenize pipeline run on this workspace:
+// out[0] capcode lengths + scan (incl. the 8-byte host round trip), out[1] capcode text,
+// out[2] position table, out[3] chain.  Stages that did not run report 0.  Returns 4, or 0 when
+// nothing has run yet.  Synchronises on the last event.
+extern "C" int tmgpu_workspace_stage_times(tmgpu_workspace* ws, float out[4]) {
+  if (!ws || !out || !ws->stage_valid) return 0;
+  if (cudaEventSynchronize(ws->stage_ev[4]) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  for (int k = 0; k < 4; k++) {
+    out[k] = 0.f;
+    if (!ws->stage_enc && k < 2) continue;
+    if (cudaEventElapsedTime(&out[k], ws->stage_ev[k], ws->stage_ev[k + 1]) != cudaSuccess) {
+      cudaGetLastError();
+      out[k] = -1.f;
+    }
+  }
+  return 4;
 }
 
 extern "C" int tmgpu_last_launch_count(const tmgpu_workspace* ws) { return ws ? ws->last_launches : 0; }

@@ -204,7 +204,7 @@ static int grow(uint8_t** p, uint64_t* cap, uint64_t need) {
   if (*p) cudaFree(*p);
   *p = nullptr;
   *cap = need + need / 4 + 4096;
-  CU(cudaMalloc(p, *cap));
+  CU(tm_malloc(p, *cap));
   return TMGPU_OK;
 }
 

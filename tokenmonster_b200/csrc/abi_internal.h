@@ -146,14 +146,33 @@ struct tmgpu_workspace {
   static constexpr int kEv = 64;
   cudaEvent_t ev0[kEv] = {}, ev1[kEv] = {};
   int ev_head = 0, ev_count = 0;
+  // stage boundaries of the most recent pipeline run: start, lengths+scan, text, table, chain
+  cudaEvent_t stage_ev[5] = {};
+  bool stage_enc = false, stage_valid = false;
 };
+
+// Debug aid (TMGPU_POISON=1): every device allocation is filled with 0xA5, so that a kernel that
+// reads memory nobody wrote gives the same wrong answer on every run instead of a flaky one.
+inline cudaError_t tm_malloc(void** p, size_t bytes) {
+  static const bool poison = getenv("TMGPU_POISON") != nullptr;
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e == cudaSuccess && poison) {
+    e = cudaMemset(*p, 0xA5, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  }
+  return e;
+}
+template <class T>
+inline cudaError_t tm_malloc(T** p, size_t bytes) {
+  return tm_malloc(reinterpret_cast<void**>(p), bytes);
+}
 
 template <class T>
 inline int dev_alloc(std::vector<void*>& pool, T** out, size_t count) {
   void* p = nullptr;
   size_t bytes = count * sizeof(T);
   if (bytes == 0) bytes = 16;
-  cudaError_t e = cudaMalloc(&p, bytes + 16);
+  cudaError_t e = tm_malloc(&p, bytes + 16);
   if (e != cudaSuccess) {
     g_err = std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e);
     return TMGPU_E_NOMEM;

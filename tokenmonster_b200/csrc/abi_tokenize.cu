@@ -10,7 +10,7 @@ static int grow_device(void** p, uint64_t* cap, uint64_t want, size_t unit, cons
   *p = nullptr;
   *cap = 0;
   const uint64_t c = want + want / 8 + 4096;
-  cudaError_t e = cudaMalloc(p, c * unit);
+  cudaError_t e = tm_malloc(p, c * unit);
   if (e != cudaSuccess) {
     g_err = std::string("cudaMalloc(") + what + ", " + std::to_string(c * unit) + "): " + cudaGetErrorString(e);
     return TMGPU_E_NOMEM;
@@ -34,6 +34,9 @@ static int run_pipeline(tmgpu_workspace* ws, TokenizeArgs a, bool store, cudaStr
   a.pflag = ws->p_flag;
   a.pipe_counters = ws->p_counters;
   CU(cudaMemsetAsync(ws->p_counters, 0, 16, st));
+  ws->stage_enc = enc;
+  ws->stage_valid = true;
+  CU(cudaEventRecord(ws->stage_ev[0], st));
   if (enc) {
     CU(launch_encode(a, false, v->sms, st));
     CU(cudaMemsetAsync(a.npad + a.n, 0, 4, st));
@@ -46,6 +49,7 @@ static int run_pipeline(tmgpu_workspace* ws, TokenizeArgs a, bool store, cudaStr
     if (rc) return rc;
     a.text = ws->p_text;
     a.words = ws->p_words;
+    CU(cudaEventRecord(ws->stage_ev[1], st));
     CU(launch_encode(a, true, v->sms, st));
     ws->last_launches += 4;
   } else {
@@ -54,8 +58,11 @@ static int run_pipeline(tmgpu_workspace* ws, TokenizeArgs a, bool store, cudaStr
     if (rc) return rc;
     a.words = ws->p_words;
   }
+  CU(cudaEventRecord(ws->stage_ev[2], st));
   CU(launch_table(a, enc, v->sms, st));
+  CU(cudaEventRecord(ws->stage_ev[3], st));
   CU(launch_chain(a, enc, store, v->sms, st));
+  CU(cudaEventRecord(ws->stage_ev[4], st));
   ws->last_launches += 2;
   return TMGPU_OK;
 }
@@ -221,7 +228,7 @@ static int unicode_pass(tmgpu_workspace* ws, const TokenizeArgs& first, bool sto
     if (ws->uni_text) cudaFree(ws->uni_text);
     ws->uni_text = nullptr;
     ws->uni_text_cap = h[1] + h[1] / 4 + 4096;
-    cudaError_t e = cudaMalloc(&ws->uni_text, ws->uni_text_cap);
+    cudaError_t e = tm_malloc(&ws->uni_text, ws->uni_text_cap);
     if (e != cudaSuccess) {
       ws->uni_text_cap = 0;
       g_err = std::string("cudaMalloc(normalizer scratch): ") + cudaGetErrorString(e);
@@ -430,7 +437,7 @@ int ensure_host_path(tmgpu_vocab* v, uint32_t n, uint64_t bytes) {
     if (v->d_in) cudaFree(v->d_in);
     v->d_in = nullptr;
     v->d_in_cap = bytes + bytes / 8 + 4096;
-    CU(cudaMalloc(&v->d_in, v->d_in_cap));
+    CU(tm_malloc(&v->d_in, v->d_in_cap));
   }
   if (v->d_off_cap < size_t(n) + 1) {
     if (v->d_off) cudaFree(v->d_off);
@@ -438,7 +445,7 @@ int ensure_host_path(tmgpu_vocab* v, uint32_t n, uint64_t bytes) {
     v->d_off = nullptr;
     v->h_off = nullptr;
     v->d_off_cap = size_t(n) + n / 8 + 1024;
-    CU(cudaMalloc(&v->d_off, v->d_off_cap * 16));
+    CU(tm_malloc(&v->d_off, v->d_off_cap * 16));
     CU(cudaMallocHost(&v->h_off, v->d_off_cap * 16));
   }
   return TMGPU_OK;

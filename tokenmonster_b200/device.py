@@ -72,6 +72,12 @@ class DeviceWorkspace:
         k = lib().tmgpu_workspace_kernel_times(self._h, buf, 64)
         return [float(buf[i]) for i in range(k)]
 
+    def stage_times_ms(self):
+        """CUDA-event durations of the last run's stages: capcode lengths+scan, capcode text, table, chain."""
+        buf = (C.c_float * 4)()
+        k = lib().tmgpu_workspace_stage_times(self._h, buf)
+        return [float(buf[i]) for i in range(k)]
+
     def results(self):
         """Synchronise and wrap the outputs of the last launch_tokenize (mode 0) as torch tensors."""
         torch.cuda.current_stream(self.device).synchronize()
