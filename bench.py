@@ -1,21 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- MB/s tokenized (input bytes) on the BASELINE.json configuration.
+"""bench.py -- MB/s tokenized (input bytes) on the BASELINE.json configurations.
 
-    python bench.py --gpus N --steps K --warmup W            (this repo's CUDA path)
+    python bench.py --gpus N --steps K --warmup W            (this repo's CUDA path, config c2)
     python bench.py --impl reference --gpus N --steps K ...  (the reference's own C++ CPU runtime)
     torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, weak scaling)
+    python bench.py --config c3|c4|c5 [--gpus N]             (the other named configurations)
 
-A "step" = one pass of the hot path (tokenize kernel + offset scan + id packing) over one batch of
-synthetic strings.  N=1 workload = BASELINE.json configs[1]: the englishcode-32000 stand-in,
-1,000,000 strings ~U[64,960] bytes (mean 512), resident in HBM before the timed region
-(512 MB of input per step >> 126 MB L2, so no L2 flush is needed between steps).
-`value`  : whole-job MB/s (10^6 B) with inputs already in HBM, device-timed, max over ranks.
-`e2e`    : the same metric through the C-ABI host-buffer call tmgpu_tokenize_batch with pinned HOST
-           buffers -- H2D of the strings and D2H of the ids inside the timed region.
-`roofline`: the tokenize kernel against the measured HBM copy bandwidth; algorithmic bytes = 1 B
-           read per input byte.
+A "step" = one pass of the hot path (capcode text, position table, ungreedy chain, offset scan, id
+packing) over one batch of synthetic strings resident in HBM before the timed region.  Every batch
+is far larger than the 126 MB L2, so no flush is needed between steps.
+`value`   : whole-job MB/s (10^6 B) with inputs already in HBM, device-timed, max over ranks.
+`e2e`     : the same metric through the C-ABI host-buffer call tmgpu_tokenize_batch with pinned HOST
+            buffers -- H2D of the strings and D2H of the ids inside the timed region; `e2e.pageable`
+            repeats it with ordinary (pageable) host memory, which is what a cgo caller passes.
+`roofline`: the tokenize pipeline against the measured HBM copy bandwidth; algorithmic bytes = 1 B
+            read per input byte; per-stage times from CUDA events inside the library.
+`parity`  : checksum of the ids of the CPU sample (per-string FNV-1a, summed) against the same fold of
+            the reference runtime's own output.
+`decode`  : Vocab.Decode of the ids just produced (ids read + bytes written against HBM).
 `cpu_baseline`: oracle/_ref (the reference's unmodified C++ runtime) on the box's host cores, on a
-           bounded sample of the same batch.
+            bounded sample of the same batch.
 Prints exactly one JSON line on rank 0.
 """
 from __future__ import annotations
@@ -34,6 +38,13 @@ sys.path.insert(0, ROOT)
 METRIC = "MB/s tokenized (input bytes) at 32K vocab, 1/2/4/8 B200; bit-exact token IDs"
 UNIT = "MB/s"
 WORKLOAD = "c2"
+# BASELINE.json configs[k]: which one, on how many GPUs it is named, id width of the server path
+NAMED = {
+    "c2": dict(idx=1, gpus=1, enc=2, name="englishcode-32000-consistent-v1"),
+    "c3": dict(idx=2, gpus=1, enc=2, name="gpt2 imported vocab (50257)"),
+    "c4": dict(idx=3, gpus=4, enc=2, name="code-65536-unfiltered-nocapcode-v1"),
+    "c5": dict(idx=4, gpus=8, enc=4, name="englishcode-100256-clean-v1"),
+}
 
 
 def parse():
@@ -42,29 +53,38 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--strings", type=int, default=0, help="strings per GPU (default: the config's 1,000,000)")
-    ap.add_argument("--config", default=WORKLOAD)
-    ap.add_argument("--e2e-steps", type=int, default=3, help="timed steps of the host-buffer (e2e) leg, >= 1")
+    ap.add_argument("--strings", type=int, default=0, help="strings per GPU (default: the config's share)")
+    ap.add_argument("--config", default=WORKLOAD, choices=sorted(NAMED))
+    ap.add_argument("--e2e-steps", type=int, default=5, help="timed steps of the host-buffer (e2e) legs, >= 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--check", action="store_true", help="verify a sample of the GPU ids against the oracle")
+    ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline / parity")
     args = ap.parse_args()
     args.e2e_steps = max(1, args.e2e_steps)
     return args
 
 
+def strings_per_gpu(args):
+    from workloads import configs
+    if args.strings:
+        return args.strings
+    return configs.CONFIGS[args.config]["n"] // NAMED[args.config]["gpus"]
+
+
 def config_block(args, n_strings, total_bytes, world):
     from workloads import configs
-    cfg = configs.CONFIGS[args.config]
+    cfg, nm = configs.CONFIGS[args.config], NAMED[args.config]
     return {
-        "workload": f"{cfg['vocab']} (stand-in for BASELINE configs[1] englishcode-32000-consistent-v1), "
+        "workload": f"{cfg['vocab']} (stand-in for BASELINE configs[{nm['idx']}] {nm['name']}), "
                     f"{n_strings} strings/GPU ~U[{cfg['lo']},{cfg['hi']}] B, ASCII prose+code",
+        "baseline_config": nm["idx"],
         "strings_per_gpu": n_strings,
         "bytes_per_gpu": int(total_bytes),
         "vocab_ids": cfg["ids"],
         "capcode": cfg["capcode"],
-        "enc_len": 2,
+        "enc_len": nm["enc"],
         "parallelism": f"strings sharded over {world} GPU(s), no data-path collective",
-        "l2_policy": "inputs larger than L2 (512 MB/step vs 126 MB), no flush",
+        "l2_policy": f"inputs larger than L2 ({total_bytes / 1e6:.0f} MB/step vs 126 MB), no flush",
         "mb": "1e6 bytes",
     }
 
@@ -79,6 +99,7 @@ def clocks_sampler(gpu_index: int, stop: threading.Event, out: list):
                               "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
     except OSError:
         return
+
     def reader():
         for line in p.stdout:
             out.append(line.strip())
@@ -121,27 +142,51 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the tokenize kernel from the committed ncu --set full capture."""
+def ncu_capture(config):
+    """Numbers that only a profiler can give (dram bytes, warp instructions per launch), from the
+    committed ncu --set full capture of the same command (profiles/traffic.json), keyed by config."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(p) as f:
-            return json.load(f)
+            t = json.load(f)
+        return t.get(config) if isinstance(t.get(config), dict) else None
     except Exception:
         return None
 
 
+def host_cores():
+    """(threads used, what the OS says, what this process may actually use)."""
+    logical = os.cpu_count() or 1
+    try:
+        affinity = len(os.sched_getaffinity(0))
+    except Exception:
+        affinity = logical
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            a, b = f.read().split()
+            if a != "max":
+                quota = float(a) / float(b)
+    except Exception:
+        pass
+    eff = affinity if quota is None else max(1, min(affinity, int(quota + 0.5)))
+    return eff, {"logical": logical, "affinity": affinity, "cgroup_quota": quota, "effective": eff}
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_rate(vocab_bytes, data_np, off_np, budget_s=12.0, threads=None):
-    """Time oracle/_ref (reference C++ runtime) on `threads` host cores on a bounded prefix."""
-    import numpy as np
+    """Time oracle/_ref (reference C++ runtime) on `threads` host cores on a bounded prefix of the
+    batch.  Returns the rate, the prefix length and the checksum of its ids."""
     from oracle import oracle
     kind = "reference" if oracle.have_reference() else "port"
-    threads = threads or os.cpu_count() or 1
+    eff, cores = host_cores()
+    threads = threads or eff
     n = len(off_np) - 1
     if kind == "reference":
         v = oracle.OracleVocab(vocab_bytes, "reference")
         probe = min(n, 2000)
+        for _ in range(2):   # warm-ups (page in the tables, spin up the threads)
+            v.tokenize_batch_timed(data_np, off_np[:probe + 1], threads)
         t = time.perf_counter()
         v.tokenize_batch_timed(data_np, off_np[:probe + 1], threads)
         dt = max(time.perf_counter() - t, 1e-4)
@@ -151,14 +196,31 @@ def cpu_reference_rate(vocab_bytes, data_np, off_np, budget_s=12.0, threads=None
         ids, chk = v.tokenize_batch_timed(data_np, off_np[:take + 1], threads)
         dt = time.perf_counter() - t
         nbytes = float(off_np[take] - off_np[0])
-        t1 = time.perf_counter()
-        one = min(take, max(200, take // (4 * threads)))
-        v.tokenize_batch_timed(data_np, off_np[:one + 1], 1)
-        dt1 = time.perf_counter() - t1
-        return {"value": nbytes / dt / 1e6, "unit": UNIT, "cores": threads, "kind": kind,
+        # single thread, pinned to one CPU, >= 2 s after warm-ups (tokenmonster-cpp/tests/bench.cpp:56-80)
+        one_rate = None
+        try:
+            old = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, {sorted(old)[0]})
+        except Exception:
+            old = None
+        try:
+            one = min(take, 400)
+            for _ in range(5):
+                v.tokenize_batch_timed(data_np, off_np[:one + 1], 1)
+            t1 = time.perf_counter()
+            done_bytes, reps = 0.0, 0
+            while time.perf_counter() - t1 < 2.0:
+                v.tokenize_batch_timed(data_np, off_np[:one + 1], 1)
+                done_bytes += float(off_np[one] - off_np[0])
+                reps += 1
+            one_rate = done_bytes / (time.perf_counter() - t1) / 1e6
+        finally:
+            if old is not None:
+                os.sched_setaffinity(0, old)
+        return {"value": nbytes / dt / 1e6, "unit": UNIT, "cores": threads, "cores_detail": cores, "kind": kind,
                 "sample": f"first {take} strings ({nbytes / 1e6:.1f} MB) of the same batch, {dt:.1f} s wall, one std::thread "
                           f"per contiguous slice (training/tokenmonsterserver.go:364-377 analogue)",
-                "single_thread_value": float(off_np[one] - off_np[0]) / dt1 / 1e6, "ids": int(ids)}
+                "single_thread_value": one_rate, "ids": int(ids), "strings": take, "checksum": int(chk)}
     v = oracle.OracleVocab(vocab_bytes, "port")
     take, nbytes = 0, 0
     t = time.perf_counter()
@@ -167,24 +229,29 @@ def cpu_reference_rate(vocab_bytes, data_np, off_np, budget_s=12.0, threads=None
         nbytes += int(off_np[take + 1] - off_np[take])
         take += 1
     dt = time.perf_counter() - t
-    return {"value": nbytes / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"first {take} strings ({nbytes / 1e6:.1f} MB), scalar C port, 1 thread"}
+    return {"value": nbytes / dt / 1e6, "unit": UNIT, "cores": 1, "cores_detail": cores, "kind": "port",
+            "sample": f"first {take} strings ({nbytes / 1e6:.1f} MB), scalar C port, 1 thread", "strings": take,
+            "checksum": None}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation on the host cores."""
+    """--impl reference: the reference's own CPU implementation on the host cores, on the batch the
+    GPU arm tokenizes (same generator, same seed: rank 0's shard)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import numpy as np
-    from workloads import configs
+    from workloads import configs, corpus
     cfg = configs.CONFIGS[args.config]
-    n = args.strings or cfg["n"]
+    n = strings_per_gpu(args)
     vb = configs.vocab_bytes(args.config)
-    sample_n = min(n, 600000)
-    data, off = configs.batch(args.config, sample_n, "cpu")
+    base = corpus.base_text(cfg["seed"], 16 << 20, cfg["code"])
+    # the same strings as the GPU arm's rank 0 (the generator is deterministic in (n, seed)); each
+    # step times a bounded prefix of it
+    data, off = corpus.make_batch(base, n, cfg["lo"], cfg["hi"], cfg["seed"] + 1, "cpu")
     data_np, off_np = data.numpy(), off.numpy().astype(np.uint64)
-    threads = os.cpu_count() or 1
+    total_bytes = int(off_np[-1])
+    threads, _ = host_cores()
     per_step_budget = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
         cpu_reference_rate(vb, data_np, off_np, budget_s=min(1.0, per_step_budget), threads=threads)
@@ -199,12 +266,13 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": config_block(args, n, float(off_np[-1]) / sample_n * n, max(1, args.gpus)),   # the GPU arm's config
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"],
-                         "sample": last["sample"]},
+        "config": config_block(args, n, total_bytes, max(1, args.gpus)),   # the GPU arm's config
+        "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "cores_detail", "kind", "sample",
+                                              "single_thread_value") if k in last},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    line["cpu_baseline"]["value"] = value
     emit_line(line)
     return 0
 
@@ -227,6 +295,20 @@ def emit_line(obj):
     out = _REAL_STDOUT or sys.stdout
     out.write(json.dumps(obj) + "\n")
     out.flush()
+
+
+def time_host_calls(vocab, h_np, h_off, enc, steps, dev):
+    import torch
+    r = vocab.tokenize_batch(h_np, h_off, enc)  # warm-up (allocations, pinned pools)
+    r = None
+    r = vocab.tokenize_batch(h_np, h_off, enc)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r = None  # hand the previous result's pinned buffers back to the pool first
+        r = vocab.tokenize_batch(h_np, h_off, enc)
+    torch.cuda.synchronize(dev)
+    return (time.perf_counter() - t0) / steps, r
 
 
 def main():
@@ -254,7 +336,8 @@ def main():
     from workloads import configs, corpus
 
     cfg = configs.CONFIGS[args.config]
-    n = args.strings or cfg["n"]
+    n = strings_per_gpu(args)
+    enc = NAMED[args.config]["enc"]
     if rank == 0:
         vb = configs.vocab_bytes(args.config)  # builds + caches the stand-in once
     if world > 1:
@@ -267,7 +350,6 @@ def main():
     data, off = corpus.make_batch(base, n, cfg["lo"], cfg["hi"], cfg["seed"] + 1 + 1000 * rank, dev)
     total_bytes = int(off[-1].item())
     ws = DeviceWorkspace(vocab, n, total_bytes)
-    enc = 2
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -293,57 +375,85 @@ def main():
     elapsed_ms = e0.elapsed_time(e1)
     launches = ws.launches() * args.steps
     ktimes = [t for t in ws.kernel_times_ms() if t > 0]
+    stages = ws.stage_times_ms()
     res = ws.results()
     n_tokens = res["n_tokens"]
     bad_status = int((res["status"] != 0).sum().item())
 
-    # ---- end to end through the C-ABI host call (pinned host buffers) --------------------------
+    # ---- decode of the ids just produced (device resident) ------------------------------------
+    decode_line = None
+    if not args.no_decode:
+        toks = res["tokens_u8"].clone()
+        toff = res["tok_off"].clone()
+        for _ in range(2):
+            out_b, out_off = ws.decode(toks, toff, enc)
+        torch.cuda.synchronize(dev)
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(2, min(args.steps, 5))
+        d0.record()
+        for _ in range(reps):
+            out_b, out_off = ws.decode(toks, toff, enc)
+        d1.record()
+        torch.cuda.synchronize(dev)
+        dec_ms = d0.elapsed_time(d1) / reps
+        same = bool(out_b.numel() == data.numel() and torch.equal(out_b, data)) if (cfg["capcode"] == 0 or True) else None
+        decode_line = {"ms": dec_ms, "text_bytes": int(out_b.numel()), "ids": int(n_tokens),
+                       "value": out_b.numel() / (dec_ms / 1e3) / 1e6, "unit": "MB/s of text",
+                       "round_trip_identical": same, "launches": ws.launches()}
+        del toks, toff, out_b, out_off
+
+    # ---- end to end through the C-ABI host call ------------------------------------------------
     h_data = torch.empty(total_bytes, dtype=torch.uint8, pin_memory=True)
     h_data.copy_(data)
     h_off = off.cpu().numpy().astype(np.uint64)
     h_np = h_data.numpy()
-    r = vocab.tokenize_batch(h_np, h_off, enc)  # warm-up (allocations, pinned pools)
+    sync_all()
+    e2e_s, r = time_host_calls(vocab, h_np, h_off, enc, args.e2e_steps, dev)
     d2h = r.raw.nbytes + r.tok_off.nbytes + r.missing.nbytes + r.status.nbytes
     h2d = total_bytes + h_off.nbytes
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        r = None  # hand the previous result's pinned buffers back to the pool first
-        r = vocab.tokenize_batch(h_np, h_off, enc)
-    torch.cuda.synchronize(dev)
-    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
     stop.set()
     th.join(timeout=3)
+    p_np = np.empty(total_bytes, dtype=np.uint8)   # ordinary (pageable) memory: what a cgo caller passes
+    p_np[:] = h_np
+    page_s, rp = time_host_calls(vocab, p_np, h_off, enc, max(1, args.e2e_steps // 2), dev)
+    rp = None
+    del p_np
 
-    # ---- N > 1: the single-root path (one NCCL scatter of bytes, one gather of ids) -----------
+    # ---- N > 1: the single-root path (pipelined NCCL scatter of bytes / gather of ids) ---------
     root_line = None
     if world > 1:
-        from tokenmonster_b200.dist import gpu_compute, tokenize_from_root
-        comp = gpu_compute(ws, enc)
+        from tokenmonster_b200.dist import RootPipeline
+        pipe = RootPipeline(vocab, ws, enc, dev, n, total_bytes)
         for _ in range(2):
-            out = tokenize_from_root(data if rank == 0 else None, off if rank == 0 else None, comp, 0, dev)
+            out = pipe.run(data if rank == 0 else None, off if rank == 0 else None)
         sync_all()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
         r0.record()
-        out = tokenize_from_root(data if rank == 0 else None, off if rank == 0 else None, comp, 0, dev)
+        for _ in range(reps):
+            out = pipe.run(data if rank == 0 else None, off if rank == 0 else None)
         r1.record()
         sync_all()
-        tr = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+        tr = torch.tensor([r0.elapsed_time(r1) / reps], dtype=torch.float64, device=dev)
         dist.all_reduce(tr, op=dist.ReduceOp.MAX)
         if rank == 0:
             same = bool(torch.equal(out[0], res["tokens_u8"]))   # identical bytes to the 1-GPU result
+            one_ms = (sum(ktimes) / len(ktimes)) if ktimes else None
             root_line = {"value": total_bytes / (float(tr[0]) / 1e3) / 1e6, "unit": UNIT, "ms": float(tr[0]),
-                         "what": "rank 0's batch scattered over all ranks by bytes, tokenized, ids gathered back "
-                                 "(NCCL grouped send/recv); strong scaling of one batch", "identical_to_1gpu": same}
+                         "what": "rank 0's batch scattered over all ranks by bytes in chunks, tokenized, ids gathered back "
+                                 "(NCCL send/recv, scatter k+1 || kernels k || gather k-1); strong scaling of one batch",
+                         "identical_to_1gpu": same, "chunks": pipe.chunks,
+                         "nvlink_bound_ms": (total_bytes * (world - 1) / world / 770e9 + n_tokens * enc * (world - 1) / world / 770e9) * 1e3,
+                         "strong_scaling_efficiency": (one_ms / (float(tr[0]) * world)) if one_ms else None}
 
     # ---- reduce over ranks --------------------------------------------------------------------
-    t = torch.tensor([elapsed_ms, e2e_s, float(total_bytes), float(n_tokens)], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms, e2e_s, float(total_bytes), float(n_tokens), page_s], dtype=torch.float64, device=dev)
     if world > 1:
         mx = t.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = t.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        elapsed_ms, e2e_s = float(mx[0]), float(mx[1])
+        elapsed_ms, e2e_s, page_s = float(mx[0]), float(mx[1]), float(mx[4])
         all_bytes, all_tokens = float(sm[2]), float(sm[3])
     else:
         all_bytes, all_tokens = float(total_bytes), float(n_tokens)
@@ -357,38 +467,54 @@ def main():
     peak, peak_src = hbm_peak()
     k_ms = sum(ktimes) / len(ktimes) if ktimes else None
     achieved = (total_bytes / (k_ms / 1e3) / 1e9) if k_ms else None
-    traffic = ncu_traffic()
+    cap = ncu_capture(args.config)
+    clocks = summarize_clocks(samples)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": config_block(args, n, total_bytes, world),
         "e2e": {"value": all_bytes / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "api": "tmgpu_tokenize_batch (C ABI, pinned host buffers)", "steps": args.e2e_steps},
+                "api": "tmgpu_tokenize_batch (C ABI, pinned host buffers)", "steps": args.e2e_steps,
+                "pageable": {"value": all_bytes / page_s / 1e6, "unit": UNIT,
+                             "what": "same call, input in ordinary pageable host memory (what cgo passes)"}},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None,
-                     "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
-                     "kernel": "tokenize_thread_kernel<1024, capcode, store>", "kernel_ms": k_ms, "kernel_share_of_step": (k_ms * args.steps / elapsed_ms) if k_ms else None,
+                     "traffic": cap.get("dram_bytes_per_launch") if cap else None,
+                     "traffic_source": cap.get("source") if cap else None,
+                     "kernel": "tokenize pipeline: encode_kernel x2 + table_kernel + chain_kernel (CUDA events around the four)",
+                     "kernel_ms": k_ms, "kernel_share_of_step": (k_ms * args.steps / elapsed_ms) if k_ms else None,
+                     "stages_ms": dict(zip(("capcode_lengths_scan", "capcode_text", "position_table", "chain"), stages)),
                      "algorithmic_bytes_per_launch": total_bytes, "peak_source": peak_src},
-        "clocks": summarize_clocks(samples),
+        "clocks": clocks,
         "tokens_per_step": all_tokens, "chars_per_token": all_bytes / max(all_tokens, 1.0), "strings_failed": bad_status,
-        "kernel_mapping": {"1": "lane-per-string (T2)"}.get(os.environ.get("TMGPU_GROUP", "1"), "lanes-over-branches G=" + os.environ.get("TMGPU_GROUP", "1")),
     }
+    if cap and cap.get("warp_inst_per_launch") and k_ms:
+        # issue roofline: warp instructions of one launch (ncu, committed capture) against what the
+        # 148 SMs x 4 schedulers can issue at the clock sampled during this run
+        mhz = clocks.get("sm_mhz") or 1965.0
+        floor_ms = cap["warp_inst_per_launch"] / (148 * 4 * mhz * 1e6) * 1e3
+        line["issue_roofline"] = {"warp_inst_per_launch": cap["warp_inst_per_launch"], "issue_floor_ms": floor_ms,
+                                  "frac": floor_ms / k_ms, "source": cap.get("source")}
+    if decode_line:
+        dec_bytes = decode_line["ids"] * enc + decode_line["text_bytes"]
+        decode_line["roofline"] = {"bound": "hbm", "achieved": dec_bytes / (decode_line["ms"] / 1e3) / 1e9, "peak": peak,
+                                   "unit": "GB/s", "frac": dec_bytes / (decode_line["ms"] / 1e3) / 1e9 / peak,
+                                   "algorithmic_bytes": dec_bytes, "what": "ids read + text written, whole decode call"}
+        line["decode"] = decode_line
     if root_line:
         line["root_scatter_gather"] = root_line
-    if args.check:
-        from oracle import oracle
-        chk = oracle.OracleVocab(vb, "port")
-        ok = 0
-        for s in range(0, min(n, 20000), 97):
-            want, _ = chk.tokenize(h_np[int(h_off[s]):int(h_off[s + 1])].tobytes())
-            assert np.array_equal(r[s].astype(np.uint32), want), f"string {s} differs from the oracle"
-            ok += 1
-        line["checked_strings"] = ok
     if not args.no_cpu_baseline:
-        sample_n = min(n, 600000)
-        cb = cpu_reference_rate(vb, h_np, h_off[:sample_n + 1], budget_s=12.0)
+        cb = cpu_reference_rate(vb, h_np, h_off, budget_s=args.cpu_budget)
+        take, chk = cb.pop("strings"), cb.pop("checksum")
+        if chk is not None:
+            from oracle import oracle
+            mine = oracle.ids_checksum(r.raw, enc, r.tok_off, take)
+            ids_mine = int(r.tok_off[take])
+            line["parity"] = {"strings": take, "ids": ids_mine, "match": bool(mine == chk and ids_mine == cb["ids"]),
+                              "checksum": f"{mine:016x}", "reference_checksum": f"{chk:016x}",
+                              "against": "oracle/_ref (reference C++ runtime), per-string FNV-1a of the ids, summed"}
         line["cpu_baseline"] = cb
     emit_line(line)
     if world > 1:

@@ -67,7 +67,8 @@ std::vector<uint32_t> table(const Sim& S, const uint8_t* text, int L, bool to_lo
     if (to_lower && b - 'A' < 26u) b |= 0x20u;
     if (p == L - 1) packed = t.dfa_d1[b];
     else
-      packed = dfa_next(packed, prev, b, 32u - t.dfa_bits, (1u << t.dfa_bits) - 1u, [&](uint32_t i) { return bk[i]; },
+      packed = dfa_next(packed, prev, b, 32u - t.dfa_bits, (1u << t.dfa_bits) - 1u,
+                        [&](uint32_t i, uint4* k, uint4* v) { *k = bk[2 * i]; *v = bk[2 * i + 1]; },
                         [&](uint32_t i) { return t.dfa_d2[i]; });
     const uint32_t code = t.class_code[b];
     words[p] = position_word(packed, code, tr, off);
@@ -177,7 +178,8 @@ long hs_tokenize(void* h, const uint8_t* data, size_t n, int prenorm, int count_
     }
     return 0u;
   };
-  while (z.i < L) chain_step(T, cs, z, count_mode == 0, emit, on_miss);
+  auto load_rec = [&](uint32_t idx, uint4* r0, uint4* r1) { *r0 = T.rec[2 * idx]; *r1 = T.rec[2 * idx + 1]; };
+  while (z.i < L) chain_step(T, cs, z, count_mode == 0, load_rec, emit, on_miss);
   *missing = z.miss;
   return long(count_mode ? z.cnt : cnt);
 }

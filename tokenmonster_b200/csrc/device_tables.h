@@ -35,16 +35,17 @@ struct DfaDev {
 };
 
 // One transition: the packed state after consuming byte b (previous text byte `prev`) from the
-// state in `packed`.  load4(i) reads uint4 number i of the bucket array, d2(i) entry i of dfa_d2.
-template <class Load4, class LoadD2>
-TM_HD uint32_t dfa_next(uint32_t packed, uint32_t prev, uint32_t b, uint32_t shift, uint32_t mask, Load4 load4,
-                        LoadD2 d2) {
+// state in `packed`.  load_bucket(h, &keys, &vals) reads the 32-byte bucket h, d2(i) entry i of dfa_d2.
+template <class LoadBucket, class LoadD2>
+TM_HD uint32_t dfa_next(uint32_t packed, uint32_t prev, uint32_t b, uint32_t shift, uint32_t mask,
+                        LoadBucket load_bucket, LoadD2 d2) {
   const uint32_t s = packed & kDfaStateMask;
   if (s != 0) {   // the root has no transition to depth >= 3
     const uint32_t key = (s << 8) | b;
     uint32_t h = dfa_hash(key, shift);
     for (;;) {
-      const uint4 k = load4(2 * h), v = load4(2 * h + 1);
+      uint4 k, v;
+      load_bucket(h, &k, &v);
       if ((k.x & ~kDfaOverflow) == key) return v.x;
       if (k.y == key) return v.y;
       if (k.z == key) return v.z;

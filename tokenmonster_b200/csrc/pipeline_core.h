@@ -187,8 +187,10 @@ TM_HD void chain_reset(ChainLane& z) {
 // the delete token of a two-id step), adv = characters the step advances by.
 // on_miss(position) -> ids added: a byte no token covers (go:1269-1276); the caller emits unk.
 // two_ids: false for Vocab.Count, which adds 1 where tokenize emits 2 ids.
-template <class Emit, class Miss>
-TM_HD void chain_step(const ChainTables& T, const ChainString& S, ChainLane& z, bool two_ids, Emit emit, Miss on_miss) {
+// load_rec(index, &r0, &r1): the 32-byte token record (one 256-bit load on the device).
+template <class LoadRec, class Emit, class Miss>
+TM_HD void chain_step(const ChainTables& T, const ChainString& S, ChainLane& z, bool two_ids, LoadRec load_rec, Emit emit,
+                      Miss on_miss) {
   if (!z.have) {   // loop top: the longest token at i (go:1049)
     const uint32_t w = S.words[z.i];
     const uint32_t l = pw_len(w);
@@ -203,7 +205,8 @@ TM_HD void chain_step(const ChainTables& T, const ChainString& S, ChainLane& z, 
     z.tok_len = int(l);
     z.have = true;
   }
-  const uint4 r0 = T.rec[2 * z.idx], r1 = T.rec[2 * z.idx + 1];
+  uint4 r0, r1;
+  load_rec(z.idx, &r0, &r1);
   const uint32_t oflag = r0.x & 0xFFu;
   const int onw = int((r0.x >> 8) & 0xFFu);
   const int alen1 = int(r0.x >> 24), alen2 = int(r1.x & 0xFFu);

@@ -66,6 +66,13 @@ __device__ __forceinline__ void pipe_stage_tma(uint8_t* smem, const uint8_t* ima
   }
 }
 
+// one 256-bit read-only load (SASS: LDG.E.256.CONSTANT): a whole 32-byte bucket / record per lane
+__device__ __forceinline__ void pipe_load32(const uint4* p, uint4* a, uint4* b) {
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a->x), "=r"(a->y), "=r"(a->z), "=r"(a->w), "=r"(b->x), "=r"(b->y), "=r"(b->z), "=r"(b->w)
+               : "l"(p));
+}
+
 __device__ __forceinline__ uint32_t pipe_lower4(uint32_t w) {  // ASCII A-Z -> a-z in 4 packed bytes
   const uint32_t hi = w & 0x80808080u;
   const uint32_t x = w & 0x7F7F7F7Fu;
@@ -337,7 +344,8 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
     if (p == L - 1) {
       packed = s_d1[b];
     } else {
-      packed = dfa_next(packed, prev, b, D.shift, D.mask, [&](uint32_t i) { return __ldg(&D.buckets[i]); },
+      packed = dfa_next(packed, prev, b, D.shift, D.mask,
+                        [&](uint32_t i, uint4* k, uint4* v) { pipe_load32(D.buckets + 2 * i, k, v); },
                         [&](uint32_t i) { return __ldg(&D.d2[i]); });
     }
     const uint32_t code = s_code[b];
@@ -433,7 +441,7 @@ __global__ void __launch_bounds__(kPipeBlock) chain_kernel(const TokenizeArgs A)
     }
     uint32_t stored = z.cnt;   // ids stored so far follow the lane's own count
     chain_step(
-        T, S, z, two_ids,
+        T, S, z, two_ids, [&](uint32_t idx, uint4* r0, uint4* r1) { pipe_load32(T.rec + 2 * idx, r0, r1); },
         [&](uint32_t id, uint32_t, uint32_t adv) {
           if (!STORE && A.scores) atomicAdd(&A.scores[id], static_cast<unsigned long long>(adv));
           if (STORE && stored < cap) A.slab[slab_base + stored] = id;

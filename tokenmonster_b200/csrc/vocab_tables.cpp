@@ -213,7 +213,8 @@ int host_dfa_lookup(const HostTables& h, const uint8_t* window, int n, uint32_t*
     if (p == n - 1) w = h.dfa_d1[window[p]];
     else
       w = dfa_next(w, window[p + 1], window[p], 32u - h.dfa_bits, (1u << h.dfa_bits) - 1u,
-                   [&](uint32_t i) { return bk[i]; }, [&](uint32_t i) { return h.dfa_d2[i]; });
+                   [&](uint32_t i, uint4* k, uint4* v) { *k = bk[2 * i]; *v = bk[2 * i + 1]; },
+                   [&](uint32_t i) { return h.dfa_d2[i]; });
   }
   const uint32_t* hot = &h.dfa_hot[size_t(w & kDfaStateMask) * 4];
   if (index) *index = hot[0] & 0xFFFFFFu;

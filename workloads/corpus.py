@@ -218,7 +218,7 @@ def make_batch(base: bytes, n_strings: int, min_len: int, max_len: int, seed: in
         return torch.frombuffer(bytearray(blob), dtype=torch.uint8), off
     b, starts, lens, off_d = b.to(dev), starts.to(dev), lens.to(dev), off.to(dev)
     data = torch.empty(total, dtype=torch.uint8, device=dev)
-    chunk = 1 << 16  # strings per chunk keeps the index temporaries bounded
+    chunk = max(1, min(1 << 16, (128 << 20) // max(1, max_len)))  # bounds the index temporaries (~128 MB of positions)
     for lo in range(0, n_strings, chunk):
         hi = min(lo + chunk, n_strings)
         l = lens[lo:hi]
