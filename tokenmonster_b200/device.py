@@ -36,6 +36,7 @@ class DeviceWorkspace:
 
     def __init__(self, vocab: Vocab, max_strings: int, max_bytes: int):
         self.vocab = vocab
+        self.max_strings, self.max_bytes = int(max_strings), int(max_bytes)
         self.device = torch.device("cuda", vocab.device)
         self._h = C.c_void_p()
         check(lib().tmgpu_workspace_create(vocab._h, max_strings, max_bytes, C.byref(self._h)))
@@ -93,6 +94,19 @@ class DeviceWorkspace:
             "counts": _view(self.view.counts, n, "<i4", self.device),
             "n_tokens": total,
             "enc_len": self._enc,
+        }
+
+    def raw_views(self, n: int, token_bytes: int):
+        """Byte views of the last launch's outputs WITHOUT synchronising (valid in stream order):
+        the 8-byte id total, counts / missing as bytes, status, and the first `token_bytes` bytes of
+        the dense id buffer (which may reach beyond the ids actually written)."""
+        v = self.view
+        return {
+            "n_tokens_u8": _view(v.n_tokens, 8, "|u1", self.device),
+            "counts_u8": _view(v.counts, 4 * n, "|u1", self.device),
+            "missing_u8": _view(v.missing, 4 * n, "|u1", self.device),
+            "status": _view(v.status, n, "|u1", self.device),
+            "tokens_u8": _view(v.tokens, token_bytes, "|u1", self.device),
         }
 
     def decode(self, tokens_u8: torch.Tensor, tok_off: torch.Tensor, enc_len: int, stream=None):
