@@ -4,6 +4,7 @@
 // that tests/test_host_sim.py can compare tables + logic with the oracle on a machine without a
 // GPU.  Never linked into libtmgpu.so; the product has no CPU path.
 #include <cstdint>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -21,61 +22,60 @@ struct Sim {
   uint8_t cls[128];
 };
 
-// stage 1 as the encode kernel does it (fast path of 4, else one character)
-std::vector<uint8_t> encode(const Sim& S, const uint8_t* raw, int n, bool to_lower, bool* bad) {
-  std::vector<uint8_t> out;
-  *bad = false;
-  for (int k = 0; k < n; k++)
-    if (raw[k] & 0x80) { *bad = true; return out; }
+// stages 1 + 2 as the table kernel does them: from the end of the string, the encoder yields the
+// bytes of one raw character at a time (forward order), a byte queue hands them to the automaton
+// last byte first, one byte per step.  Returns the position words (index = normalized position)
+// and the normalized text.
+struct Tabled {
+  std::vector<uint32_t> words;
+  std::vector<uint8_t> text;
+  bool bad = false;
+};
+
+Tabled table(const Sim& S, const uint8_t* raw, int n, bool cap, bool to_lower, bool want_ascii) {
+  const HostTables& t = S.t;
+  Tabled R;
+  if (want_ascii)
+    for (int k = 0; k < n; k++)
+      if (raw[k] & 0x80) { R.bad = true; return R; }
   auto at = [&](int j) -> uint32_t {
     uint32_t c = raw[j];
     if (to_lower && c - 'A' < 26u) c |= 0x20u;
     return c;
   };
-  CapState e;
-  cap_reset(e);
-  int k = 0;
-  while (k < n) {
-    if (k + 4 <= n) {
-      const uint32_t w4 = at(k) | (at(k + 1) << 8) | (at(k + 2) << 16) | (at(k + 3) << 24);
-      const uint32_t c5 = (k + 4 < n) ? at(k + 4) : 0u;
-      if (cap_fast4(e, w4, c5)) {
-        for (int j = 0; j < 4; j++) out.push_back(uint8_t(at(k + j)));
-        k += 4;
-        continue;
-      }
-    }
-    uint32_t bytes = 0;
-    const uint32_t nb = cap_step(e, S.cls, at(k), (k + 1 < n) ? at(k + 1) : uint32_t('.'), k, n, at, &bytes);
-    for (uint32_t j = 0; j < nb; j++) out.push_back(uint8_t(bytes >> (8 * j)));
-    k++;
-  }
-  return out;
-}
-
-// stage 2 as the table kernel does it
-std::vector<uint32_t> table(const Sim& S, const uint8_t* text, int L, bool to_lower) {
-  const HostTables& t = S.t;
-  std::vector<uint32_t> words(size_t(L) + 1, 0);
   const uint4* bk = reinterpret_cast<const uint4*>(t.dfa_buckets.data());
   const uint32_t off = t.charset == 2 ? 2u : 1u;
   ClassTrail tr;
   trail_reset(tr, t.class_code[0]);
-  uint32_t packed = 0, prev = 0;
-  for (int p = L - 1; p >= 0; p--) {
-    uint32_t b = text[p];
-    if (to_lower && b - 'A' < 26u) b |= 0x20u;
-    if (p == L - 1) packed = t.dfa_d1[b];
+  RevCap e;
+  revcap_reset(e);
+  uint32_t packed = 0, prev = 0, qbytes = 0, qn = 0;
+  int k = n - 1;
+  bool first = true;
+  while (k >= 0 || qn) {
+    if (qn == 0) {
+      if (cap) qn = revcap_step(e, S.cls, at(k), k >= 1 ? at(k - 1) : 0u, k >= 2 ? at(k - 2) : 0u, k, at, &qbytes);
+      else { qbytes = at(k); qn = 1; }
+      k--;
+      if (qn == 0) continue;   // a space replaced by a marker emits nothing
+    }
+    const uint32_t b = (qbytes >> (8 * (qn - 1))) & 0xFFu;
+    qn--;
+    if (first) packed = t.dfa_d1[b];
     else
       packed = dfa_next(packed, prev, b, 32u - t.dfa_bits, (1u << t.dfa_bits) - 1u,
-                        [&](uint32_t i, uint4* k, uint4* v) { *k = bk[2 * i]; *v = bk[2 * i + 1]; },
+                        [&](uint32_t i, uint4* kk, uint4* v) { *kk = bk[2 * i]; *v = bk[2 * i + 1]; },
                         [&](uint32_t i) { return t.dfa_d2[i]; });
+    first = false;
     const uint32_t code = t.class_code[b];
-    words[p] = position_word(packed, code, tr, off);
+    R.words.push_back(position_word(packed, code, tr, off));
+    R.text.push_back(uint8_t(b));
     trail_push(tr, code);
     prev = b;
   }
-  return words;
+  std::reverse(R.words.begin(), R.words.end());
+  std::reverse(R.text.begin(), R.text.end());
+  return R;
 }
 }  // namespace
 
@@ -115,22 +115,12 @@ int hs_dfa_lookup(void* h, const uint8_t* window, int n, uint32_t* index, uint32
 // normalized text of an ASCII string (capcode 2 and / or lower-casing); -1 = refused (byte >= 0x80)
 long hs_normalize(void* h, const uint8_t* data, size_t n, uint8_t* out, size_t cap) {
   const Sim& S = *static_cast<Sim*>(h);
-  const bool to_lower = (S.t.normflag & 2) != 0;
-  std::vector<uint8_t> text;
-  if (S.t.capcode == 2) {
-    bool bad = false;
-    text = encode(S, data, int(n), to_lower, &bad);
-    if (bad) return -1;
-  } else {
-    text.assign(data, data + n);
-    for (auto& c : text) {
-      if ((S.t.normflag != 0) && (c & 0x80)) return -1;
-      if (to_lower && uint32_t(c) - 'A' < 26u) c |= 0x20;
-    }
-  }
-  if (text.size() > cap) return -2;
-  if (!text.empty()) std::memcpy(out, text.data(), text.size());
-  return long(text.size());
+  const HostTables& t = S.t;
+  const Tabled R = table(S, data, int(n), t.capcode == 2, (t.normflag & 2) != 0, t.normflag != 0 || t.capcode == 2);
+  if (R.bad) return -1;
+  if (R.text.size() > cap) return -2;
+  if (!R.text.empty()) std::memcpy(out, R.text.data(), R.text.size());
+  return long(R.text.size());
 }
 
 // ids of one string.  prenorm: the text is already normalized.  count_mode: Vocab.Count (quirk Q2).
@@ -141,21 +131,10 @@ long hs_tokenize(void* h, const uint8_t* data, size_t n, int prenorm, int count_
   const HostTables& t = S.t;
   *missing = 0;
   if (t.max_len == 0) return 0;
-  const bool to_lower = !prenorm && (t.normflag & 2) != 0;
-  std::vector<uint8_t> text;
-  const uint8_t* tp = data;
-  int L = int(n);
-  if (!prenorm && t.capcode == 2) {
-    bool bad = false;
-    text = encode(S, data, int(n), to_lower, &bad);
-    if (bad) return -1;
-    tp = text.data();
-    L = int(text.size());
-  } else if (!prenorm && t.normflag != 0) {
-    for (size_t k = 0; k < n; k++)
-      if (data[k] & 0x80) return -1;
-  }
-  const std::vector<uint32_t> words = table(S, tp, L, to_lower && t.capcode != 2);
+  const Tabled R = table(S, data, int(n), !prenorm && t.capcode == 2, !prenorm && (t.normflag & 2) != 0,
+                         !prenorm && (t.normflag != 0 || t.capcode == 2));
+  if (R.bad) return -1;
+  const int L = int(R.words.size());
   ChainTables T;
   T.rec = reinterpret_cast<const uint4*>(t.rec.data());
   T.hot = reinterpret_cast<const uint4*>(t.dfa_hot.data());
@@ -163,7 +142,7 @@ long hs_tokenize(void* h, const uint8_t* data, size_t n, int prenorm, int count_
   T.unk = t.unk;
   T.off = t.charset == 2 ? 2u : 1u;
   T.can_retry = t.delete_token != 0xFFFFFFu;
-  ChainString cs{words.data(), L};
+  ChainString cs{R.words.data(), L};
   ChainLane z;
   chain_reset(z);
   size_t cnt = 0;

@@ -107,7 +107,23 @@ def test_seeded_batches_against_oracle(built, name, group):
     v.close()
 
 
-@pytest.mark.parametrize("group,cta", [("1", 256), ("1", 768), ("1", 1024), ("8", None)])
+@pytest.mark.parametrize("name", ["small_cap2", "c2"])
+def test_capcode_text_that_outgrows_its_slot(built, name):
+    """The table kernel gives every string room for 1.25 x + 48 normalized bytes; alternating case and
+    digits grow 2.5-4 x and must come back through the full-size second run -- also when the string
+    turns out to be non-ASCII only then, and when such strings sit among ordinary ones."""
+    vb = configs.vocab_bytes(name) if name in configs.CONFIGS else gold_vocab(name)
+    v, chk = make_vocab(vb), oracle.OracleVocab(vb, "port")
+    base = bytes(corpus.base_text(77, 1 << 16, 0.3))
+    texts = [b"A1B2C3D4" * 60, b"AbAbAb" * 200, base[:700], b"X" + b"1a" * 300, b"Q.R.S.T." * 90, base[700:1300],
+             "é".encode() + b"A1" * 400, b"Z9" * 30, b"", b"A1B2" * 3000, base[2000:2100], b"I" * 500 + b"b"]
+    for pad in (0, 5):
+        data, off = flat([b"#" * pad] + texts)
+        check_batch(v, chk, data, off, 2)
+    v.close()
+
+
+@pytest.mark.parametrize("group,cta", [("1", None)])
 def test_edge_cases(built, group, cta):
     """Empty / 1-byte / unaligned / non-ASCII / look-ahead at the very end / offsets not starting at 0."""
     vb = gold_vocab("small_cap2")

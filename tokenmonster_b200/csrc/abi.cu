@@ -321,9 +321,31 @@ extern "C" int tmgpu_workspace_create(tmgpu_vocab* v, uint32_t max_strings, uint
   A(&ws->p_nlen, n1);
   A(&ws->p_npad, n1);
   A(&ws->p_toff, n1);
-  A(&ws->p_wbase, n1);
+  A(&ws->p_key, n1);
+  A(&ws->p_key2, n1);
+  A(&ws->p_val, n1);
+  A(&ws->p_order, n1);
+  ws->p_sort_bytes = sort_temp_bytes(uint32_t(n1)) + 256;
+  A(reinterpret_cast<uint8_t**>(&ws->p_sort_temp), ws->p_sort_bytes);
   A(&ws->p_flag, n1);
   A(&ws->p_counters, 4);
+  A(&ws->ov_list, n1);
+  A(&ws->ov_begin, n1);
+  A(&ws->ov_end, n1);
+  A(&ws->ov_ctr, 4);   // non-ASCII {strings, scratch bytes}, overflowed {strings, words}
+  {  // position words of a full batch: 1.25 x + 64 per string under capcode 2, else 1 x + 16
+    const uint64_t words = v->host.capcode == 2 ? max_bytes + max_bytes / 4 + 64ull * max_strings + 4096
+                                                : max_bytes + 16ull * max_strings + 4096;
+    if (!rc) {
+      cudaError_t e = tm_malloc(&ws->p_words, words * 4);
+      if (e != cudaSuccess) {
+        g_err = std::string("cudaMalloc(position words, ") + std::to_string(words * 4) + "): " + cudaGetErrorString(e);
+        rc = TMGPU_E_NOMEM;
+      } else {
+        ws->p_words_cap = words;
+      }
+    }
+  }
   A(&ws->overflow, 4);
   ws->scan_bytes = scan_temp_bytes(uint32_t(n1)) + 256;
   A(reinterpret_cast<uint8_t**>(&ws->scan_temp), ws->scan_bytes);
@@ -331,7 +353,6 @@ extern "C" int tmgpu_workspace_create(tmgpu_vocab* v, uint32_t max_strings, uint
     A(&ws->uni_list, n1);
     A(&ws->uni_begin, n1);
     A(&ws->uni_end, n1);
-    A(&ws->uni_ctr, 2);
   }
   A(&ws->ck_n, n1);
   A(&ws->ck_base, n1);
@@ -379,18 +400,17 @@ extern "C" int tmgpu_workspace_kernel_times(tmgpu_workspace* ws, float* ms_out, 
 }
 
 // Durations (ms) of the stages of the most recent tokenize pipeline run on this workspace:
-// out[0] capcode lengths + scan (incl. the 8-byte host round trip), out[1] capcode text,
-// out[2] position table, out[3] chain.  Stages that did not run report 0.  Returns 4, or 0 when
-// nothing has run yet.  Synchronises on the last event.
+// out[0] prep + slot scan + length sort, out[1] encoder + position table, out[2] chain, out[3] 0.
+// Returns 4, or 0 when nothing has run yet.  Synchronises on the last event.
 extern "C" int tmgpu_workspace_stage_times(tmgpu_workspace* ws, float out[4]) {
   if (!ws || !out || !ws->stage_valid) return 0;
-  if (cudaEventSynchronize(ws->stage_ev[4]) != cudaSuccess) {
+  if (cudaEventSynchronize(ws->stage_ev[3]) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
-  for (int k = 0; k < 4; k++) {
+  out[3] = 0.f;
+  for (int k = 0; k < 3; k++) {
     out[k] = 0.f;
-    if (!ws->stage_enc && k < 2) continue;
     if (cudaEventElapsedTime(&out[k], ws->stage_ev[k], ws->stage_ev[k + 1]) != cudaSuccess) {
       cudaGetLastError();
       out[k] = -1.f;

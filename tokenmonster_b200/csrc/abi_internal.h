@@ -93,21 +93,31 @@ struct tmgpu_workspace {
   size_t scan_bytes = 0;
   // position-table pipeline (pipeline_kernels.cuh): normalized text, one word per position, and
   // per work item: normalized length, slot size, slot offset, first word, verdict
-  uint8_t* p_text = nullptr;
+  uint8_t* p_text = nullptr;             // training scores only
   uint64_t p_text_cap = 0;
   uint32_t* p_words = nullptr;
   uint64_t p_words_cap = 0;              // entries
   uint32_t* p_nlen = nullptr;            // n + 1
   uint32_t* p_npad = nullptr;            // n + 1
   uint64_t* p_toff = nullptr;            // n + 1
-  uint64_t* p_wbase = nullptr;           // n + 1
+  uint32_t* p_key = nullptr;             // n + 1: sort keys / values in, out
+  uint32_t* p_key2 = nullptr;
+  uint32_t* p_val = nullptr;
+  uint32_t* p_order = nullptr;
+  void* p_sort_temp = nullptr;
+  size_t p_sort_bytes = 0;
   uint8_t* p_flag = nullptr;             // n + 1
   uint32_t* p_counters = nullptr;        // 4
+  // strings whose normalized text did not fit the optimistic slot: redone with full-size slots
+  uint32_t* ov_list = nullptr;           // n
+  int64_t* ov_begin = nullptr;           // n
+  int64_t* ov_end = nullptr;             // n
+  unsigned long long* ov_ctr = nullptr;  // {strings, words needed}
+  uint32_t last_overflowed = 0;
   // device normalizer (non-ASCII strings): work list, placement, scratch text
   uint32_t* uni_list = nullptr;          // n
   int64_t* uni_begin = nullptr;          // n
   int64_t* uni_end = nullptr;            // n
-  unsigned long long* uni_ctr = nullptr; // {strings, scratch bytes}
   uint8_t* uni_text = nullptr;
   uint64_t uni_text_cap = 0;
   uint32_t last_unicode = 0;             // strings the normalizer handled in the most recent launch
@@ -146,9 +156,9 @@ struct tmgpu_workspace {
   static constexpr int kEv = 64;
   cudaEvent_t ev0[kEv] = {}, ev1[kEv] = {};
   int ev_head = 0, ev_count = 0;
-  // stage boundaries of the most recent pipeline run: start, lengths+scan, text, table, chain
-  cudaEvent_t stage_ev[5] = {};
-  bool stage_enc = false, stage_valid = false;
+  // stage boundaries of the most recent pipeline run: start, prep + scan + sort, table, chain
+  cudaEvent_t stage_ev[4] = {};
+  bool stage_valid = false;
 };
 
 // Debug aid (TMGPU_POISON=1): every device allocation is filled with 0xA5, so that a kernel that

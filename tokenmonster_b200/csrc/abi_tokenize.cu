@@ -19,51 +19,46 @@ static int grow_device(void** p, uint64_t* cap, uint64_t want, size_t unit, cons
   return TMGPU_OK;
 }
 
-// Runs the stages for the work items of `a` (a.n <= ws->max_strings).  `extent` = bytes spanned by
-// the items' text when it is read in place (capcode 0, or text the device normalizer produced).
-// Capcode-2 text is written to ws->p_text first: lengths, scan, ONE 8-byte D2H for the total (the
-// text and word buffers grow on demand), then the text itself.
-static int run_pipeline(tmgpu_workspace* ws, TokenizeArgs a, bool store, cudaStream_t st, uint64_t extent) {
+// Runs the stages for the work items of `a` (a.n <= ws->max_strings): prep + slot scan + length
+// sort, encoder + position table, chain.  No host round trip.  `need_words` = a bound on the sum
+// of the items' slots (0: a full batch, which the workspace was created for); the stream must be
+// idle when the buffers have to grow (every caller with need_words != 0 has just synchronised).
+static int run_pipeline(tmgpu_workspace* ws, TokenizeArgs a, bool store, cudaStream_t st, uint64_t need_words,
+                        bool slot_full = false) {
   tmgpu_vocab* v = ws->v;
   if (a.n == 0) return TMGPU_OK;
-  const bool enc = !a.prenorm && v->host.capcode == 2;
+  const bool cap = !a.prenorm && v->host.capcode == 2;
+  const bool text = !store && a.scores != nullptr;
+  int rc = grow_device(reinterpret_cast<void**>(&ws->p_words), &ws->p_words_cap, need_words, 4, "position words");
+  if (!rc && text) {
+    if (ws->p_text_cap < ws->p_words_cap) CU(cudaStreamSynchronize(st));
+    rc = grow_device(reinterpret_cast<void**>(&ws->p_text), &ws->p_text_cap, ws->p_words_cap, 1, "normalized text");
+  }
+  if (rc) return rc;
+  a.text = text ? ws->p_text : nullptr;
+  a.words = ws->p_words;
+  a.words_cap = ws->p_words_cap;
   a.nlen = ws->p_nlen;
   a.npad = ws->p_npad;
   a.toff = ws->p_toff;
-  a.wbase = ws->p_wbase;
+  a.sort_key = ws->p_key;
+  a.sort_val = ws->p_val;
+  a.sort_order = ws->p_order;
   a.pflag = ws->p_flag;
   a.pipe_counters = ws->p_counters;
   CU(cudaMemsetAsync(ws->p_counters, 0, 16, st));
-  ws->stage_enc = enc;
   ws->stage_valid = true;
   CU(cudaEventRecord(ws->stage_ev[0], st));
-  if (enc) {
-    CU(launch_encode(a, false, v->sms, st));
-    CU(cudaMemsetAsync(a.npad + a.n, 0, 4, st));
-    CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, a.npad, a.toff, a.n + 1, st));
-    uint64_t total = 0;
-    CU(cudaMemcpyAsync(&total, a.toff + a.n, 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    int rc = grow_device(reinterpret_cast<void**>(&ws->p_text), &ws->p_text_cap, total + 64, 1, "normalized text");
-    if (!rc) rc = grow_device(reinterpret_cast<void**>(&ws->p_words), &ws->p_words_cap, total + 64, 4, "position words");
-    if (rc) return rc;
-    a.text = ws->p_text;
-    a.words = ws->p_words;
-    CU(cudaEventRecord(ws->stage_ev[1], st));
-    CU(launch_encode(a, true, v->sms, st));
-    ws->last_launches += 4;
-  } else {
-    int rc = grow_device(reinterpret_cast<void**>(&ws->p_words), &ws->p_words_cap, extent + 4ull * ws->max_strings + 64, 4,
-                         "position words");
-    if (rc) return rc;
-    a.words = ws->p_words;
-  }
+  CU(launch_prep(a, cap, slot_full, v->sms, st));
+  CU(cudaMemsetAsync(a.npad + a.n, 0, 4, st));
+  CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, a.npad, a.toff, a.n + 1, st));
+  CU(sort_items_by_length(ws->p_sort_temp, ws->p_sort_bytes, ws->p_key, ws->p_key2, ws->p_val, ws->p_order, a.n, st));
+  CU(cudaEventRecord(ws->stage_ev[1], st));
+  CU(launch_table(a, cap, text, v->sms, st));
   CU(cudaEventRecord(ws->stage_ev[2], st));
-  CU(launch_table(a, enc, v->sms, st));
+  CU(launch_chain(a, store, v->sms, st));
   CU(cudaEventRecord(ws->stage_ev[3], st));
-  CU(launch_chain(a, enc, store, v->sms, st));
-  CU(cudaEventRecord(ws->stage_ev[4], st));
-  ws->last_launches += 2;
+  ws->last_launches += 8;   // prep, scan x2, sort (histogram + onesweep passes ~ 3), table, chain
   return TMGPU_OK;
 }
 
@@ -203,26 +198,54 @@ static int chunk_run(tmgpu_workspace* ws, const TokenizeArgs& first, uint32_t to
     b.raw_ends = first.ends;
     b.skip = nullptr;
     b.watermark = nullptr;
-    int rc = run_pipeline(ws, b, mode == 0, st, ws->max_bytes);
+    int rc = run_pipeline(ws, b, mode == 0, st, 0);
     if (rc) return rc;
   }
   return TMGPU_OK;
 }
 
-// Strings the tokenize kernel gave up on (first byte >= 0x80 under a normalizing vocabulary) are
-// normalized by the device normalizer and tokenized by a second launch that reads the normalized
-// text verbatim.  One small D2H tells the host whether there are any; ASCII batches pay only that.
-static int unicode_pass(tmgpu_workspace* ws, const TokenizeArgs& first, bool store, cudaStream_t st) {
+// After the main launch: strings the table kernel refused at a byte >= 0x80 (status 13) are
+// normalized by the device normalizer and run through the pipeline again, reading the normalized
+// text verbatim; strings whose capcode text outgrew the optimistic slot (status 14) are run again
+// with full-size slots.  One 32-byte D2H tells the host whether there are any of either; plain
+// batches pay only that.
+static int side_passes(tmgpu_workspace* ws, const TokenizeArgs& first, bool store, cudaStream_t st) {
   tmgpu_vocab* v = ws->v;
   ws->last_unicode = 0;
-  if (!v->unicode || first.n == 0 || v->host.max_len == 0) return TMGPU_OK;
-  CU(cudaMemsetAsync(ws->uni_ctr, 0, 16, st));
-  CU(launch_select_refused(first.status, first.off, first.ends, first.n, ws->uni_list, ws->uni_begin, ws->uni_ctr,
-                           v->sms, st));
-  unsigned long long h[2] = {0, 0};
-  CU(cudaMemcpyAsync(h, ws->uni_ctr, 16, cudaMemcpyDeviceToHost, st));
+  ws->last_overflowed = 0;
+  const bool need_uni = v->unicode, need_ov = v->host.capcode == 2;
+  if ((!need_uni && !need_ov) || first.n == 0 || v->host.max_len == 0) return TMGPU_OK;
+  unsigned long long* uni_ctr = ws->ov_ctr;        // {strings, scratch bytes}
+  unsigned long long* ov_ctr = ws->ov_ctr + 2;     // {strings, words}
+  CU(cudaMemsetAsync(ws->ov_ctr, 0, 32, st));
+  if (need_uni)
+    CU(launch_select_refused(first.status, first.off, first.ends, first.n, ws->uni_list, ws->uni_begin, uni_ctr, v->sms, st));
+  if (need_ov)
+    CU(launch_select_overflowed(first.status, first.off, first.ends, first.n, ws->ov_list, ws->ov_begin, ws->ov_end, ov_ctr,
+                                v->sms, st));
+  unsigned long long h[4] = {0, 0, 0, 0};
+  CU(cudaMemcpyAsync(h, ws->ov_ctr, 32, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  ws->last_launches++;
+  ws->last_launches += (need_uni ? 1 : 0) + (need_ov ? 1 : 0);
+  if (h[2]) {   // full-size slots for the strings that outgrew theirs
+    TokenizeArgs b = first;
+    b.off = ws->ov_begin;
+    b.ends = ws->ov_end;
+    b.n = uint32_t(h[2]);
+    b.list = ws->ov_list;
+    b.raw_off = first.off;
+    b.raw_ends = first.ends;
+    b.skip = nullptr;
+    int rc = run_pipeline(ws, b, store, st, h[3] + 64, true);
+    if (rc) return rc;
+    ws->last_overflowed = uint32_t(h[2]);
+    if (need_uni) {   // a redone string may turn out to hold a byte >= 0x80: list the refused ones again
+      CU(cudaMemsetAsync(uni_ctr, 0, 16, st));
+      CU(launch_select_refused(first.status, first.off, first.ends, first.n, ws->uni_list, ws->uni_begin, uni_ctr, v->sms, st));
+      CU(cudaMemcpyAsync(h, uni_ctr, 16, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+    }
+  }
   if (h[0] == 0) return TMGPU_OK;
   if (ws->uni_text_cap < h[1] + 64) {
     if (ws->uni_text) cudaFree(ws->uni_text);
@@ -241,7 +264,7 @@ static int unicode_pass(tmgpu_workspace* ws, const TokenizeArgs& first, bool sto
   na.off = first.off;
   na.ends = first.ends;
   na.list = ws->uni_list;
-  na.n_list = reinterpret_cast<const uint32_t*>(ws->uni_ctr);
+  na.n_list = reinterpret_cast<const uint32_t*>(uni_ctr);
   na.scratch = ws->uni_text;
   na.n_begin = ws->uni_begin;
   na.n_end = ws->uni_end;
@@ -267,7 +290,7 @@ static int unicode_pass(tmgpu_workspace* ws, const TokenizeArgs& first, bool sto
   b.skip = nullptr;
   b.watermark = nullptr;
   {
-    int rc = run_pipeline(ws, b, store, st, h[1] + 64);
+    int rc = run_pipeline(ws, b, store, st, h[1] + 16ull * h[0] + 64);
     if (rc) return rc;
   }
   if (trace) {
@@ -349,14 +372,14 @@ int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t
       b.need = ws->need + c.s0;
       b.missing = ws->missing + c.s0;
       b.status = ws->status + c.s0;
-      int rc = run_pipeline(ws, b, mode == 0, st, ws->max_bytes);
+      int rc = run_pipeline(ws, b, mode == 0, st, 0);
       if (rc) return rc;
     }
   } else if (n > 0) {
     const int e = ws->ev_head;
     CU(cudaEventRecord(ws->ev0[e], st));
     {
-      int rc = run_pipeline(ws, a, mode == 0, st, ws->max_bytes);
+      int rc = run_pipeline(ws, a, mode == 0, st, 0);
       if (rc) return rc;
     }
     CU(cudaEventRecord(ws->ev1[e], st));
@@ -369,7 +392,7 @@ int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t
     a.skip = nullptr;
   }
   {
-    int rc = unicode_pass(ws, a, mode == 0, st);
+    int rc = side_passes(ws, a, mode == 0, st);
     if (rc) return rc;
   }
   if (mode == 0) {

@@ -16,6 +16,7 @@
 #include "kernels.h"
 
 #include <cstdlib>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "pipeline_kernels.cuh"
@@ -371,23 +372,47 @@ static int pipe_grid(K kernel, uint32_t n, int sms) {
   return int(want < full ? (want < 1 ? 1 : want) : full);
 }
 
-cudaError_t launch_encode(const TokenizeArgs& a, bool write, int sms, cudaStream_t st) {
-  if (write) encode_kernel<true><<<pipe_grid(encode_kernel<true>, a.n, sms), kPipeBlock, 0, st>>>(a);
-  else encode_kernel<false><<<pipe_grid(encode_kernel<false>, a.n, sms), kPipeBlock, 0, st>>>(a);
+cudaError_t launch_prep(const TokenizeArgs& a, bool cap, bool slot_full, int sms, cudaStream_t st) {
+  long long want = (static_cast<long long>(a.n) + 255) / 256;
+  int grid = int(want < sms * 8ll ? (want < 1 ? 1 : want) : sms * 8ll);
+  prep_kernel<<<grid, 256, 0, st>>>(a, cap ? 1 : 0, slot_full ? 1 : 0);
   return cudaGetLastError();
 }
 
-cudaError_t launch_table(const TokenizeArgs& a, bool enc, int sms, cudaStream_t st) {
-  if (enc) table_kernel<true><<<pipe_grid(table_kernel<true>, a.n, sms), kPipeBlock, 0, st>>>(a);
-  else table_kernel<false><<<pipe_grid(table_kernel<false>, a.n, sms), kPipeBlock, 0, st>>>(a);
+size_t sort_temp_bytes(uint32_t n_items) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                            (const uint32_t*)nullptr, (uint32_t*)nullptr, int(n_items), 0, 16);
+  return bytes;
+}
+
+// items by descending length key (16 bits): long strings first, equal lengths next to each other
+cudaError_t sort_items_by_length(void* temp, size_t temp_bytes, const uint32_t* key_in, uint32_t* key_out,
+                                 const uint32_t* val_in, uint32_t* val_out, uint32_t n_items, cudaStream_t st) {
+  return cub::DeviceRadixSort::SortPairsDescending(temp, temp_bytes, key_in, key_out, val_in, val_out, int(n_items), 0, 16,
+                                                   st);
+}
+
+cudaError_t launch_table(const TokenizeArgs& a, bool cap, bool text, int sms, cudaStream_t st) {
+  const uint32_t groups = (a.n + 31) / 32 * 32;
+#define TM_TABLE(C_, T_) table_kernel<C_, T_><<<pipe_grid(table_kernel<C_, T_>, groups, sms), kPipeBlock, 0, st>>>(a)
+  if (cap) { if (text) TM_TABLE(true, true); else TM_TABLE(true, false); }
+  else { if (text) TM_TABLE(false, true); else TM_TABLE(false, false); }
+#undef TM_TABLE
   return cudaGetLastError();
 }
 
-cudaError_t launch_chain(const TokenizeArgs& a, bool enc, bool store, int sms, cudaStream_t st) {
-#define TM_CHAIN(S_, E_) chain_kernel<S_, E_><<<pipe_grid(chain_kernel<S_, E_>, a.n, sms), kPipeBlock, 0, st>>>(a)
-  if (store) { if (enc) TM_CHAIN(true, true); else TM_CHAIN(true, false); }
-  else { if (enc) TM_CHAIN(false, true); else TM_CHAIN(false, false); }
-#undef TM_CHAIN
+cudaError_t launch_select_overflowed(const uint8_t* status, const int64_t* off, const int64_t* ends, uint32_t n,
+                                     uint32_t* list, int64_t* o_begin, int64_t* o_end, unsigned long long* ctr, int sms,
+                                     cudaStream_t st) {
+  select_overflowed_kernel<<<sms * 4, 256, 0, st>>>(status, off, ends, n, list, o_begin, o_end, ctr);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chain(const TokenizeArgs& a, bool store, int sms, cudaStream_t st) {
+  const uint32_t groups = (a.n + 31) / 32 * 32;
+  if (store) chain_kernel<true><<<pipe_grid(chain_kernel<true>, groups, sms), kPipeBlock, 0, st>>>(a);
+  else chain_kernel<false><<<pipe_grid(chain_kernel<false>, groups, sms), kPipeBlock, 0, st>>>(a);
   return cudaGetLastError();
 }
 

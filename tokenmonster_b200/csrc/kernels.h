@@ -59,14 +59,17 @@ struct TokenizeArgs {
   uint32_t c_cap, c_ov;      // log capacity per chunk; how far a chunk runs past the next one's start
   const unsigned long long* watermark;  // (chunk kernel only) unused
   // position-table pipeline scratch, per launch, indexed by work item
-  uint8_t* text;             // normalized text of capcode-2 vocabularies: 16-byte aligned slots at toff[item]
-  uint32_t* words;           // one word per normalized position (pipeline_core.h)
+  uint8_t* text;             // training scores only: the normalized bytes, laid out like `words`
+  uint32_t* words;           // one word per normalized position (pipeline_core.h), right aligned in the slot
+  uint64_t words_cap;        // entries
   uint32_t* nlen;            // normalized length
-  uint32_t* npad;            // n + 1: slot size (0 for refused / skipped items)
-  uint64_t* toff;            // n + 1: exclusive scan of npad
-  uint64_t* wbase;           // first word of the item when the text is read in place
-  uint8_t* pflag;            // 0 run, 1 refused (status 13), 2 nothing to do
-  uint32_t* pipe_counters;   // 4 zeroed work counters: encode lengths, encode, table, chain
+  uint32_t* npad;            // n + 1: slot size in words (0 for refused / skipped items)
+  uint64_t* toff;            // n + 1: exclusive scan of npad; the slot of item i ends at toff[i + 1]
+  uint32_t* sort_key;        // length / 8 (0: nothing to do)
+  uint32_t* sort_val;        // item
+  const uint32_t* sort_order;  // items by descending length: a warp works on 32 strings of equal length
+  uint8_t* pflag;            // 0 run, 1 refused (status 13), 2 nothing to do, 3 slot too small (status 14)
+  uint32_t* pipe_counters;   // 4 zeroed work counters (2: table, 3: chain)
 };
 
 size_t scan_temp_bytes(uint32_t n_items);
@@ -74,9 +77,15 @@ cudaError_t exclusive_scan_u32_to_u64(void* temp, size_t temp_bytes, const uint3
                                       uint32_t n_items, cudaStream_t st);
 // the position-table pipeline (pipeline_kernels.cuh); enc = the vocabulary uses capcode 2 and the
 // text is raw (not pre-normalized); store = ids (K1) vs count only (K3)
-cudaError_t launch_encode(const TokenizeArgs& a, bool write, int sms, cudaStream_t st);
-cudaError_t launch_table(const TokenizeArgs& a, bool enc, int sms, cudaStream_t st);
-cudaError_t launch_chain(const TokenizeArgs& a, bool enc, bool store, int sms, cudaStream_t st);
+cudaError_t launch_prep(const TokenizeArgs& a, bool cap, bool slot_full, int sms, cudaStream_t st);
+size_t sort_temp_bytes(uint32_t n_items);
+cudaError_t sort_items_by_length(void* temp, size_t temp_bytes, const uint32_t* key_in, uint32_t* key_out,
+                                 const uint32_t* val_in, uint32_t* val_out, uint32_t n_items, cudaStream_t st);
+cudaError_t launch_table(const TokenizeArgs& a, bool cap, bool text, int sms, cudaStream_t st);
+cudaError_t launch_select_overflowed(const uint8_t* status, const int64_t* off, const int64_t* ends, uint32_t n,
+                                     uint32_t* list, int64_t* o_begin, int64_t* o_end, unsigned long long* ctr, int sms,
+                                     cudaStream_t st);
+cudaError_t launch_chain(const TokenizeArgs& a, bool store, int sms, cudaStream_t st);
 cudaError_t launch_pack(const uint32_t* slab, const int64_t* off, uint32_t slab_pad, const uint64_t* slab_off,
                         const uint32_t* counts, const uint64_t* tok_off, uint8_t* out, uint32_t n, int enc,
                         int sms, cudaStream_t st);

@@ -118,6 +118,88 @@ TM_HD bool cap_fast4(CapState& e, uint32_t w4, uint32_t c5) {
 }
 
 // ------------------------------------------------------------------------------------------
+// stage 1, right to left: the same encoder driven from the END of the string, one raw character
+// per call.  This is what the table kernel runs (the automaton consumes the normalized text back
+// to front, so producing it back to front lets both live in one loop and the normalized text never
+// exists in memory).  Everything the encoder knows about a character is local:
+//   * the two characters to its LEFT are read directly (c1, c2);
+//   * "inside a capitalised run" = the nearest character to the left that is not a digit or an
+//     apostrophe is a capital: it is the left neighbour itself unless that is a digit / apostrophe,
+//     in which case one look-back over the run answers for every character of the run;
+//   * "the run is mixed case" = the nearest lower-case-or-other character to the RIGHT is
+//     lower-case, which a right-to-left pass carries along (nlo);
+//   * the class of the character to the right (clr) decides whether a space is replaced by a marker.
+// ------------------------------------------------------------------------------------------
+struct RevCap {
+  uint32_t clr;          // class of the character to the right
+  uint32_t nlo;          // class of the nearest lower-case-or-other character to the right (other if none)
+  bool has_right;        // there is a character to the right
+  bool iw_valid, iw;     // cached answer for the current run of digits / apostrophes
+};
+
+TM_HD void revcap_reset(RevCap& e) {
+  e.clr = PC_O;
+  e.nlo = PC_O;
+  e.has_right = false;
+  e.iw_valid = false;
+  e.iw = false;
+}
+
+// Encodes raw character c0 at index k; c1 / c2 = the characters at k-1 / k-2 (ignored where they do
+// not exist); raw_at(j) reads character j (rare deeper look-back).  Returns the number of bytes
+// (0..4) placed in *out in FORWARD order, little endian -- the caller feeds them to the automaton
+// last byte first.  Same output as cap_step() run left to right (tests/test_host_sim.py).
+template <class RawAt>
+TM_HD uint32_t revcap_step(RevCap& e, const uint8_t* cls, uint32_t c0, uint32_t c1, uint32_t c2, int k, RawAt raw_at,
+                           uint32_t* out) {
+  const uint32_t cl = cls[c0 & 127u];
+  const uint32_t cl1 = (k >= 1) ? uint32_t(cls[c1 & 127u]) : uint32_t(PC_O);
+  const uint32_t cl2 = (k >= 2) ? uint32_t(cls[c2 & 127u]) : uint32_t(PC_O);
+  const bool sp1 = (k >= 1) && (c1 == ' ');
+  bool in_word;
+  if (cl1 != PC_N && cl1 != PC_A) {        // also k == 0: no left neighbour counts as "other"
+    in_word = (cl1 == PC_U);
+    e.iw_valid = false;
+  } else {
+    if (!e.iw_valid) {
+      uint32_t x = cl2;
+      int j = k - 2;
+      while ((x == PC_N || x == PC_A) && j > 0) {
+        j--;
+        x = cls[raw_at(j) & 127u];
+      }
+      e.iw = (k >= 2) && (x == PC_U);
+      e.iw_valid = true;
+    }
+    in_word = e.iw;
+  }
+  const bool mixed = (e.nlo == PC_L);
+  const bool letter1 = (cl1 == PC_U) || (cl1 == PC_L);
+  const bool glue1 = letter1 || (cl1 == PC_A);
+  const bool start = (cl == PC_U) && !in_word;
+  const bool joined_l = in_word ? glue1 : (sp1 || letter1 || (((cl2 == PC_U) || (cl2 == PC_L)) && cl1 == PC_A));
+  const bool joined_n = in_word ? (cl1 == PC_N) : (sp1 || cl1 == PC_N);
+  const bool k_dspace = (cl == PC_L && !joined_l) || (cl == PC_N && !joined_n) ||
+                        (cl == PC_U && in_word && !mixed && !glue1);
+  const bool k_dcs = (cl == PC_U) && in_word && mixed;
+  const uint32_t marker = mixed ? 'C' : 'W';
+  uint32_t pre = 0, np = 0;
+  if (k_dspace) { pre = 'D' | (' ' << 8); np = 2; }
+  if (k_dcs) { pre = 'D' | ('C' << 8) | (' ' << 16); np = 3; }
+  if (start) {
+    pre = sp1 ? (marker | (' ' << 8)) : ('D' | (marker << 8) | (' ' << 16));
+    np = sp1 ? 2 : 3;
+  }
+  const bool eaten = (c0 == ' ') && e.has_right && (e.clr == PC_U);
+  const uint32_t ch = (cl == PC_U) ? (c0 | 0x20u) : c0;
+  *out = eaten ? pre : (pre | (ch << (8 * np)));
+  e.clr = cl;
+  e.has_right = true;
+  if (cl == PC_L || cl == PC_O) e.nlo = cl;
+  return np + (eaten ? 0u : 1u);
+}
+
+// ------------------------------------------------------------------------------------------
 // stage 2: the position word
 // ------------------------------------------------------------------------------------------
 TM_HD uint32_t pw_state(uint32_t w) { return w & kDfaStateMask; }

@@ -1,24 +1,28 @@
 // pipeline_kernels.cuh -- K1/K3 of round 2: the position-table pipeline (pipeline_core.h has the
 // per-string logic and the reference citations; vocab_tables.h the automaton).
 //
-//   encode_kernel<false>   capcode-2 vocabularies: normalized length of every string   } one lane
-//   (scan)                 16-byte aligned text slots                                   } per
-//   encode_kernel<true>    normalized text -> HBM                                       } string,
-//   table_kernel           reversed-key automaton, right to left: one word / position   } lanes pull
-//   chain_kernel<STORE>    the ungreedy loop over the position words -> ids / counts    } strings
+//   prep_kernel            per string: anything to do? slot size, sort key (length / 8)
+//   (scan, radix sort)     slot offsets; strings by descending length
+//   table_kernel           capcode encoder + reversed-key automaton in ONE right-to-left loop:
+//                          one 32-bit word per normalized position goes to HBM, the normalized
+//                          text itself never exists in memory
+//   chain_kernel<STORE>    the ungreedy loop over the position words -> ids / counts
 //
-// Why three passes over HBM instead of one fused kernel: the round-1 kernel kept everything in
+// Why passes over HBM instead of one fused kernel: the round-1 kernel kept everything in
 // shared-memory rings and paid for it with ~12 dependent trie probes per emitted id under SIMT
 // divergence (165 warp instructions per id, 13 of 32 lanes active, profiles/r01_*).  Here the
 // automaton needs ONE table probe per byte whatever the token lengths, the chain stage has no
 // inner loop at all, and every lane of a warp does the same thing in every iteration; the price is
-// ~10 bytes of HBM traffic per input byte, on a GPU whose HBM was 99 % idle.
+// ~9 bytes of HBM traffic per input byte, on a GPU whose HBM was 99 % idle.
 //
-// All three kernels are persistent: a lane takes the next string from a global counter the moment
-// its own string ends, so ragged batches balance themselves.  Per-lane loads are 16-byte vectors
-// wherever the data is a stream (raw text, normalized text, position words are stored 16 bytes at
-// a time): with one string per lane every load instruction touches 32 different lines, and the
-// L1 pipeline charges per line, so the number of load INSTRUCTIONS per byte is what matters.
+// One lane per string, 32 strings of EQUAL LENGTH per warp (the sort): the first version of this
+// pipeline let every lane pull its next string the moment its own ended, and rare per-lane events
+// (a 16-byte refill, a store, the fetch of a new string) then happen at a different iteration in
+// every lane, so the warp executes their code almost every iteration for one or two lanes (ncu:
+// 13-20 of 32 lanes active, profiles/r02_v1_*).  With equal lengths the lanes stay in phase: they
+// start together, refill together and end together.  Per-lane loads are 16-byte vectors
+// wherever the data is a stream: with one string per lane every load instruction touches 32
+// different lines, and the L1 pipeline charges per line.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -108,275 +112,226 @@ __device__ __forceinline__ uint32_t pipe_word_of(const uint4& q, int wi) {
 }
 
 // ------------------------------------------------------------------------------------------
-// stage 1: capcode level 2 (WRITE = false: lengths only)
+// prep: one thread per work item -- is there anything to do, how many words may it need, and a
+// sort key (length / 8) so that the 32 strings a warp works on together have the same length
 // ------------------------------------------------------------------------------------------
-template <bool WRITE>
-__global__ void __launch_bounds__(kPipeBlock) encode_kernel(const TokenizeArgs A) {
-  constexpr unsigned FULL = 0xFFFFFFFFu;
-  __shared__ uint8_t s_cls[128];
-  if (threadIdx.x < 128) s_cls[threadIdx.x] = uint8_t(pc_class(threadIdx.x));
-  __syncthreads();
-  const bool to_lower = (A.v.normflag & 2) != 0;
-  uint32_t* counter = A.pipe_counters + (WRITE ? 1 : 0);
+__global__ void __launch_bounds__(256) prep_kernel(const TokenizeArgs A, int cap_mode, int slot_full) {
+  for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < A.n; item += gridDim.x * blockDim.x) {
+    uint32_t s = 0;
+    int64_t o0 = 0;
+    int slen = 0;
+    const bool ok = pipe_fetch(A, item, &s, &o0, &slen);
+    uint64_t slot = 0;
+    if (ok) {
+      const uint64_t l = uint64_t(slen);
+      // capcode 2 grows ASCII text by a few percent (a capital costs up to 3 extra bytes): room for
+      // 1.25 x + 48, the rare string that needs more is redone with 4 x + 32 (slot_full)
+      slot = !cap_mode ? l : (slot_full ? 4 * l + 32 : l + (l >> 2) + 48);
+      slot = (slot + 15) & ~uint64_t(15);
+      if (slot > 0xFFFFFFF0ull) slot = 0xFFFFFFF0ull;
+    }
+    A.npad[item] = uint32_t(slot);
+    A.sort_key[item] = ok ? min(uint32_t(slen >> 3) + 1u, 0xFFFFu) : 0u;
+    A.sort_val[item] = item;
+    A.pflag[item] = ok ? 0 : 2;
+  }
+}
 
-  bool running = false, no_more = false, bad = false;
-  uint32_t item = 0, s = 0, ow = 0;
-  int galign = 0, total_c = 0, rc = 0, qbase = -16, avail = 0, outpos = 0;
-  uint64_t win = 0;
-  uint4 q = make_uint4(0, 0, 0, 0);
-  const uint8_t* ga = nullptr;
-  uint32_t* dst = nullptr;
-  CapState e;
-  cap_reset(e);
-
-  for (;;) {
-    if (!running && !no_more) {
-      item = atomicAdd(counter, 1u);
-      if (item >= A.n) {
-        no_more = true;
-      } else {
-        int64_t o0 = 0;
-        int slen = 0;
-        const bool ok = pipe_fetch(A, item, &s, &o0, &slen);
-        if (!ok) {
-          if (!WRITE) { A.npad[item] = 0; A.nlen[item] = 0; A.pflag[item] = 2; }
-        } else if (WRITE && A.pflag[item] != 0) {
-          // refused by the length pass
-        } else {
-          const uint8_t* g0 = A.data + o0;
-          galign = int(reinterpret_cast<uintptr_t>(g0) & 15);
-          ga = g0 - galign;
-          total_c = galign + slen;
-          rc = galign;
-          qbase = -16;
-          win = 0;
-          avail = 0;
-          outpos = 0;
-          ow = 0;
-          bad = false;
-          cap_reset(e);
-          if (WRITE) dst = reinterpret_cast<uint32_t*>(A.text + A.toff[item]);
-          running = true;
-        }
-      }
-    }
-    if (__all_sync(FULL, !running)) break;
-    if (!running) continue;
-    if (rc >= total_c || bad) {   // the string is done
-      if (WRITE) {
-        if (outpos & 3) dst[outpos >> 2] = ow;
-      } else {
-        A.nlen[item] = bad ? 0u : uint32_t(outpos);
-        A.npad[item] = bad ? 0u : (uint32_t(outpos) + 16u) & ~15u;
-        A.pflag[item] = bad ? 1 : 0;
-        if (bad) { A.counts[s] = 0; A.need[s] = 0; A.missing[s] = 0; A.status[s] = 13; }
-      }
-      running = false;
-      continue;
-    }
-    // keep >= 5 raw bytes in the window: 4 for the fast path + 1 to peek at the next character
-    while (avail < 5 && rc + avail < total_c) {
-      const int nwc = rc + avail;            // first coordinate not yet in the window
-      const int wc = nwc & ~3;
-      const int cb = wc & ~15;
-      if (cb != qbase) {
-        q = pipe_load16(ga, cb, total_c);
-        qbase = cb;
-        uint32_t m0 = q.x, m1 = q.y, m2 = q.z, m3 = q.w;
-        if (cb == 0 && galign) {             // bytes before the string start are foreign
-          uint32_t t[4] = {m0, m1, m2, m3};
-          for (int k = 0; k < galign; k++) t[k >> 2] &= ~(0xFFu << (8 * (k & 3)));
-          m0 = t[0]; m1 = t[1]; m2 = t[2]; m3 = t[3];
-        }
-        if ((m0 | m1 | m2 | m3) & 0x80808080u) bad = true;
-        if (to_lower) { q.x = pipe_lower4(q.x); q.y = pipe_lower4(q.y); q.z = pipe_lower4(q.z); q.w = pipe_lower4(q.w); }
-      }
-      const uint32_t wq = pipe_word_of(q, (wc >> 2) & 3);
-      const int skip = nwc - wc;             // non-zero only for the first, unaligned word
-      win |= uint64_t(wq >> (8 * skip)) << (8 * avail);
-      avail += 4 - skip;
-    }
-    if (bad) continue;
-    uint32_t bytes = 0, total = 0;
-    bool fast = false;
-    if (rc + 4 <= total_c) {
-      const uint32_t c5 = (rc + 4 < total_c) ? (uint32_t(win >> 32) & 0xFFu) : 0u;
-      fast = cap_fast4(e, uint32_t(win), c5);
-    }
-    if (fast) {
-      bytes = uint32_t(win);
-      total = 4;
-      win >>= 32;
-      avail -= 4;
-      rc += 4;
-    } else {
-      const uint32_t c = uint32_t(win) & 0xFFu;
-      const uint32_t cn = uint32_t(win >> 8) & 0xFFu;
-      const int k = rc - galign, n = total_c - galign;
-      const uint8_t* g0 = ga + galign;
-      total = cap_step(e, s_cls, c, cn, k, n,
-                       [&](int j) -> uint32_t {
-                         uint32_t x = g0[j];
-                         if (to_lower && x - 'A' < 26u) x |= 0x20u;
-                         return x;
-                       },
-                       &bytes);
-      win >>= 8;
-      avail--;
-      rc++;
-    }
-    // append `total` bytes through the partial word ow
-    const uint32_t sh = (uint32_t(outpos) & 3u) * 8u;
-    const uint64_t acc = uint64_t(ow) | (uint64_t(bytes) << sh);
-    const int nf = outpos + int(total);
-    if ((nf >> 2) != (outpos >> 2)) {
-      if (WRITE) dst[outpos >> 2] = uint32_t(acc);
-      ow = uint32_t(acc >> 32);
-    } else {
-      ow = uint32_t(acc);
-    }
-    outpos = nf;
+// strings whose text did not fit the optimistic slot (status 14): listed with their extents and the
+// words a full-size slot needs, for the second run
+__global__ void __launch_bounds__(256) select_overflowed_kernel(const uint8_t* __restrict__ status,
+                                                                const int64_t* __restrict__ off,
+                                                                const int64_t* __restrict__ ends, uint32_t n,
+                                                                uint32_t* __restrict__ list, int64_t* __restrict__ o_begin,
+                                                                int64_t* __restrict__ o_end,
+                                                                unsigned long long* __restrict__ ctr) {
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    if (status[s] != 14) continue;
+    const int64_t b0 = off[s], b1 = ends ? ends[s] : off[s + 1];
+    const unsigned long long k = atomicAdd(&ctr[0], 1ull);
+    atomicAdd(&ctr[1], (4ull * static_cast<unsigned long long>(b1 - b0) + 32ull + 15ull) & ~15ull);
+    list[k] = s;
+    o_begin[k] = b0;
+    o_end[k] = b1;
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// stage 2: position words.  ENC: the text is what encode_kernel wrote (slot toff[item], length
-// nlen[item]); otherwise the string itself (capcode 0, or text the device normalizer produced),
-// checked for non-ASCII bytes / lower-cased on the fly when the vocabulary asks for it.
+// stages 1 + 2: capcode encoder and reversed-key automaton in one right-to-left loop.
+// A warp takes 32 strings of (nearly) equal length; every iteration each lane consumes exactly one
+// normalized byte: if its byte queue is empty it first encodes the next raw character (0..4 bytes),
+// then the automaton takes one byte and the position word goes out (16 bytes at a time, right
+// aligned in the string's slot, so the slot's start need not be known in advance).
+// CAP: capcode level 2; otherwise the text is read as it is (capcode 0, or text the device
+// normalizer produced), lower-cased / checked for non-ASCII bytes when the vocabulary asks for it.
+// TEXT: also keep the normalized bytes (the training scores need the byte no token covers).
 // ------------------------------------------------------------------------------------------
-template <bool ENC>
+template <bool CAP, bool TEXT>
 __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A) {
   constexpr unsigned FULL = 0xFFFFFFFFu;
   __shared__ __align__(128) uint8_t s_img[kPipeImageBytes];
   __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint8_t s_cls[128];
   pipe_stage_tma(s_img, A.v.pipe_image, &s_bar);
+  if (threadIdx.x < 128) s_cls[threadIdx.x] = uint8_t(pc_class(threadIdx.x));
   __syncthreads();
   const uint32_t* s_d1 = reinterpret_cast<const uint32_t*>(s_img);
   const uint8_t* s_code = s_img + 1024;
   const DfaDev D = A.v.dfa;
   const uint32_t voff = uint32_t(A.v.off);
-  const bool want_ascii = !ENC && !A.prenorm && (A.v.normflag != 0);
-  const bool to_lower = !ENC && !A.prenorm && (A.v.normflag & 2) != 0;
+  const bool want_ascii = CAP || (!A.prenorm && (A.v.normflag != 0));
+  const bool to_lower = !A.prenorm && (A.v.normflag & 2) != 0;
   const uint32_t code0 = s_code[0];
+  const int lane = threadIdx.x & 31;
   uint32_t* counter = A.pipe_counters + 2;
-  const int64_t origin = (A.list && A.prenorm) ? 0 : (A.list ? A.raw_off[0] : A.off[0]);
-
-  bool running = false, no_more = false, bad = false;
-  uint32_t item = 0, s = 0, packed = 0, prev = 0, nbuf = 0;
-  int p = -1, L = 0, ta = 0, qbase = -16, total_c = 0;
-  const uint8_t* ga = nullptr;
-  uint32_t* wdst = nullptr;
-  uint4 q = make_uint4(0, 0, 0, 0), wbuf = make_uint4(0, 0, 0, 0);
-  ClassTrail tr;
-  trail_reset(tr, code0);
 
   for (;;) {
-    if (!running && !no_more) {
-      item = atomicAdd(counter, 1u);
-      if (item >= A.n) {
-        no_more = true;
-      } else {
+    uint32_t g = 0;
+    if (lane == 0) g = atomicAdd(counter, 1u);
+    g = __shfl_sync(FULL, g, 0);
+    if (uint64_t(g) * 32u >= A.n) break;
+    const uint32_t slot_i = g * 32u + uint32_t(lane);
+    // ---- this lane's string ---------------------------------------------------------------
+    bool active = false, bad = false, over = false;
+    uint32_t item = 0, s = 0, slot = 0;
+    int k = -1, galign = 0, total_c = 0, fbase = -16;
+    const uint8_t* ga = nullptr;
+    uint32_t* wend = nullptr;
+    uint8_t* tend = nullptr;
+    uint4 fb = make_uint4(0, 0, 0, 0);
+    if (slot_i < A.n) {
+      item = A.sort_order[slot_i];
+      if (A.pflag[item] == 0) {
         int64_t o0 = 0;
         int slen = 0;
-        bool ok = pipe_fetch(A, item, &s, &o0, &slen);
-        if (ENC) {
-          ok = ok && A.pflag[item] == 0;
-        } else if (!ok) {
-          A.pflag[item] = 2;
+        pipe_fetch(A, item, &s, &o0, &slen);
+        const uint8_t* g0 = A.data + o0;
+        galign = int(reinterpret_cast<uintptr_t>(g0) & 15);
+        ga = g0 - galign;
+        total_c = galign + slen;
+        k = slen - 1;
+        const uint64_t e = A.toff[item + 1];
+        slot = uint32_t(e - A.toff[item]);
+        wend = A.words + e;
+        if (TEXT) tend = A.text + e;
+        active = true;
+        if (e > A.words_cap) {   // the batch is larger than the workspace was created for: refuse
+          A.nlen[item] = 0;
+          A.pflag[item] = 1;
+          A.counts[s] = 0; A.need[s] = 0; A.missing[s] = 0; A.status[s] = 13;
+          active = false;
         }
-        if (ok) {
-          const uint8_t* g0;
-          if (ENC) {
-            g0 = A.text + A.toff[item];
-            L = int(A.nlen[item]);
-            wdst = A.words + A.toff[item];
-          } else {
-            g0 = A.data + o0;
-            L = slen;
-            // words of string s start at a multiple of 4: (offset rounded down) + 4 per string in
-            // front for contiguous strings, (offset rounded up) inside the string's own slack for
-            // the normalizer's scratch slots
-            const uint64_t wb = (A.list && A.prenorm) ? uint64_t((o0 - origin + 3) & ~int64_t(3))
-                                                      : uint64_t((o0 - origin) & ~int64_t(3)) + 4ull * (A.list ? s : item);
-            wdst = A.words + wb;
-            A.wbase[item] = wb;
+      }
+    }
+    // raw character at aligned coordinate x (16-byte blocks, loaded as the cursor walks left)
+    auto fetch = [&](int x) -> uint32_t {
+      if ((x & ~15) != fbase) {
+        fbase = x & ~15;
+        fb = pipe_load16(ga, fbase, total_c);
+        if (want_ascii) {
+          uint32_t m0 = fb.x, m1 = fb.y, m2 = fb.z, m3 = fb.w;
+          if (fbase == 0 && galign) {            // bytes before the string start are foreign
+            uint32_t t[4] = {m0, m1, m2, m3};
+            for (int j = 0; j < galign; j++) t[j >> 2] &= ~(0xFFu << (8 * (j & 3)));
+            m0 = t[0]; m1 = t[1]; m2 = t[2]; m3 = t[3];
           }
-          ta = int(reinterpret_cast<uintptr_t>(g0) & 15);
-          ga = g0 - ta;
-          total_c = ta + L;
-          p = L - 1;
-          qbase = -16;
-          bad = false;
-          nbuf = 0;
-          trail_reset(tr, code0);
-          running = true;
+          if ((m0 | m1 | m2 | m3) & 0x80808080u) bad = true;
         }
+        if (to_lower) { fb.x = pipe_lower4(fb.x); fb.y = pipe_lower4(fb.y); fb.z = pipe_lower4(fb.z); fb.w = pipe_lower4(fb.w); }
       }
+      return (pipe_word_of(fb, (x >> 2) & 3) >> (8 * (x & 3))) & 0xFFu;
+    };
+    // read-ahead of the three characters the encoder looks at: k, k-1, k-2
+    uint32_t c0 = 0, c1 = 0, c2 = 0;
+    if (active) {
+      if (k >= 0) c0 = fetch(galign + k);
+      if (CAP && k >= 1) c1 = fetch(galign + k - 1);
+      if (CAP && k >= 2) c2 = fetch(galign + k - 2);
     }
-    if (__all_sync(FULL, !running)) break;
-    if (!running) continue;
-    if (p < 0 || bad) {
-      if (!ENC) {
-        A.pflag[item] = bad ? 1 : 0;
-        if (bad) { A.counts[s] = 0; A.need[s] = 0; A.missing[s] = 0; A.status[s] = 13; }
-      }
-      running = false;
-      continue;
-    }
-    const int c = ta + p;
-    if ((c & ~15) != qbase) {
-      qbase = c & ~15;
-      q = pipe_load16(ga, qbase, total_c);
-      if (want_ascii) {
-        uint32_t m0 = q.x, m1 = q.y, m2 = q.z, m3 = q.w;
-        if (qbase == 0 && ta) {
-          uint32_t t[4] = {m0, m1, m2, m3};
-          for (int k = 0; k < ta; k++) t[k >> 2] &= ~(0xFFu << (8 * (k & 3)));
-          m0 = t[0]; m1 = t[1]; m2 = t[2]; m3 = t[3];
+    RevCap e;
+    revcap_reset(e);
+    ClassTrail tr;
+    trail_reset(tr, code0);
+    uint32_t packed = 0, prev = 0, qbytes = 0, qn = 0, dist = 0;
+    uint4 wbuf = make_uint4(0, 0, 0, 0);
+
+    while (__any_sync(FULL, active)) {
+      if (!active) continue;
+      if (qn == 0) {
+        if (k < 0 || bad) {
+          // ---- the string is done: the last (partial) group of words, the verdict --------------
+          const uint32_t r = dist & 3u;
+          if (!bad && r) {
+            uint32_t* d = wend - dist;
+            d[0] = wbuf.x;
+            if (r > 1) d[1] = wbuf.y;
+            if (r > 2) d[2] = wbuf.z;
+          }
+          A.nlen[item] = bad ? 0u : dist;
+          A.pflag[item] = bad ? 1 : 0;
+          if (bad) { A.counts[s] = 0; A.need[s] = 0; A.missing[s] = 0; A.status[s] = 13; }
+          active = false;
+          continue;
         }
-        if (qbase + 16 > total_c) {   // (only the vector path can carry foreign bytes behind the end, and it never does)
+        if (CAP) {
+          qn = revcap_step(e, s_cls, c0, c1, c2, k,
+                           [&](int j) -> uint32_t {
+                             uint32_t x = ga[galign + j];
+                             if (to_lower && x - 'A' < 26u) x |= 0x20u;
+                             return x;
+                           },
+                           &qbytes);
+          c0 = c1;
+          c1 = c2;
+          c2 = (k >= 3) ? fetch(galign + k - 3) : 0u;
+        } else {
+          qbytes = c0;
+          qn = 1;
+          c0 = (k >= 1) ? fetch(galign + k - 1) : 0u;
         }
-        if ((m0 | m1 | m2 | m3) & 0x80808080u) { bad = true; continue; }
+        k--;
+        if (bad) continue;
       }
-      if (to_lower) { q.x = pipe_lower4(q.x); q.y = pipe_lower4(q.y); q.z = pipe_lower4(q.z); q.w = pipe_lower4(q.w); }
-    }
-    const uint32_t b = (pipe_word_of(q, (c >> 2) & 3) >> (8 * (c & 3))) & 0xFFu;
-    if (p == L - 1) {
-      packed = s_d1[b];
-    } else {
-      packed = dfa_next(packed, prev, b, D.shift, D.mask,
-                        [&](uint32_t i, uint4* k, uint4* v) { pipe_load32(D.buckets + 2 * i, k, v); },
-                        [&](uint32_t i) { return __ldg(&D.d2[i]); });
-    }
-    const uint32_t code = s_code[b];
-    const uint32_t w = position_word(packed, code, tr, voff);
-    trail_push(tr, code);
-    prev = b;
-    wbuf.w = wbuf.z;
-    wbuf.z = wbuf.y;
-    wbuf.y = wbuf.x;
-    wbuf.x = w;
-    nbuf++;
-    if ((p & 3) == 0) {
-      uint32_t* d = wdst + p;
-      if (nbuf == 4) {
-        *reinterpret_cast<uint4*>(d) = wbuf;
-      } else {
-        d[0] = wbuf.x;
-        if (nbuf > 1) d[1] = wbuf.y;
-        if (nbuf > 2) d[2] = wbuf.z;
+      if (qn != 0) {
+        const uint32_t b = (qbytes >> (8u * (qn - 1u))) & 0xFFu;
+        qn--;
+        if (dist >= slot) {   // more text than the slot holds: redone with a full-size slot
+          over = true;
+          A.nlen[item] = 0;
+          A.pflag[item] = 3;
+          A.counts[s] = 0; A.need[s] = 0; A.missing[s] = 0; A.status[s] = 14;
+          active = false;
+          continue;
+        }
+        if (dist == 0) {
+          packed = s_d1[b];
+        } else {
+          packed = dfa_next(packed, prev, b, D.shift, D.mask,
+                            [&](uint32_t i, uint4* kk, uint4* vv) { pipe_load32(D.buckets + 2 * i, kk, vv); },
+                            [&](uint32_t i) { return __ldg(&D.d2[i]); });
+        }
+        const uint32_t code = s_code[b];
+        const uint32_t w = position_word(packed, code, tr, voff);
+        trail_push(tr, code);
+        prev = b;
+        dist++;
+        if (TEXT) tend[-int64_t(dist)] = uint8_t(b);
+        wbuf.w = wbuf.z;
+        wbuf.z = wbuf.y;
+        wbuf.y = wbuf.x;
+        wbuf.x = w;
+        if ((dist & 3u) == 0) *reinterpret_cast<uint4*>(wend - dist) = wbuf;
       }
-      nbuf = 0;
     }
-    p--;
+    (void)over;
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// stage 3: the ungreedy loop.  STORE = ids into the slab (K1), otherwise counts (K3, and the
-// training worker's score histogram when A.scores is set).
+// stage 3: the ungreedy loop, 32 strings of equal length per warp.  STORE = ids into the slab
+// (K1), otherwise counts (K3, and the training worker's score histogram when A.scores is set).
 // ------------------------------------------------------------------------------------------
-template <bool STORE, bool ENC>
+template <bool STORE>
 __global__ void __launch_bounds__(kPipeBlock) chain_kernel(const TokenizeArgs A) {
   constexpr unsigned FULL = 0xFFFFFFFFu;
   ChainTables T;
@@ -388,33 +343,31 @@ __global__ void __launch_bounds__(kPipeBlock) chain_kernel(const TokenizeArgs A)
   T.can_retry = A.v.delete_token != 0xFFFFFFu;
   uint32_t* counter = A.pipe_counters + 3;
   const bool two_ids = STORE || A.scores != nullptr;
-
-  bool running = false, no_more = false;
-  uint32_t item = 0, s = 0, cap = 0;
-  uint64_t slab_base = 0;
-  const uint8_t* text = nullptr;
-  ChainString S{nullptr, 0};
-  ChainLane z;
-  chain_reset(z);
+  const int lane = threadIdx.x & 31;
 
   for (;;) {
-    if (!running && !no_more) {
-      item = atomicAdd(counter, 1u);
-      if (item >= A.n) {
-        no_more = true;
-      } else if (A.pflag[item] == 0) {
+    uint32_t g = 0;
+    if (lane == 0) g = atomicAdd(counter, 1u);
+    g = __shfl_sync(FULL, g, 0);
+    if (uint64_t(g) * 32u >= A.n) break;
+    const uint32_t slot_i = g * 32u + uint32_t(lane);
+    bool active = false;
+    uint32_t s = 0, cap = 0;
+    uint64_t slab_base = 0;
+    const uint8_t* text = nullptr;
+    ChainString S{nullptr, 0};
+    ChainLane z;
+    chain_reset(z);
+    if (slot_i < A.n) {
+      const uint32_t item = A.sort_order[slot_i];
+      if (A.pflag[item] == 0) {
         int64_t o0 = 0;
         int slen = 0;
         pipe_fetch(A, item, &s, &o0, &slen);
-        if (ENC) {
-          S.words = A.words + A.toff[item];
-          S.len = int(A.nlen[item]);
-          text = A.text + A.toff[item];
-        } else {
-          S.words = A.words + A.wbase[item];
-          S.len = slen;
-          text = A.data + o0;
-        }
+        const uint64_t e = A.toff[item + 1];
+        S.len = int(A.nlen[item]);
+        S.words = A.words + e - S.len;
+        if (A.text) text = A.text + e - S.len;
         if (A.list) {   // placement follows the string's own (raw) extent, like the first pass
           const int64_t r0 = A.raw_off[s];
           const int64_t r1 = A.raw_ends ? A.raw_ends[s] : A.raw_off[s + 1];
@@ -424,43 +377,41 @@ __global__ void __launch_bounds__(kPipeBlock) chain_kernel(const TokenizeArgs A)
           slab_base = A.slab_off ? A.slab_off[s] : uint64_t(o0 - A.off[0]) + uint64_t(A.slab_pad) * s;
           cap = A.slab_off ? uint32_t(A.slab_off[s + 1] - A.slab_off[s]) : uint32_t(slen) + A.slab_pad;
         }
-        chain_reset(z);
-        running = true;
+        active = true;
       }
     }
-    if (__all_sync(FULL, !running)) break;
-    if (!running) continue;
-    if (z.i >= S.len) {
-      A.counts[s] = STORE ? min(z.cnt, cap) : z.cnt;
-      A.need[s] = z.cnt;
-      A.missing[s] = z.miss;
-      A.status[s] = 0;
-      if (STORE && z.cnt > cap) atomicExch(A.overflow, 1u);
-      running = false;
-      continue;
-    }
-    uint32_t stored = z.cnt;   // ids stored so far follow the lane's own count
-    chain_step(
-        T, S, z, two_ids, [&](uint32_t idx, uint4* r0, uint4* r1) { pipe_load32(T.rec + 2 * idx, r0, r1); },
-        [&](uint32_t id, uint32_t, uint32_t adv) {
-          if (!STORE && A.scores) atomicAdd(&A.scores[id], static_cast<unsigned long long>(adv));
-          if (STORE && stored < cap) A.slab[slab_base + stored] = id;
-          stored++;
-        },
-        [&](int pos) -> uint32_t {
-          if (!STORE && A.scores) {   // trainvocab.go:1164-1171: counted, never scored
-            uint32_t b = text[pos];
-            if (!ENC && !A.prenorm && (A.v.normflag & 2) && b - 'A' < 26u) b |= 0x20u;
-            atomicAdd(&A.miss_hist[b], 1ull);
-            return 1u;
-          }
-          if (A.v.unk != 0xFFFFFFu) {
-            if (STORE && stored < cap) A.slab[slab_base + stored] = A.v.unk;
+    while (__any_sync(FULL, active)) {
+      if (!active) continue;
+      if (z.i >= S.len) {
+        A.counts[s] = STORE ? min(z.cnt, cap) : z.cnt;
+        A.need[s] = z.cnt;
+        A.missing[s] = z.miss;
+        A.status[s] = 0;
+        if (STORE && z.cnt > cap) atomicExch(A.overflow, 1u);
+        active = false;
+        continue;
+      }
+      uint32_t stored = z.cnt;   // ids stored so far follow the lane's own count
+      chain_step(
+          T, S, z, two_ids, [&](uint32_t idx, uint4* r0, uint4* r1) { pipe_load32(T.rec + 2 * idx, r0, r1); },
+          [&](uint32_t id, uint32_t, uint32_t adv) {
+            if (!STORE && A.scores) atomicAdd(&A.scores[id], static_cast<unsigned long long>(adv));
+            if (STORE && stored < cap) A.slab[slab_base + stored] = id;
             stored++;
-            return 1u;
-          }
-          return 0u;
-        });
+          },
+          [&](int pos) -> uint32_t {
+            if (!STORE && A.scores) {   // trainvocab.go:1164-1171: counted, never scored
+              atomicAdd(&A.miss_hist[text[pos]], 1ull);
+              return 1u;
+            }
+            if (A.v.unk != 0xFFFFFFu) {
+              if (STORE && stored < cap) A.slab[slab_base + stored] = A.v.unk;
+              stored++;
+              return 1u;
+            }
+            return 0u;
+          });
+    }
   }
 }
 
