@@ -183,6 +183,13 @@ int tmgpu_wire_decode(tmgpu_vocab* v, uint8_t enc_len, const uint8_t* payload, u
                       tmgpu_wire_reply** out);
 void tmgpu_wire_reply_free(tmgpu_wire_reply* r);
 
+/* Deserialize (go/tokenmonster.go:749-784): little-endian ids of enc_len (2, 3, 4; 0 = by the
+ * vocabulary, 2 if len(reverse) <= 65536 else 3) bytes -> uint32.  `out` has room for
+ * n_bytes / enc_len ids; a ragged tail is ignored.  Host-side byte shuffling, no device work;
+ * v may be NULL when enc_len != 0.  Returns the number of ids, or -1 for an invalid enc_len. */
+int64_t tmgpu_deserialize(const tmgpu_vocab* v, const uint8_t* data, uint64_t n_bytes, uint8_t enc_len,
+                          uint32_t* out);
+
 /* ---- device-resident path (inputs already in HBM; used for the kernel roofline figure and
  *      by the sharded multi-GPU host) -------------------------------------------------------
  * A workspace owns the device output buffers for batches up to (max_strings, max_bytes).

@@ -123,6 +123,21 @@ long hs_normalize(void* h, const uint8_t* data, size_t n, uint8_t* out, size_t c
   return long(R.text.size());
 }
 
+// position words + normalized text of one string (analysis / tests); returns the normalized length
+long hs_table(void* h, const uint8_t* data, size_t n, int prenorm, uint32_t* words, uint8_t* text, size_t cap) {
+  const Sim& S = *static_cast<Sim*>(h);
+  const HostTables& t = S.t;
+  const Tabled R = table(S, data, int(n), !prenorm && t.capcode == 2, !prenorm && (t.normflag & 2) != 0,
+                         !prenorm && (t.normflag != 0 || t.capcode == 2));
+  if (R.bad) return -1;
+  if (R.words.size() > cap) return -2;
+  for (size_t k = 0; k < R.words.size(); k++) {
+    words[k] = R.words[k];
+    text[k] = R.text[k];
+  }
+  return long(R.words.size());
+}
+
 // ids of one string.  prenorm: the text is already normalized.  count_mode: Vocab.Count (quirk Q2).
 // Returns the id count (ids beyond cap are dropped), -1 = refused (status 13).
 long hs_tokenize(void* h, const uint8_t* data, size_t n, int prenorm, int count_mode, uint32_t* ids, size_t cap,

@@ -148,3 +148,26 @@ def test_cpp_mirror_runs_unit_cpp_assertions_on_gpu(built, tmp_path):
     exe, voc = _build_cpp_smoke(tmp_path)
     r = subprocess.run([exe, voc, "gpu"], capture_output=True, text=True)
     assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
+
+
+def test_deserialize_matches_reference_serializations(built):
+    """Vocab.Deserialize (go/tokenmonster.go:749-784) of the reference's own 16/24/32-bit streams
+    (tests/golden/cases.json, produced by oracle/_ref) gives back the reference's ids."""
+    import json
+    from tokenmonster_b200 import Vocab
+    from tokenmonster_b200.vocab import TmgpuError
+    with open(os.path.join(GOLD, "cases.json")) as f:
+        cases = json.load(f)
+    for name in ("small_cap2", "gpt2"):
+        with open(os.path.join(GOLD, name + ".vocab"), "rb") as f:
+            v = Vocab(f.read(), device=-1)
+        for row in cases[name]["rows"][:60]:
+            for enc in (2, 3, 4):
+                if f"ser{enc}" in row:
+                    got = v.deserialize_tokens(bytes.fromhex(row[f"ser{enc}"]), enc)
+                    assert got.tolist() == row["ids"]
+            assert v.deserialize_tokens(bytes.fromhex(row["ser2"]), 0).tolist() == row["ids"]   # both have <= 65536 ids
+            assert v.deserialize_tokens(bytes.fromhex(row["ser4"]) + b"\x01\x02", 4).tolist() == row["ids"]   # ragged tail
+        with pytest.raises(TmgpuError):
+            v.deserialize_tokens(b"\x00\x00", 5)
+        v.close()

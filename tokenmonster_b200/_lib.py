@@ -83,6 +83,7 @@ PROTOTYPES = {
     "tmgpu_workspace_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     "tmgpu_decode_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8, C.c_void_p,
                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "tmgpu_deserialize": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint8, C.c_void_p]),
     "tmgpu_workspace_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "tmgpu_selftest_trie_lookup": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, u32p]),
     "tmgpu_selftest_unicode": (C.c_uint32, [C.c_uint32, u32p, u32p, u32p, C.POINTER(C.c_int)]),

@@ -229,6 +229,24 @@ extern "C" int tmgpu_vocab_info_get(const tmgpu_vocab* v, tmgpu_vocab_info* o) {
   return TMGPU_OK;
 }
 
+extern "C" int64_t tmgpu_deserialize(const tmgpu_vocab* v, const uint8_t* data, uint64_t n_bytes, uint8_t enc_len,
+                                     uint32_t* out) {
+  if (enc_len == 0 && v) enc_len = v->host.n_reverse <= 65536 ? 2 : 3;   // go:751-757
+  if (!(enc_len == 2 || enc_len == 3 || enc_len == 4) || (!data && n_bytes) || (!out && n_bytes >= enc_len)) {
+    g_err = "tmgpu_deserialize: invalid encoding length or null buffer";
+    return -1;
+  }
+  const uint64_t n = n_bytes / enc_len;
+  for (uint64_t k = 0; k < n; k++) {
+    const uint8_t* p = data + k * enc_len;
+    uint32_t id = uint32_t(p[0]) | (uint32_t(p[1]) << 8);
+    if (enc_len > 2) id |= uint32_t(p[2]) << 16;
+    if (enc_len > 3) id |= uint32_t(p[3]) << 24;
+    out[k] = id;
+  }
+  return int64_t(n);
+}
+
 // Table self-check (host): walks the same prefix trie the kernels walk, for a single window.
 // Not a tokenizer and not a fallback -- it exists so that CPU-only CI can verify the table
 // builder against the oracle's dictionary.  Returns matched length in window bytes.

@@ -309,14 +309,15 @@ class Vocab:
 
     # ---- (de)serialization helpers (py:916-943, go Deserialize :749-784) ----------------
     def deserialize_tokens(self, binary: bytes, enc_len: int = 0) -> np.ndarray:
+        """Vocab.Deserialize (go:749-784) through the C ABI (tmgpu_deserialize)."""
+        raw = np.frombuffer(bytes(binary), dtype=np.uint8)
         enc = enc_len or self.default_encoding_length()
-        raw = np.frombuffer(binary, dtype=np.uint8)
-        raw = raw[: (len(raw) // enc) * enc]
-        if enc == 2:
-            return raw.view(np.uint16).astype(np.uint32)
-        if enc == 4:
-            return raw.view(np.uint32).copy()
-        return _widen24(raw)
+        out = np.zeros(len(raw) // max(enc, 1) if enc in (2, 3, 4) else 0, np.uint32)
+        n = lib().tmgpu_deserialize(self._h, raw.ctypes.data if raw.size else None, len(raw), enc_len,
+                                    out.ctypes.data if out.size else None)
+        if n < 0:
+            raise TmgpuError(1, "Invalid encoding length")
+        return out[:n]
 
     # ---- table self-check (host walk of the device trie; CPU-only CI) ---------------------
     def _trie_lookup(self, window: bytes, spaced: bool = False, shortcut: bool = False):
