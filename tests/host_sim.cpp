@@ -20,6 +20,7 @@ namespace {
 struct Sim {
   HostTables t;
   uint8_t cls[128];
+  uint32_t lut[kCapLutSize];
 };
 
 // stages 1 + 2 as the table kernel does them: from the end of the string, the encoder yields the
@@ -54,7 +55,9 @@ Tabled table(const Sim& S, const uint8_t* raw, int n, bool cap, bool to_lower, b
   bool first = true;
   while (k >= 0 || qn) {
     if (qn == 0) {
-      if (cap) qn = revcap_step(e, S.cls, at(k), k >= 1 ? at(k - 1) : 0u, k >= 2 ? at(k - 2) : 0u, k, at, &qbytes);
+      auto xc = [&](int j) -> uint32_t { const uint32_t c = at(j); return c | (pc_class_sp(c) << 8); };
+      if (cap) qn = revcap_step(e, S.lut, xc(k), k >= 1 ? xc(k - 1) : 0u, k >= 2 ? xc(k - 2) : 0u, k,
+                                [&](int j) -> uint32_t { return pc_class_sp(at(j)); }, &qbytes);
       else { qbytes = at(k); qn = 1; }
       k--;
       if (qn == 0) continue;   // a space replaced by a marker emits nothing
@@ -94,6 +97,7 @@ void* hs_load(const uint8_t* vocab, size_t n, char* err, int errcap) {
     return nullptr;
   }
   for (uint32_t c = 0; c < 128; c++) S->cls[c] = uint8_t(pc_class(c));
+  for (uint32_t i = 0; i < uint32_t(kCapLutSize); i++) S->lut[i] = revcap_lut_entry(i);
   return S;
 }
 
@@ -151,7 +155,7 @@ long hs_tokenize(void* h, const uint8_t* data, size_t n, int prenorm, int count_
   if (R.bad) return -1;
   const int L = int(R.words.size());
   ChainTables T;
-  T.rec = reinterpret_cast<const uint4*>(t.rec.data());
+  T.crec = reinterpret_cast<const uint4*>(t.chain_rec.data());
   T.hot = reinterpret_cast<const uint4*>(t.dfa_hot.data());
   T.delete_token = t.delete_token;
   T.unk = t.unk;
@@ -172,8 +176,8 @@ long hs_tokenize(void* h, const uint8_t* data, size_t n, int prenorm, int count_
     }
     return 0u;
   };
-  auto load_rec = [&](uint32_t idx, uint4* r0, uint4* r1) { *r0 = T.rec[2 * idx]; *r1 = T.rec[2 * idx + 1]; };
-  while (z.i < L) chain_step(T, cs, z, count_mode == 0, load_rec, emit, on_miss);
+  auto load32 = [&](const uint4* tab, uint32_t idx, uint4* a, uint4* b) { *a = tab[2 * idx]; *b = tab[2 * idx + 1]; };
+  while (z.i < L) chain_step(T, cs, z, count_mode == 0, load32, emit, on_miss);
   *missing = z.miss;
   return long(count_mode ? z.cnt : cnt);
 }

@@ -129,6 +129,9 @@ extern "C" int tmgpu_vocab_create(const uint8_t* file_bytes, size_t n, int devic
     if ((rc = upload(v, h.dfa_buckets.data(), h.dfa_buckets.size(), &bk))) return fail(rc);
     if ((rc = upload(v, h.dfa_d2.data(), h.dfa_d2.size(), &d.dfa.d2))) return fail(rc);
     if ((rc = upload(v, h.dfa_hot.data(), h.dfa_hot.size(), &hot))) return fail(rc);
+    const uint32_t* crec = nullptr;
+    if ((rc = upload(v, h.chain_rec.data(), h.chain_rec.size(), &crec))) return fail(rc);
+    d.dfa.crec = reinterpret_cast<const uint4*>(crec);
     d.dfa.buckets = reinterpret_cast<const uint4*>(bk);
     d.dfa.hot = reinterpret_cast<const uint4*>(hot);
     d.dfa.shift = 32u - h.dfa_bits;

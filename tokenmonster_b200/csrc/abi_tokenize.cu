@@ -528,18 +528,17 @@ int stage_input(tmgpu_vocab* v, const uint8_t* data, const uint64_t* off, uint32
 int stage_copy(tmgpu_vocab* v, const uint8_t* src, uint32_t n, uint64_t total_bytes, bool gapped,
                       std::vector<ChunkPlan>* plan) {
   const uint64_t* total = &total_bytes;
-  // watermark = 0, then the offsets; the compute stream may start once both are on the device
-  v->h_info[40] = 0;
-  CU(cudaMemcpyAsync(v->d_run + 4, v->h_info + 40, 8, cudaMemcpyHostToDevice, v->copy_stream));
   CU(cudaMemcpyAsync(v->d_off, v->h_off, (size_t(n) + 1) * 8, cudaMemcpyHostToDevice, v->copy_stream));
   if (gapped && n)
     CU(cudaMemcpyAsync(v->d_off + v->d_off_cap, v->h_off + v->d_off_cap, size_t(n) * 8, cudaMemcpyHostToDevice,
                        v->copy_stream));
   CU(cudaEventRecord(v->chunk_ev[31], v->copy_stream));
-  // chunks of ~equal bytes; after each one the watermark (bytes landed) moves forward
-  int want = int(*total / (16ull << 20)) + 1;
-  if (want > 24) want = 24;
-  if (n < uint32_t(v->sms) * 800u) want = 1;   // small batches: one copy, then the plain path
+  // Chunks of ~equal bytes: the kernels of chunk k run while chunk k+1 is still on the wire.  One
+  // lane works on one string, so a chunk wants at least ~1000 strings per SM to fill the GPU, and
+  // a few of them are enough to hide all but the first copy.
+  int want = int(n / (uint32_t(v->sms) * 1024u));
+  if (want > 8) want = 8;
+  if (want < 1) want = 1;
   if (plan) plan->clear();
   uint32_t s0 = 0;
   const uint32_t pad = v->ws->slab_pad;
@@ -556,8 +555,6 @@ int stage_copy(tmgpu_vocab* v, const uint8_t* src, uint32_t n, uint64_t total_by
     }
     const uint64_t b0 = uint64_t(v->h_off[s0]), b1 = uint64_t(v->h_off[s1]);
     if (b1 > b0) CU(cudaMemcpyAsync(v->d_in + b0, src + b0, b1 - b0, cudaMemcpyHostToDevice, v->copy_stream));
-    v->h_info[41 + c] = b1;
-    CU(cudaMemcpyAsync(v->d_run + 4, v->h_info + 41 + c, 8, cudaMemcpyHostToDevice, v->copy_stream));
     CU(cudaEventRecord(v->chunk_ev[c], v->copy_stream));
     if (plan) plan->push_back({s0, s1, (b0 - uint64_t(v->h_off[0])) + uint64_t(pad) * s0, v->chunk_ev[c]});
     s0 = s1;

@@ -28,7 +28,8 @@ TM_HD uint32_t dfa_hash(uint32_t key, uint32_t shift) { return (key * 0x9E3779B1
 struct DfaDev {
   const uint4* buckets;      // 2 x uint4 per bucket: keys, values
   const uint32_t* d2;        // 65536
-  const uint4* hot;          // per state
+  const uint4* hot;          // 2 per state
+  const uint4* crec;         // 2 per dictionary index
   uint32_t shift;            // 32 - log2(buckets)
   uint32_t mask;             // buckets - 1
   uint32_t n_states;

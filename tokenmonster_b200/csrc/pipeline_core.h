@@ -24,7 +24,7 @@
 namespace tmgpu {
 
 // ------------------------------------------------------------------------------------------
-// stage 1: capcode level 2 encoder, one raw character per call
+// stage 1: capcode level 2 encoder
 // ------------------------------------------------------------------------------------------
 enum : uint32_t { PC_O = 0, PC_U = 1, PC_L = 2, PC_N = 3, PC_A = 4 };   // other, upper, lower, digit, apostrophe
 
@@ -36,89 +36,10 @@ TM_HD uint32_t pc_class(uint32_t c) {
   return PC_O;
 }
 
-struct CapState {
-  uint32_t cl1, cl2;        // classes of the previous two raw characters
-  bool in_word, mixed, sp1; // inside a capitalised run; that run is mixed case; previous char was ' '
-};
-
-TM_HD void cap_reset(CapState& e) {
-  e.cl1 = PC_O;
-  e.cl2 = PC_O;
-  e.in_word = false;
-  e.mixed = false;
-  e.sp1 = false;
-}
-
-// Encodes raw character c (index k of n; next character cn, '.' behind the end).  `cls` maps an
-// ASCII byte to its class; `raw_at(j)` reads raw character j (only used by the rare look-ahead
-// over a run of capitals / digits / apostrophes).  Returns the number of bytes (0..4) placed in
-// *out, little endian.  Forward-looking restatement of js:900-1005: the marker of a capitalised
-// run (W = stays capital, C = mixed case) is decided when the run starts, from the class of the
-// first lower-case-or-other character behind it, so nothing already emitted is ever rewritten.
-template <class RawAt>
-TM_HD uint32_t cap_step(CapState& e, const uint8_t* cls, uint32_t c, uint32_t cn, int k, int n, RawAt raw_at,
-                        uint32_t* out) {
-  const bool has_next = (k + 1 < n);
-  const uint32_t cl = cls[c & 127u], cln = has_next ? cls[cn & 127u] : uint32_t(PC_O);
-  const bool letter1 = (e.cl1 == PC_U) || (e.cl1 == PC_L);
-  const bool glue1 = letter1 || (e.cl1 == PC_A);
-  const bool start = (cl == PC_U) && !e.in_word;
-  if (start) {
-    uint32_t k_cl = cln;
-    if (!(k_cl == PC_L || k_cl == PC_O)) {   // rare: a run of 2+ capitals / digits / apostrophes
-      k_cl = PC_O;
-      for (int j = k + 2; j < n; j++) {
-        const uint32_t x = cls[raw_at(j) & 127u];
-        if (x == PC_L || x == PC_O) { k_cl = x; break; }
-      }
-    }
-    e.mixed = (k_cl == PC_L);
-  }
-  const bool joined_l = e.in_word ? glue1 : (e.sp1 || letter1 || (((e.cl2 == PC_U) || (e.cl2 == PC_L)) && e.cl1 == PC_A));
-  const bool joined_n = e.in_word ? (e.cl1 == PC_N) : (e.sp1 || e.cl1 == PC_N);
-  const bool k_dspace = (cl == PC_L && !joined_l) || (cl == PC_N && !joined_n) ||
-                        (cl == PC_U && e.in_word && !e.mixed && !glue1);
-  const bool k_dcs = (cl == PC_U) && e.in_word && e.mixed;
-  const uint32_t marker = e.mixed ? 'C' : 'W';
-  uint32_t pre = 0, np = 0;
-  if (k_dspace) { pre = 'D' | (' ' << 8); np = 2; }
-  if (k_dcs) { pre = 'D' | ('C' << 8) | (' ' << 16); np = 3; }
-  if (start) {
-    pre = e.sp1 ? (marker | (' ' << 8)) : ('D' | (marker << 8) | (' ' << 16));
-    np = e.sp1 ? 2 : 3;
-  }
-  // a space right before the first letter of a capitalised word is replaced by the marker
-  // (js:976-979): the capital emits "<marker> x" and the space emits nothing
-  const bool eaten = (c == ' ') && has_next && (cln == PC_U);
-  const uint32_t ch = (cl == PC_U) ? (c | 0x20u) : c;
-  *out = eaten ? pre : (pre | (ch << (8 * np)));
-  e.in_word = (cl == PC_U) ? true : ((cl == PC_L || cl == PC_O) ? false : e.in_word);
-  e.cl2 = e.cl1;
-  e.cl1 = cl;
-  e.sp1 = (c == ' ');
-  return np + (eaten ? 0u : 1u);
-}
-
-// Four raw characters at once: all lower-case letters or spaces, behind a letter or a space, encode
-// to themselves (js:969-974: no "D " is due; js:976-979: no capital follows inside; the rule for
-// a trailing space only needs the fifth character c5, 0 behind the end).
-TM_HD bool cap_fast4(CapState& e, uint32_t w4, uint32_t c5) {
-  const uint32_t low = (w4 + 0x1F1F1F1Fu) & ~(w4 + 0x05050505u);             // 'a'..'z'
-  const uint32_t y = w4 ^ 0x20202020u;
-  const uint32_t spc = ~(((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y);              // == ' '
-  const bool prev_ok = e.sp1 || e.cl1 == PC_U || e.cl1 == PC_L;
-  const bool tail_ok = ((w4 >> 24) != ' ') || !(c5 - 'A' < 26u);
-  if (!(prev_ok && tail_ok && (w4 & 0x80808080u) == 0 && ((low | spc) & 0x80808080u) == 0x80808080u)) return false;
-  const uint32_t b2 = (w4 >> 16) & 0xFFu, b3 = w4 >> 24;
-  e.in_word = false;
-  e.cl2 = (b2 == ' ') ? uint32_t(PC_O) : uint32_t(PC_L);
-  e.cl1 = (b3 == ' ') ? uint32_t(PC_O) : uint32_t(PC_L);
-  e.sp1 = (b3 == ' ');
-  return true;
-}
-
 // ------------------------------------------------------------------------------------------
-// stage 1, right to left: the same encoder driven from the END of the string, one raw character
+// stage 1, right to left: the encoder (a forward-looking restatement of js:900-1005: the marker
+// of a capitalised run -- W = stays capital, C = mixed case -- is decided where the run starts, so
+// nothing already emitted is ever rewritten) driven from the END of the string, one raw character
 // per call.  This is what the table kernel runs (the automaton consumes the normalized text back
 // to front, so producing it back to front lets both live in one loop and the normalized text never
 // exists in memory).  Everything the encoder knows about a character is local:
@@ -145,39 +66,23 @@ TM_HD void revcap_reset(RevCap& e) {
   e.iw = false;
 }
 
-// Encodes raw character c0 at index k; c1 / c2 = the characters at k-1 / k-2 (ignored where they do
-// not exist); raw_at(j) reads character j (rare deeper look-back).  Returns the number of bytes
-// (0..4) placed in *out in FORWARD order, little endian -- the caller feeds them to the automaton
-// last byte first.  Same output as cap_step() run left to right (tests/test_host_sim.py).
-template <class RawAt>
-TM_HD uint32_t revcap_step(RevCap& e, const uint8_t* cls, uint32_t c0, uint32_t c1, uint32_t c2, int k, RawAt raw_at,
-                           uint32_t* out) {
-  const uint32_t cl = cls[c0 & 127u];
-  const uint32_t cl1 = (k >= 1) ? uint32_t(cls[c1 & 127u]) : uint32_t(PC_O);
-  const uint32_t cl2 = (k >= 2) ? uint32_t(cls[c2 & 127u]) : uint32_t(PC_O);
-  const bool sp1 = (k >= 1) && (c1 == ' ');
-  bool in_word;
-  if (cl1 != PC_N && cl1 != PC_A) {        // also k == 0: no left neighbour counts as "other"
-    in_word = (cl1 == PC_U);
-    e.iw_valid = false;
-  } else {
-    if (!e.iw_valid) {
-      uint32_t x = cl2;
-      int j = k - 2;
-      while ((x == PC_N || x == PC_A) && j > 0) {
-        j--;
-        x = cls[raw_at(j) & 127u];
-      }
-      e.iw = (k >= 2) && (x == PC_U);
-      e.iw_valid = true;
-    }
-    in_word = e.iw;
-  }
-  const bool mixed = (e.nlo == PC_L);
+// The encoder's decision is a function of ten bits, so the kernels read it from a table:
+//   index = cl | cl1 << 3 | (cl2 is a letter) << 6 | in_word << 7 | mixed << 8 | (a capital follows) << 9
+//   (classes as PC_*, with the space as a class of its own, PC_S)
+//   entry = bytes in front of the character (<= 3, little endian) | count << 24 | eaten << 26 | lower << 27
+constexpr uint32_t PC_S = 5;       // ' ' -- behaves as PC_O except where the encoder asks for a space
+constexpr int kCapLutSize = 1024;
+
+TM_HD uint32_t pc_class_sp(uint32_t c) { return c == ' ' ? PC_S : pc_class(c); }
+
+TM_HD uint32_t revcap_lut_entry(uint32_t idx) {
+  const uint32_t cl = idx & 7u, cl1 = (idx >> 3) & 7u;
+  const bool cl2_letter = (idx >> 6) & 1u, in_word = (idx >> 7) & 1u, mixed = (idx >> 8) & 1u, cap_follows = (idx >> 9) & 1u;
+  const bool sp1 = (cl1 == PC_S);
   const bool letter1 = (cl1 == PC_U) || (cl1 == PC_L);
   const bool glue1 = letter1 || (cl1 == PC_A);
   const bool start = (cl == PC_U) && !in_word;
-  const bool joined_l = in_word ? glue1 : (sp1 || letter1 || (((cl2 == PC_U) || (cl2 == PC_L)) && cl1 == PC_A));
+  const bool joined_l = in_word ? glue1 : (sp1 || letter1 || (cl2_letter && cl1 == PC_A));
   const bool joined_n = in_word ? (cl1 == PC_N) : (sp1 || cl1 == PC_N);
   const bool k_dspace = (cl == PC_L && !joined_l) || (cl == PC_N && !joined_n) ||
                         (cl == PC_U && in_word && !mixed && !glue1);
@@ -190,13 +95,52 @@ TM_HD uint32_t revcap_step(RevCap& e, const uint8_t* cls, uint32_t c0, uint32_t 
     pre = sp1 ? (marker | (' ' << 8)) : ('D' | (marker << 8) | (' ' << 16));
     np = sp1 ? 2 : 3;
   }
-  const bool eaten = (c0 == ' ') && e.has_right && (e.clr == PC_U);
-  const uint32_t ch = (cl == PC_U) ? (c0 | 0x20u) : c0;
-  *out = eaten ? pre : (pre | (ch << (8 * np)));
+  // a space right before the first letter of a capitalised word is replaced by the marker
+  // (js:976-979): the capital emits "<marker> x" and the space emits nothing
+  const bool eaten = (cl == PC_S) && cap_follows;
+  return pre | (np << 24) | (uint32_t(eaten) << 26) | (uint32_t(cl == PC_U) << 27);
+}
+
+// Encodes the raw character at index k.  x0 / x1 / x2 = character | class << 8 (pc_class_sp) of the
+// characters at k / k-1 / k-2 (x1, x2 ignored where they do not exist); class_at(j) = class of
+// character j (rare deeper look-back); lut = the kCapLutSize entries of revcap_lut_entry().
+// Returns the number of bytes (0..4) placed in *out in FORWARD order, little endian -- the caller
+// feeds them to the automaton last byte first (checked against the oracle's encoder,
+// tests/test_host_sim.py).
+template <class ClassAt>
+TM_HD uint32_t revcap_step(RevCap& e, const uint32_t* lut, uint32_t x0, uint32_t x1, uint32_t x2, int k, ClassAt class_at,
+                           uint32_t* out) {
+  const uint32_t cl = x0 >> 8;
+  const uint32_t cl1 = (k >= 1) ? (x1 >> 8) : uint32_t(PC_O);
+  const uint32_t cl2 = (k >= 2) ? (x2 >> 8) : uint32_t(PC_O);
+  bool in_word;
+  if (cl1 != PC_N && cl1 != PC_A) {        // also k == 0: no left neighbour counts as "other"
+    in_word = (cl1 == PC_U);
+    e.iw_valid = false;
+  } else {
+    if (!e.iw_valid) {
+      uint32_t x = cl2;
+      int j = k - 2;
+      while ((x == PC_N || x == PC_A) && j > 0) {
+        j--;
+        x = class_at(j);
+      }
+      e.iw = (k >= 2) && (x == PC_U);
+      e.iw_valid = true;
+    }
+    in_word = e.iw;
+  }
+  const uint32_t idx = cl | (cl1 << 3) | (uint32_t(cl2 == PC_U || cl2 == PC_L) << 6) | (uint32_t(in_word) << 7) |
+                       (uint32_t(e.nlo == PC_L) << 8) | (uint32_t(e.has_right && e.clr == PC_U) << 9);
+  const uint32_t a = lut[idx];
+  const uint32_t np = (a >> 24) & 3u, eaten = (a >> 26) & 1u;
+  const uint32_t ch = (x0 & 0xFFu) | (((a >> 27) & 1u) << 5);
+  *out = (a & 0xFFFFFFu) | (eaten ? 0u : (ch << (8u * np)));
   e.clr = cl;
   e.has_right = true;
-  if (cl == PC_L || cl == PC_O) e.nlo = cl;
-  return np + (eaten ? 0u : 1u);
+  if (cl == PC_L) e.nlo = PC_L;
+  else if (cl == PC_O || cl == PC_S) e.nlo = PC_O;
+  return np + 1u - eaten;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -214,21 +158,21 @@ TM_HD int class_value(uint32_t code) { return int((0x0C0A0100u >> (8 * code)) & 
 // behind the end of the string are the pad byte 0 (defined as 0).  48 positions
 // are kept (a key has at most 40 bytes).
 struct ClassTrail {
-  uint32_t a, b, c;   // positions +1..+16, +17..+32, +33..+48
+  unsigned long long lo;   // positions +1..+32
+  uint32_t hi;             // positions +33..+48
 };
 TM_HD void trail_reset(ClassTrail& t, uint32_t code0) {
-  t.a = t.b = t.c = code0 * 0x55555555u;
+  t.lo = code0 * 0x5555555555555555ull;
+  t.hi = code0 * 0x55555555u;
 }
 TM_HD void trail_push(ClassTrail& t, uint32_t code) {
-  t.c = (t.c << 2) | (t.b >> 30);
-  t.b = (t.b << 2) | (t.a >> 30);
-  t.a = (t.a << 2) | code;
+  t.hi = (t.hi << 2) | uint32_t(t.lo >> 62);
+  t.lo = (t.lo << 2) | code;
 }
 // class of the byte d positions to the right (d >= 1)
 TM_HD uint32_t trail_at(const ClassTrail& t, uint32_t d) {
   const uint32_t k = d - 1u;
-  const uint32_t w = k < 16u ? t.a : (k < 32u ? t.b : t.c);
-  return (w >> (2u * (k & 15u))) & 3u;
+  return (k < 32u ? uint32_t(t.lo >> (2u * k)) : (t.hi >> (2u * (k - 32u)))) & 3u;
 }
 
 // The word of the position whose byte (class code `code`) was just consumed into `packed`.
@@ -241,11 +185,20 @@ TM_HD uint32_t position_word(uint32_t packed, uint32_t code, const ClassTrail& t
 }
 
 // ------------------------------------------------------------------------------------------
-// stage 3: one step of the ungreedy loop
+// stage 3: one step of the ungreedy loop, branch free.
+// The score of "first token a, then second token b" (go:1075-1084 plain, :1096-1105 retry;
+// pair_score() in device_tables.h is the direct restatement) is split at table-build time into
+//   A(a, fd)   = (a.flag>>7) + max0(nw-1) + 100*nw,  nw = a.nWords - fd          (token record)
+//   B(b, nb)   = (b.flag>>7) + max0(b.nWords-1) + ((nb>>2)&1) + 100*(b.nWords + (nb>>3))
+//                - 3*(b.flag & 1 & nb) [+ ((b.flag>>2)&1) plain | - 1 retry]      (state record,
+//                one value per class nb of the following byte)
+//   and the two interaction bits: -100*(a.flag>>3 & b.flag>>4 & 1), -103*(a.flag & 1 [& b.flag>>1])
+// so a candidate costs one add chain instead of ~30 instructions, and all six candidates are
+// evaluated unconditionally (invalid ones score -1000000): 32 lanes execute the same instructions.
 // ------------------------------------------------------------------------------------------
 struct ChainTables {
-  const uint4* rec;      // 2 x uint4 per dictionary index (vocab_tables.h: TokenRecord)
-  const uint4* hot;      // per automaton state
+  const uint4* crec;     // 2 x uint4 per dictionary index (vocab_tables.h: chain record)
+  const uint4* hot;      // 2 x uint4 per automaton state  (vocab_tables.h: state record)
   uint32_t delete_token, unk;
   uint32_t off;          // bytes of the virtual space
   bool can_retry;        // a delete token exists (go:1088)
@@ -265,13 +218,21 @@ TM_HD void chain_reset(ChainLane& z) {
   z.i = 0; z.fd = 0; z.tok_len = 0; z.idx = 0; z.have = false; z.cnt = 0; z.miss = 0;
 }
 
+TM_HD int i16_lo(uint32_t x) { return int(int16_t(x & 0xFFFFu)); }
+TM_HD int i16_hi(uint32_t x) { return int(int16_t(x >> 16)); }
+// value number `code` (0..3) of four int16 packed in two words
+TM_HD int i16_sel(uint32_t w01, uint32_t w23, uint32_t code) {
+  const uint32_t w = (code & 2u) ? w23 : w01;
+  return int(int16_t((w >> (16u * (code & 1u))) & 0xFFFFu));
+}
+
 // emit(id, pos_code, adv): pos_code = position | forward-delete << 31 of the step (0xFFFFFFFF for
 // the delete token of a two-id step), adv = characters the step advances by.
 // on_miss(position) -> ids added: a byte no token covers (go:1269-1276); the caller emits unk.
 // two_ids: false for Vocab.Count, which adds 1 where tokenize emits 2 ids.
-// load_rec(index, &r0, &r1): the 32-byte token record (one 256-bit load on the device).
-template <class LoadRec, class Emit, class Miss>
-TM_HD void chain_step(const ChainTables& T, const ChainString& S, ChainLane& z, bool two_ids, LoadRec load_rec, Emit emit,
+// load32(table, index, &a, &b): one 32-byte record (a 256-bit load on the device).
+template <class Load32, class Emit, class Miss>
+TM_HD void chain_step(const ChainTables& T, const ChainString& S, ChainLane& z, bool two_ids, Load32 load32, Emit emit,
                       Miss on_miss) {
   if (!z.have) {   // loop top: the longest token at i (go:1049)
     const uint32_t w = S.words[z.i];
@@ -283,106 +244,95 @@ TM_HD void chain_step(const ChainTables& T, const ChainString& S, ChainLane& z, 
       z.fd = 0;
       return;
     }
-    z.idx = T.hot[pw_state(w)].x & 0xFFFFFFu;
+    uint4 ha, hb;
+    load32(T.hot, pw_state(w), &ha, &hb);
+    z.idx = ha.x & 0xFFFFFFu;
     z.tok_len = int(l);
     z.have = true;
   }
-  uint4 r0, r1;
-  load_rec(z.idx, &r0, &r1);
-  const uint32_t oflag = r0.x & 0xFFu;
-  const int onw = int((r0.x >> 8) & 0xFFu);
-  const int alen1 = int(r0.x >> 24), alen2 = int(r1.x & 0xFFu);
+  uint4 ra, rb;
+  load32(T.crec, z.idx, &ra, &rb);
+  const uint32_t bits = ra.x >> 24;
+  const int alen1 = int(ra.y >> 24), alen2 = int(ra.z >> 24);
   const int i = z.i, fd = z.fd, len = z.tok_len, L = S.len;
   const int i1 = i + len;
   const int base1 = alen1 - fd, base2 = alen2 - fd;
   // the three look-ahead positions (go:1068, 1113, 1165); alternative 2 only with alternative 1 (Q10)
-  const uint32_t w0 = (i1 < L) ? S.words[i1] : 0u;
-  const bool look = (i1 < L) && (((oflag & 32u) == 0) || pw_cls(w0) != 3u);   // go:1057 (class 3 = 12 = space)
-  const bool has1 = look && alen1 != 0, has2 = has1 && alen2 != 0;
-  const uint32_t w1 = (has1 && i + base1 < L) ? S.words[i + base1] : 0u;
-  const uint32_t w2 = (has2 && i + base2 < L) ? S.words[i + base2] : 0u;
+  const bool in0 = i1 < L;
+  const uint32_t w0 = in0 ? S.words[i1] : 0u;
+  const bool look = in0 & (((bits & 4u) == 0) | (pw_cls(w0) != 3u));   // go:1057 (class 3 = 12 = space)
+  const bool has1 = look & (alen1 != 0), has2 = has1 & (alen2 != 0);
+  const uint32_t w1 = (has1 & (i + base1 < L)) ? S.words[i + base1] : 0u;
+  const uint32_t w2 = (has2 & (i + base2 < L)) ? S.words[i + base2] : 0u;
   const int l0 = int(pw_len(w0)), l1 = int(pw_len(w1)), l2 = int(pw_len(w2));
-  uint4 h0 = make_uint4(0, 0, 0, 0), h1 = h0, h2 = h0;
-  if (l0) h0 = T.hot[pw_state(w0)];
-  if (l1) h1 = T.hot[pw_state(w1)];
-  if (l2) h2 = T.hot[pw_state(w2)];
-  int best_s = kNegScore, pick = -1;   // pick: 0..2 plain, 3..5 retry
-  if (look) {
-    const uint32_t aflag1 = (r1.x >> 8) & 0xFFu, aflag2 = (r1.x >> 24) & 0xFFu;
-    const int anw1 = int((r1.x >> 16) & 0xFFu), anw2 = int(r1.y & 0xFFu);
-    // plain candidates in the order s1, s2, s3 (strict > keeps the first maximum, go:1217-1262)
-    const int nb0 = class_value(pw_nb(w0)), nb1 = class_value(pw_nb(w1)), nb2 = class_value(pw_nb(w2));
-    if (l0 > 0) {
-      const int sc = pair_score(len + l0, oflag, onw - fd, h0.z & 0xFFu, int((h0.z >> 8) & 0xFFu), nb0, false);
-      if (sc > best_s) { best_s = sc; pick = 0; }
-    }
-    if (has1 && l1 > 0) {
-      const int bl = base1 + l1;
-      const int sc = pair_score(bl, aflag1, anw1 - fd, h1.z & 0xFFu, int((h1.z >> 8) & 0xFFu), nb1, false) -
-                     100 * int(bl < len) - 10000 * int(bl == len);
-      if (sc > best_s) { best_s = sc; pick = 1; }
-    }
-    if (has2 && l2 > 0) {
-      const int bl = base2 + l2;
-      const int sc = pair_score(bl, aflag2, anw2 - fd, h2.z & 0xFFu, int((h2.z >> 8) & 0xFFu), nb2, false) -
-                     100 * int(bl < len) - 10000 * int(bl == len);
-      if (sc > best_s) { best_s = sc; pick = 2; }
-    }
-    if (T.can_retry) {
-      // retries in the order s1b, s2b, s3b (go:1088-1107): wanted when the second token begins
-      // with a letter, has no word boundary inside and a letter follows it; accepted when the
-      // space-prefixed key is more than one byte longer than the plain one
-      const int off = int(T.off);
-      if (l0 > 0 && (h0.z & 2u) && nb0 == 1 && ((h0.z >> 8) & 0xFFu) == 0 && int(h0.y >> 24) > l0 + 1) {
-        const int lb = int(h0.y >> 24) - off;
-        const int sc = pair_score(len + lb, oflag, onw - fd, (h0.z >> 16) & 0xFFu, int(h0.z >> 24), class_value(pw_nbb(w0)), true);
-        if (sc > best_s) { best_s = sc; pick = 3; }
-      }
-      if (has1 && l1 > 0 && (h1.z & 2u) && nb1 == 1 && ((h1.z >> 8) & 0xFFu) == 0 && int(h1.y >> 24) > l1 + 1) {
-        const int bl = base1 + int(h1.y >> 24) - off;
-        const int sc = pair_score(bl, aflag1, anw1 - fd, (h1.z >> 16) & 0xFFu, int(h1.z >> 24), class_value(pw_nbb(w1)), true) -
-                       100 * int(bl < len) - 10000 * int(bl == len);
-        if (sc > best_s) { best_s = sc; pick = 4; }
-      }
-      if (has2 && l2 > 0 && (h2.z & 2u) && nb2 == 1 && ((h2.z >> 8) & 0xFFu) == 0 && int(h2.y >> 24) > l2 + 1) {
-        const int bl = base2 + int(h2.y >> 24) - off;
-        const int sc = pair_score(bl, aflag2, anw2 - fd, (h2.z >> 16) & 0xFFu, int(h2.z >> 24), class_value(pw_nbb(w2)), true) -
-                       100 * int(bl < len) - 10000 * int(bl == len);
-        if (sc > best_s) { best_s = sc; pick = 5; }
-      }
-    }
-  }
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  uint4 h0a = zero, h0b = zero, h1a = zero, h1b = zero, h2a = zero, h2b = zero;
+  if (l0) load32(T.hot, pw_state(w0), &h0a, &h0b);
+  if (l1) load32(T.hot, pw_state(w1), &h1a, &h1b);
+  if (l2) load32(T.hot, pw_state(w2), &h2a, &h2b);
+  // first-token parts: the current token, its alternative 1, its alternative 2
+  const int A0 = fd ? i16_hi(ra.w) : i16_lo(ra.w);
+  const int A1 = fd ? i16_hi(rb.x) : i16_lo(rb.x);
+  const int A2 = fd ? i16_hi(rb.y) : i16_lo(rb.y);
+  const int a1_0 = int(bits & 1u), a8_0 = int((bits >> 1) & 1u);
+  const int a1_1 = int((bits >> 3) & 1u), a8_1 = int((bits >> 4) & 1u);
+  const int a1_2 = int((bits >> 5) & 1u), a8_2 = int((bits >> 6) & 1u);
+  const bool v0 = look & (l0 > 0), v1 = has1 & (l1 > 0), v2 = has2 & (l2 > 0);
+  const int bl1 = base1 + l1, bl2 = base2 + l2;
+  // plain candidates s1, s2, s3
+  const int s0 = v0 ? (len + l0) + A0 + i16_sel(h0b.x, h0b.y, pw_nb(w0)) - 100 * (a8_0 & int((h0a.z >> 1) & 1u)) -
+                          103 * (a1_0 & int(h0a.z & 1u))
+                    : kNegScore;
+  const int s1 = v1 ? bl1 + A1 + i16_sel(h1b.x, h1b.y, pw_nb(w1)) - 100 * (a8_1 & int((h1a.z >> 1) & 1u)) -
+                          103 * (a1_1 & int(h1a.z & 1u)) - 100 * int(bl1 < len) - 10000 * int(bl1 == len)
+                    : kNegScore;
+  const int s2 = v2 ? bl2 + A2 + i16_sel(h2b.x, h2b.y, pw_nb(w2)) - 100 * (a8_2 & int((h2a.z >> 1) & 1u)) -
+                          103 * (a1_2 & int(h2a.z & 1u)) - 100 * int(bl2 < len) - 10000 * int(bl2 == len)
+                    : kNegScore;
+  // retries s1b, s2b, s3b (go:1088-1107): wanted when the second token begins with a letter, has
+  // no word boundary inside and a letter follows it; accepted when the space-prefixed key is more
+  // than one byte longer than the plain one
+  const int off = int(T.off);
+  const int sl0 = int(h0a.y >> 24), sl1 = int(h1a.y >> 24), sl2 = int(h2a.y >> 24);
+  const bool r0 = T.can_retry & v0 & (((h0a.z >> 2) & 1u) != 0) & (pw_nb(w0) == 1u) & (sl0 > l0 + 1);
+  const bool r1 = T.can_retry & v1 & (((h1a.z >> 2) & 1u) != 0) & (pw_nb(w1) == 1u) & (sl1 > l1 + 1);
+  const bool r2 = T.can_retry & v2 & (((h2a.z >> 2) & 1u) != 0) & (pw_nb(w2) == 1u) & (sl2 > l2 + 1);
+  const int bb1 = base1 + sl1 - off, bb2 = base2 + sl2 - off;
+  const int s3 = r0 ? (len + sl0 - off) + A0 + i16_sel(h0b.z, h0b.w, pw_nbb(w0)) - 100 * (a8_0 & int((h0a.z >> 3) & 1u)) - 103 * a1_0
+                    : kNegScore;
+  const int s4 = r1 ? bb1 + A1 + i16_sel(h1b.z, h1b.w, pw_nbb(w1)) - 100 * (a8_1 & int((h1a.z >> 3) & 1u)) - 103 * a1_1 -
+                          100 * int(bb1 < len) - 10000 * int(bb1 == len)
+                    : kNegScore;
+  const int s5 = r2 ? bb2 + A2 + i16_sel(h2b.z, h2b.w, pw_nbb(w2)) - 100 * (a8_2 & int((h2a.z >> 3) & 1u)) - 103 * a1_2 -
+                          100 * int(bb2 < len) - 10000 * int(bb2 == len)
+                    : kNegScore;
+  // first maximum in the order s1, s2, s3, s1b, s2b, s3b (go:1217-1262)
+  int best_s = kNegScore, pick = -1;
+  if (s0 > best_s) { best_s = s0; pick = 0; }
+  if (s1 > best_s) { best_s = s1; pick = 1; }
+  if (s2 > best_s) { best_s = s2; pick = 2; }
+  if (s3 > best_s) { best_s = s3; pick = 3; }
+  if (s4 > best_s) { best_s = s4; pick = 4; }
+  if (s5 > best_s) { best_s = s5; pick = 5; }
   const uint32_t pos_code = uint32_t(i) | (uint32_t(fd) << 31);
-  if (pick < 0) {   // no branch: emit the token, its successor is the longest token behind it (go:1265-1267)
-    emit(r0.y, pos_code, uint32_t(len));
-    z.cnt++;
-    z.i = i1;
-    z.fd = 0;
-    z.have = (l0 > 0);
-    z.idx = h0.x & 0xFFFFFFu;
-    z.tok_len = l0;
-    return;
-  }
-  const int br = pick >= 3 ? pick - 3 : pick;
-  const int adv = br == 0 ? len : (br == 1 ? base1 : base2);
-  emit(br == 0 ? r0.y : (br == 1 ? r0.z : r0.w), pos_code, uint32_t(adv));
+  const int br = pick >= 3 ? pick - 3 : (pick < 0 ? 0 : pick);
+  const bool retry = pick >= 3;
+  const uint32_t id = br == 0 ? ra.x : (br == 1 ? ra.y : ra.z);
+  const int adv = br == 0 ? len : (br == 1 ? base1 : base2);   // no branch taken: the token itself (go:1265-1267)
+  emit(id & 0xFFFFFFu, pos_code, uint32_t(adv));
   z.cnt++;
-  const uint4 hh = br == 0 ? h0 : (br == 1 ? h1 : h2);
-  if (pick >= 3) {
-    if (two_ids) {
-      emit(T.delete_token, 0xFFFFFFFFu, 1u);
-      z.cnt++;
-    }
-    z.idx = hh.y & 0xFFFFFFu;
-    z.tok_len = int(hh.y >> 24) - int(T.off);
-    z.fd = 1;
-  } else {
-    z.idx = hh.x & 0xFFFFFFu;
-    z.tok_len = br == 0 ? l0 : (br == 1 ? l1 : l2);
-    z.fd = 0;
+  if (retry & two_ids) {
+    emit(T.delete_token, 0xFFFFFFFFu, 1u);
+    z.cnt++;
   }
+  const uint32_t hx = br == 0 ? h0a.x : (br == 1 ? h1a.x : h2a.x);
+  const uint32_t hy = br == 0 ? h0a.y : (br == 1 ? h1a.y : h2a.y);
+  const int lx = br == 0 ? l0 : (br == 1 ? l1 : l2);
+  z.idx = (retry ? hy : hx) & 0xFFFFFFu;
+  z.tok_len = retry ? int(hy >> 24) - off : lx;
+  z.fd = retry ? 1 : 0;
   z.i = i + adv;
-  z.have = true;
+  z.have = (pick >= 0) | (l0 > 0);
 }
 
 }  // namespace tmgpu

@@ -159,21 +159,33 @@ __global__ void __launch_bounds__(256) select_overflowed_kernel(const uint8_t* _
 // ------------------------------------------------------------------------------------------
 // stages 1 + 2: capcode encoder and reversed-key automaton in one right-to-left loop.
 // A warp takes 32 strings of (nearly) equal length; every iteration each lane consumes exactly one
-// normalized byte: if its byte queue is empty it first encodes the next raw character (0..4 bytes),
-// then the automaton takes one byte and the position word goes out (16 bytes at a time, right
-// aligned in the string's slot, so the slot's start need not be known in advance).
+// normalized byte: if its byte queue is empty it first encodes the next raw character (0..4 bytes,
+// one table read decides), then the automaton takes one byte and the position word goes out (16
+// bytes at a time, right aligned in the string's slot, so the slot's start need not be known).
+// Raw text comes in through a 32-byte ring per lane in shared memory, filled 16 bytes at a time
+// by cp.async (SASS: LDGSTS) -- no registers, no wait: the copy is issued when the cursor is
+// still 8+ characters away, and by all lanes of the warp in the same iteration.
 // CAP: capcode level 2; otherwise the text is read as it is (capcode 0, or text the device
 // normalizer produced), lower-cased / checked for non-ASCII bytes when the vocabulary asks for it.
 // TEXT: also keep the normalized bytes (the training scores need the byte no token covers).
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pipe_cp_async4(uint32_t smem_addr, const void* gptr, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_addr), "l"(gptr), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void pipe_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <bool CAP, bool TEXT>
 __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A) {
   constexpr unsigned FULL = 0xFFFFFFFFu;
   __shared__ __align__(128) uint8_t s_img[kPipeImageBytes];
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ uint8_t s_cls[128];
+  __shared__ uint8_t s_cls[256];
+  __shared__ uint32_t s_lut[CAP ? kCapLutSize : 1];
+  __shared__ __align__(16) uint32_t s_ring[kPipeBlock * 8];   // word w of lane l: [warp * 256 + w * 32 + l]
   pipe_stage_tma(s_img, A.v.pipe_image, &s_bar);
-  if (threadIdx.x < 128) s_cls[threadIdx.x] = uint8_t(pc_class(threadIdx.x));
+  s_cls[threadIdx.x & 255] = uint8_t((threadIdx.x & 255) < 128 ? pc_class_sp(threadIdx.x & 255) : uint32_t(PC_O));
+  if (CAP)
+    for (int i = threadIdx.x; i < kCapLutSize; i += kPipeBlock) s_lut[i] = revcap_lut_entry(uint32_t(i));
   __syncthreads();
   const uint32_t* s_d1 = reinterpret_cast<const uint32_t*>(s_img);
   const uint8_t* s_code = s_img + 1024;
@@ -184,6 +196,7 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
   const uint32_t code0 = s_code[0];
   const int lane = threadIdx.x & 31;
   uint32_t* counter = A.pipe_counters + 2;
+  const uint32_t ring_b = pipe_smem_u32(s_ring + (threadIdx.x >> 5) * 256 + lane);   // byte address of word 0
 
   for (;;) {
     uint32_t g = 0;
@@ -192,13 +205,14 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
     if (uint64_t(g) * 32u >= A.n) break;
     const uint32_t slot_i = g * 32u + uint32_t(lane);
     // ---- this lane's string ---------------------------------------------------------------
-    bool active = false, bad = false, over = false;
+    bool active = false, bad = false;
     uint32_t item = 0, s = 0, slot = 0;
-    int k = -1, galign = 0, total_c = 0, fbase = -16;
+    int k = -1, galign = 0, total_c = 0;
+    int fcur = -1;       // aligned coordinate of the next raw byte the read-ahead takes
+    int lo_blk = 0;      // lowest 16-byte block in the ring (blocks lo_blk and lo_blk + 1 are there)
     const uint8_t* ga = nullptr;
     uint32_t* wend = nullptr;
     uint8_t* tend = nullptr;
-    uint4 fb = make_uint4(0, 0, 0, 0);
     if (slot_i < A.n) {
       item = A.sort_order[slot_i];
       if (A.pflag[item] == 0) {
@@ -223,30 +237,37 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
         }
       }
     }
-    // raw character at aligned coordinate x (16-byte blocks, loaded as the cursor walks left)
-    auto fetch = [&](int x) -> uint32_t {
-      if ((x & ~15) != fbase) {
-        fbase = x & ~15;
-        fb = pipe_load16(ga, fbase, total_c);
-        if (want_ascii) {
-          uint32_t m0 = fb.x, m1 = fb.y, m2 = fb.z, m3 = fb.w;
-          if (fbase == 0 && galign) {            // bytes before the string start are foreign
-            uint32_t t[4] = {m0, m1, m2, m3};
-            for (int j = 0; j < galign; j++) t[j >> 2] &= ~(0xFFu << (8 * (j & 3)));
-            m0 = t[0]; m1 = t[1]; m2 = t[2]; m3 = t[3];
-          }
-          if ((m0 | m1 | m2 | m3) & 0x80808080u) bad = true;
-        }
-        if (to_lower) { fb.x = pipe_lower4(fb.x); fb.y = pipe_lower4(fb.y); fb.z = pipe_lower4(fb.z); fb.w = pipe_lower4(fb.w); }
+    // 16 raw bytes of block blk -> the ring (bytes behind the end of the string read as 0)
+    auto load_block = [&](int blk) {
+      const int c0 = blk << 4;
+      const uint32_t dst = ring_b + uint32_t((blk & 1) * 4) * 128u;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int left = total_c - (c0 + 4 * j);
+        pipe_cp_async4(dst + uint32_t(j) * 128u, ga + c0 + 4 * j, left >= 4 ? 4 : (left > 0 ? left : 0));
       }
-      return (pipe_word_of(fb, (x >> 2) & 3) >> (8 * (x & 3))) & 0xFFu;
     };
-    // read-ahead of the three characters the encoder looks at: k, k-1, k-2
-    uint32_t c0 = 0, c1 = 0, c2 = 0;
-    if (active) {
-      if (k >= 0) c0 = fetch(galign + k);
-      if (CAP && k >= 1) c1 = fetch(galign + k - 1);
-      if (CAP && k >= 2) c2 = fetch(galign + k - 2);
+    // the raw character at coordinate fcur, with its class: character | class << 8
+    auto take = [&]() -> uint32_t {
+      const int x = fcur--;
+      if ((x & 15) == 15) pipe_cp_async_wait();   // entering a block: its copy was issued long ago
+      uint32_t b;
+      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(ring_b + uint32_t((x >> 2) & 7) * 128u + uint32_t(x & 3)));
+      if (want_ascii && (b & 0x80u)) bad = true;
+      if (to_lower && b - 'A' < 26u) b |= 0x20u;
+      return b | (uint32_t(s_cls[b]) << 8);
+    };
+    uint32_t x0 = 0, x1 = 0, x2 = 0;   // read-ahead: characters k, k-1, k-2
+    if (active && k >= 0) {
+      const int top = (total_c - 1) >> 4;
+      load_block(top);
+      if (top > 0) load_block(top - 1);
+      lo_blk = top > 0 ? top - 1 : 0;
+      pipe_cp_async_wait();
+      fcur = total_c - 1;
+      x0 = take();
+      if (CAP && k >= 1) x1 = take();
+      if (CAP && k >= 2) x2 = take();
     }
     RevCap e;
     revcap_reset(e);
@@ -256,74 +277,79 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
     uint4 wbuf = make_uint4(0, 0, 0, 0);
 
     while (__any_sync(FULL, active)) {
-      if (!active) continue;
-      if (qn == 0) {
-        if (k < 0 || bad) {
-          // ---- the string is done: the last (partial) group of words, the verdict --------------
-          const uint32_t r = dist & 3u;
-          if (!bad && r) {
-            uint32_t* d = wend - dist;
-            d[0] = wbuf.x;
-            if (r > 1) d[1] = wbuf.y;
-            if (r > 2) d[2] = wbuf.z;
-          }
-          A.nlen[item] = bad ? 0u : dist;
-          A.pflag[item] = bad ? 1 : 0;
-          if (bad) { A.counts[s] = 0; A.need[s] = 0; A.missing[s] = 0; A.status[s] = 13; }
-          active = false;
-          continue;
+      // ---- ring refill, all lanes of the warp together ----------------------------------------
+      const bool want = active && lo_blk > 0 && fcur >= galign && (fcur >> 4) <= lo_blk;
+      if (__any_sync(FULL, want && (fcur & 15) <= 8)) {
+        if (want) {
+          lo_blk--;
+          load_block(lo_blk);
         }
-        if (CAP) {
-          qn = revcap_step(e, s_cls, c0, c1, c2, k,
-                           [&](int j) -> uint32_t {
-                             uint32_t x = ga[galign + j];
-                             if (to_lower && x - 'A' < 26u) x |= 0x20u;
-                             return x;
-                           },
-                           &qbytes);
-          c0 = c1;
-          c1 = c2;
-          c2 = (k >= 3) ? fetch(galign + k - 3) : 0u;
-        } else {
-          qbytes = c0;
-          qn = 1;
-          c0 = (k >= 1) ? fetch(galign + k - 1) : 0u;
-        }
-        k--;
-        if (bad) continue;
       }
-      if (qn != 0) {
-        const uint32_t b = (qbytes >> (8u * (qn - 1u))) & 0xFFu;
-        qn--;
-        if (dist >= slot) {   // more text than the slot holds: redone with a full-size slot
-          over = true;
-          A.nlen[item] = 0;
-          A.pflag[item] = 3;
-          A.counts[s] = 0; A.need[s] = 0; A.missing[s] = 0; A.status[s] = 14;
-          active = false;
-          continue;
+      if (active) {
+        if (qn == 0 || bad) {
+          if (k < 0 || bad) {
+            // ---- the string is done: the last (partial) group of words, the verdict ------------
+            const uint32_t r = dist & 3u;
+            if (!bad && r) {
+              uint32_t* d = wend - dist;
+              d[0] = wbuf.x;
+              if (r > 1) d[1] = wbuf.y;
+              if (r > 2) d[2] = wbuf.z;
+            }
+            A.nlen[item] = bad ? 0u : dist;
+            A.pflag[item] = bad ? 1 : 0;
+            if (bad) { A.counts[s] = 0; A.need[s] = 0; A.missing[s] = 0; A.status[s] = 13; }
+            active = false;
+          } else if (CAP) {
+            qn = revcap_step(e, s_lut, x0, x1, x2, k,
+                             [&](int j) -> uint32_t {
+                               uint32_t c = ga[galign + j];
+                               if (to_lower && c - 'A' < 26u) c |= 0x20u;
+                               return s_cls[c];
+                             },
+                             &qbytes);
+            x0 = x1;
+            x1 = x2;
+            x2 = (k >= 3) ? take() : 0u;
+            k--;
+          } else {
+            qbytes = x0 & 0xFFu;
+            qn = 1;
+            x0 = (k >= 1) ? take() : 0u;
+            k--;
+          }
         }
-        if (dist == 0) {
-          packed = s_d1[b];
-        } else {
-          packed = dfa_next(packed, prev, b, D.shift, D.mask,
-                            [&](uint32_t i, uint4* kk, uint4* vv) { pipe_load32(D.buckets + 2 * i, kk, vv); },
-                            [&](uint32_t i) { return __ldg(&D.d2[i]); });
+        if (active && qn != 0 && !bad) {
+          const uint32_t b = (qbytes >> (8u * (qn - 1u))) & 0xFFu;
+          qn--;
+          if (dist >= slot) {   // more text than the slot holds: redone with a full-size slot
+            A.nlen[item] = 0;
+            A.pflag[item] = 3;
+            A.counts[s] = 0; A.need[s] = 0; A.missing[s] = 0; A.status[s] = 14;
+            active = false;
+          } else {
+            if (dist == 0) {
+              packed = s_d1[b];
+            } else {
+              packed = dfa_next(packed, prev, b, D.shift, D.mask,
+                                [&](uint32_t i, uint4* kk, uint4* vv) { pipe_load32(D.buckets + 2 * i, kk, vv); },
+                                [&](uint32_t i) { return __ldg(&D.d2[i]); });
+            }
+            const uint32_t code = s_code[b];
+            const uint32_t w = position_word(packed, code, tr, voff);
+            trail_push(tr, code);
+            prev = b;
+            dist++;
+            if (TEXT) tend[-int64_t(dist)] = uint8_t(b);
+            wbuf.w = wbuf.z;
+            wbuf.z = wbuf.y;
+            wbuf.y = wbuf.x;
+            wbuf.x = w;
+            if ((dist & 3u) == 0) *reinterpret_cast<uint4*>(wend - dist) = wbuf;
+          }
         }
-        const uint32_t code = s_code[b];
-        const uint32_t w = position_word(packed, code, tr, voff);
-        trail_push(tr, code);
-        prev = b;
-        dist++;
-        if (TEXT) tend[-int64_t(dist)] = uint8_t(b);
-        wbuf.w = wbuf.z;
-        wbuf.z = wbuf.y;
-        wbuf.y = wbuf.x;
-        wbuf.x = w;
-        if ((dist & 3u) == 0) *reinterpret_cast<uint4*>(wend - dist) = wbuf;
       }
     }
-    (void)over;
   }
 }
 
@@ -335,7 +361,7 @@ template <bool STORE>
 __global__ void __launch_bounds__(kPipeBlock) chain_kernel(const TokenizeArgs A) {
   constexpr unsigned FULL = 0xFFFFFFFFu;
   ChainTables T;
-  T.rec = A.v.rec;
+  T.crec = A.v.dfa.crec;
   T.hot = A.v.dfa.hot;
   T.delete_token = A.v.delete_token;
   T.unk = A.v.unk;
@@ -393,7 +419,7 @@ __global__ void __launch_bounds__(kPipeBlock) chain_kernel(const TokenizeArgs A)
       }
       uint32_t stored = z.cnt;   // ids stored so far follow the lane's own count
       chain_step(
-          T, S, z, two_ids, [&](uint32_t idx, uint4* r0, uint4* r1) { pipe_load32(T.rec + 2 * idx, r0, r1); },
+          T, S, z, two_ids, [&](const uint4* tab, uint32_t idx, uint4* a, uint4* b) { pipe_load32(tab + 2 * idx, a, b); },
           [&](uint32_t id, uint32_t, uint32_t adv) {
             if (!STORE && A.scores) atomicAdd(&A.scores[id], static_cast<unsigned long long>(adv));
             if (STORE && stored < cap) A.slab[slab_base + stored] = id;

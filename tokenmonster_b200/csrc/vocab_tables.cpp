@@ -38,8 +38,21 @@ struct KeyRef {
 };
 
 // Reversed-key Aho-Corasick automaton in DFA form (vocab_tables.h describes the tables).
+// score parts (pipeline_core.h, stage 3)
+static int score_a(uint32_t aflag, int nwords, int fd) {
+  const int nw = nwords - fd;
+  return int(aflag >> 7) + (nw > 1 ? nw - 1 : 0) + 100 * nw;
+}
+static int score_b(uint32_t bflag, int bnw, int nb, bool retry) {
+  int s = int(bflag >> 7) + (bnw > 1 ? bnw - 1 : 0) + ((nb >> 2) & 1) + 100 * (bnw + (nb >> 3)) - 3 * int(bflag & 1u & uint32_t(nb));
+  return retry ? s - 1 : s + int((bflag >> 2) & 1u);
+}
+static uint32_t pack_i16(int lo, int hi) { return (uint32_t(lo) & 0xFFFFu) | (uint32_t(hi) << 16); }
+
 static int build_dfa(HostTables* t, const std::vector<KeyRef>& keys, const std::vector<uint8_t>& blob,
-                     const std::vector<uint8_t>& flag, const std::vector<uint8_t>& nwords, std::string* err) {
+                     const std::vector<uint8_t>& flag, const std::vector<uint8_t>& nwords,
+                     const std::vector<uint32_t>& alt, const std::vector<uint32_t>& alt2, const std::vector<uint32_t>& id,
+                     std::string* err) {
   for (int b = 0; b < 256; b++) {
     const uint8_t v = t->begin_byte[b];   // go:3780-3787 writes only these four values
     if (v == 0) t->class_code[b] = 0;
@@ -160,14 +173,41 @@ static int build_dfa(HostTables* t, const std::vector<KeyRef>& keys, const std::
   t->dfa_d2.assign(65536, 0);
   for (uint32_t prev = 0; prev < 256; prev++)
     for (uint32_t b = 0; b < 256; b++) t->dfa_d2[(prev << 8) | b] = pack(delta(d1[prev], b));
-  t->dfa_hot.assign(size_t(N) * 4, 0);
+  static const int kClassValue[4] = {0, 1, 10, 12};
+  t->dfa_hot.assign(size_t(N) * 8, 0);
   for (uint32_t s = 0; s < N; s++) {
-    uint32_t* h = &t->dfa_hot[size_t(s) * 4];
+    uint32_t* h = &t->dfa_hot[size_t(s) * 8];
     const uint32_t bi = best_len[s] ? best_idx[s] : 0u, si = sp_len[s] ? sp_idx[s] : 0u;
+    const uint32_t bf = best_len[s] ? flag[bi] : 0u, sf = sp_len[s] ? flag[si] : 0u;
+    const int bn = best_len[s] ? nwords[bi] : 0, sn = sp_len[s] ? nwords[si] : 0;
     h[0] = bi | (uint32_t(best_len[s]) << 24);
     h[1] = si | (uint32_t(sp_len[s]) << 24);
-    h[2] = (best_len[s] ? (uint32_t(flag[bi]) | (uint32_t(nwords[bi]) << 8)) : 0u) |
-           (sp_len[s] ? ((uint32_t(flag[si]) << 16) | (uint32_t(nwords[si]) << 24)) : 0u);
+    h[2] = ((bf >> 1) & 1u) | (((bf >> 4) & 1u) << 1) | ((((bf & 2u) != 0 && bn == 0) ? 1u : 0u) << 2) | (((sf >> 4) & 1u) << 3);
+    int bp[4], br[4];
+    for (int c = 0; c < 4; c++) {
+      bp[c] = score_b(bf, bn, kClassValue[c], false);
+      br[c] = score_b(sf, sn, kClassValue[c], true);
+    }
+    h[4] = pack_i16(bp[0], bp[1]);
+    h[5] = pack_i16(bp[2], bp[3]);
+    h[6] = pack_i16(br[0], br[1]);
+    h[7] = pack_i16(br[2], br[3]);
+  }
+  // chain records: ids, alternative lengths, first-token score parts (forward delete 0 / 1)
+  t->chain_rec.assign(size_t(t->n_info) * 8, 0);
+  for (uint32_t i = 0; i < t->n_info; i++) {
+    uint32_t* r = &t->chain_rec[size_t(i) * 8];
+    const bool h1 = alt[i] != kDNE, h2 = alt2[i] != kDNE;
+    const uint32_t f0 = flag[i], f1 = h1 ? flag[alt[i]] : 0u, f2 = h2 ? flag[alt2[i]] : 0u;
+    const int n0 = nwords[i], n1 = h1 ? nwords[alt[i]] : 0, n2 = h2 ? nwords[alt2[i]] : 0;
+    const uint32_t bits = (f0 & 1u) | (((f0 >> 3) & 1u) << 1) | (((f0 >> 5) & 1u) << 2) | ((f1 & 1u) << 3) |
+                          (((f1 >> 3) & 1u) << 4) | ((f2 & 1u) << 5) | (((f2 >> 3) & 1u) << 6);
+    r[0] = id[i] | (bits << 24);
+    r[1] = (h1 ? id[alt[i]] : 0u) | (uint32_t(h1 ? keys[alt[i]].len : 0) << 24);
+    r[2] = (h2 ? id[alt2[i]] : 0u) | (uint32_t(h2 ? keys[alt2[i]].len : 0) << 24);
+    r[3] = pack_i16(score_a(f0, n0, 0), score_a(f0, n0, 1));
+    r[4] = pack_i16(score_a(f1, n1, 0), score_a(f1, n1, 1));
+    r[5] = pack_i16(score_a(f2, n2, 0), score_a(f2, n2, 1));
   }
   // ---- hashed transitions to depth >= 3 ----------------------------------------------------
   size_t n_deep = 0;
@@ -216,7 +256,7 @@ int host_dfa_lookup(const HostTables& h, const uint8_t* window, int n, uint32_t*
                    [&](uint32_t i, uint4* k, uint4* v) { *k = bk[2 * i]; *v = bk[2 * i + 1]; },
                    [&](uint32_t i) { return h.dfa_d2[i]; });
   }
-  const uint32_t* hot = &h.dfa_hot[size_t(w & kDfaStateMask) * 4];
+  const uint32_t* hot = &h.dfa_hot[size_t(w & kDfaStateMask) * 8];
   if (index) *index = hot[0] & 0xFFFFFFu;
   if (sp_index) *sp_index = hot[1] & 0xFFFFFFu;
   if (sp_len) *sp_len = int(dfa_splen(w));
@@ -405,7 +445,7 @@ int parse_vocab(const uint8_t* file, size_t n, HostTables* t, std::string* err) 
   }
   for (uint32_t b = 0; b < 256; b++)
     t->sp_child[b] = t->space_start == kNone ? kNone : child_of(t->space_start & 0xFFFFFFu, b);
-  return build_dfa(t, keys, blob, flag, nwords, err);
+  return build_dfa(t, keys, blob, flag, nwords, alt, alt2, id, err);
 }
 
 // spaced: 0 plain window, 1 window behind the virtual space; +2 = take the first steps from the

@@ -61,15 +61,23 @@ struct HostTables {
   //   dfa_buckets          hashed (state<<8|b) -> packed target for targets at depth >= 3;
   //                        32-byte buckets of 4 keys + 4 values, bit 31 of key 0 = "overflowed
   //                        into the next bucket", empty key = kDfaEmpty
-  //   dfa_hot[state]       what the chain stage reads per look-ahead position (4 x u32):
+  //   dfa_hot[state]       state record, what the chain stage reads per look-ahead position (8 x u32):
   //                        w0 = best index | best_len<<24, w1 = sp index | sp_len<<24,
-  //                        w2 = best.flag | best.nWords<<8 | sp.flag<<16 | sp.nWords<<24, w3 = 0
+  //                        w2 = bit 0 best.flag>>1, bit 1 best.flag>>4, bit 2 retry eligible (best
+  //                        begins with a letter and has no word boundary, go:1088), bit 3 sp.flag>>4,
+  //                        w4,w5 = B(best, nb) for the four classes nb, int16 each,
+  //                        w6,w7 = B(sp, nb) of the retry, int16 each (pipeline_core.h, stage 3)
+  //   chain_rec[index]     chain record (8 x u32): w0 = id | bits<<24 (flag&1, flag>>3, flag>>5 of the
+  //                        token, then flag&1, flag>>3 of alternative 1 and 2), w1 = id1 | alt_len1<<24,
+  //                        w2 = id2 | alt_len2<<24, w3..w5 = A(token / alt 1 / alt 2, forward delete
+  //                        0 | 1) as int16 pairs
   uint32_t dfa_states = 0;
   uint32_t dfa_bits = 0;
   std::vector<uint32_t> dfa_buckets;
   std::vector<uint32_t> dfa_d2;
   uint32_t dfa_d1[256];
   std::vector<uint32_t> dfa_hot;
+  std::vector<uint32_t> chain_rec;
   uint8_t class_code[256];       // begin_byte as a 2-bit code: 0 -> 0, 1 -> 1, 10 -> 2, 12 -> 3
 
   // reverse table for decode: reverse[id] = LAST record with that id (go:2715)
