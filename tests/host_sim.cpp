@@ -50,9 +50,8 @@ Tabled table(const Sim& S, const uint8_t* raw, int n, bool cap, bool to_lower, b
   trail_reset(tr, t.class_code[0]);
   RevCap e;
   revcap_reset(e);
-  uint32_t packed = 0, prev = 0, qbytes = 0, qn = 0;
+  uint32_t packed = 0, qbytes = 0, qn = 0;
   int k = n - 1;
-  bool first = true;
   while (k >= 0 || qn) {
     if (qn == 0) {
       auto xc = [&](int j) -> uint32_t { const uint32_t c = at(j); return c | (pc_class_sp(c) << 8); };
@@ -64,17 +63,13 @@ Tabled table(const Sim& S, const uint8_t* raw, int n, bool cap, bool to_lower, b
     }
     const uint32_t b = (qbytes >> (8 * (qn - 1))) & 0xFFu;
     qn--;
-    if (first) packed = t.dfa_d1[b];
-    else
-      packed = dfa_next(packed, prev, b, 32u - t.dfa_bits, (1u << t.dfa_bits) - 1u,
-                        [&](uint32_t i, uint4* kk, uint4* v) { *kk = bk[2 * i]; *v = bk[2 * i + 1]; },
-                        [&](uint32_t i) { return t.dfa_d2[i]; });
-    first = false;
+    packed = dfa_next(packed, b, 32u - t.dfa_bits, (1u << t.dfa_bits) - 1u,
+                      [&](uint32_t i, uint4* kk, uint4* v) { *kk = bk[2 * i]; *v = bk[2 * i + 1]; },
+                      [&](uint32_t c) { return t.dfa_d1[c]; });
     const uint32_t code = t.class_code[b];
     R.words.push_back(position_word(packed, code, tr, off));
     R.text.push_back(uint8_t(b));
     trail_push(tr, code);
-    prev = b;
   }
   std::reverse(R.words.begin(), R.words.end());
   std::reverse(R.text.begin(), R.text.end());

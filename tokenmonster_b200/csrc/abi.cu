@@ -127,7 +127,6 @@ extern "C" int tmgpu_vocab_create(const uint8_t* file_bytes, size_t n, int devic
     const uint32_t* bk = nullptr;
     const uint32_t* hot = nullptr;
     if ((rc = upload(v, h.dfa_buckets.data(), h.dfa_buckets.size(), &bk))) return fail(rc);
-    if ((rc = upload(v, h.dfa_d2.data(), h.dfa_d2.size(), &d.dfa.d2))) return fail(rc);
     if ((rc = upload(v, h.dfa_hot.data(), h.dfa_hot.size(), &hot))) return fail(rc);
     const uint32_t* crec = nullptr;
     if ((rc = upload(v, h.chain_rec.data(), h.chain_rec.size(), &crec))) return fail(rc);

@@ -27,7 +27,6 @@ TM_HD uint32_t dfa_hash(uint32_t key, uint32_t shift) { return (key * 0x9E3779B1
 
 struct DfaDev {
   const uint4* buckets;      // 2 x uint4 per bucket: keys, values
-  const uint32_t* d2;        // 65536
   const uint4* hot;          // 2 per state
   const uint4* crec;         // 2 per dictionary index
   uint32_t shift;            // 32 - log2(buckets)
@@ -35,27 +34,27 @@ struct DfaDev {
   uint32_t n_states;
 };
 
-// One transition: the packed state after consuming byte b (previous text byte `prev`) from the
-// state in `packed`.  load_bucket(h, &keys, &vals) reads the 32-byte bucket h, d2(i) entry i of dfa_d2.
-template <class LoadBucket, class LoadD2>
-TM_HD uint32_t dfa_next(uint32_t packed, uint32_t prev, uint32_t b, uint32_t shift, uint32_t mask,
-                        LoadBucket load_bucket, LoadD2 d2) {
+// One transition: the packed state after consuming byte b from the state in `packed`.
+// load_bucket(h, &keys, &vals) reads the 32-byte bucket h; d1(b) = the packed state one byte below
+// the root (every transition whose target is at depth <= 1 depends on the byte alone).
+// Straight-line code: the four key compares are selects; the loop only runs again for a key that
+// was pushed into the next bucket at build time (~1 % of the buckets are full).
+template <class LoadBucket, class LoadD1>
+TM_HD uint32_t dfa_next(uint32_t packed, uint32_t b, uint32_t shift, uint32_t mask, LoadBucket load_bucket, LoadD1 d1) {
   const uint32_t s = packed & kDfaStateMask;
-  if (s != 0) {   // the root has no transition to depth >= 3
-    const uint32_t key = (s << 8) | b;
-    uint32_t h = dfa_hash(key, shift);
-    for (;;) {
-      uint4 k, v;
-      load_bucket(h, &k, &v);
-      if ((k.x & ~kDfaOverflow) == key) return v.x;
-      if (k.y == key) return v.y;
-      if (k.z == key) return v.z;
-      if (k.w == key) return v.w;
-      if (!(k.x & kDfaOverflow)) break;
-      h = (h + 1) & mask;
-    }
+  const uint32_t key = (s << 8) | b;
+  uint32_t h = dfa_hash(key, shift);
+  uint32_t res = d1(b);
+  bool more = (s != 0);   // the root has no transition to depth >= 2
+  while (more) {
+    uint4 k, v;
+    load_bucket(h, &k, &v);
+    const bool h0 = (k.x & ~kDfaOverflow) == key, h1 = k.y == key, h2 = k.z == key, h3 = k.w == key;
+    res = h0 ? v.x : (h1 ? v.y : (h2 ? v.z : (h3 ? v.w : res)));
+    more = !(h0 | h1 | h2 | h3) & ((k.x & kDfaOverflow) != 0);
+    h = (h + 1) & mask;
   }
-  return d2((prev << 8) | b);
+  return res;
 }
 
 // Everything a kernel needs about one vocabulary (device pointers + scalars).

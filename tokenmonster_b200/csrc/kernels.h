@@ -154,8 +154,8 @@ cudaError_t launch_decode_copy(const VocabDev& v, const uint8_t* tokens, const i
                                const uint64_t* raw_off, uint8_t* out, int sms, cudaStream_t st,
                                const uint64_t* prefix_off = nullptr, const uint8_t* prefix = nullptr);
 cudaError_t launch_capcode_decode(const uint8_t* src, const uint64_t* raw_off, uint32_t n, uint8_t* dst,
-                                  uint32_t* out_len, int sms, cudaStream_t st, const uint32_t* len_in = nullptr,
-                                  uint8_t* state = nullptr, const UnicodeDev* uni = nullptr);
+                                  uint32_t* out_len, int sms, cudaStream_t st, const uint32_t* len_in,
+                                  uint8_t* state, const UnicodeDev* uni, uint32_t* counter);
 cudaError_t launch_stream_tail(const uint8_t* raw, const uint64_t* raw_off, uint32_t n, int charset,
                                uint32_t* keep_len, uint32_t* rem_len, int sms, cudaStream_t st);
 cudaError_t launch_copy_tail(const uint8_t* raw, const uint64_t* raw_off, const uint32_t* keep_len,

@@ -113,23 +113,20 @@ TM_HD uint32_t revcap_step(RevCap& e, const uint32_t* lut, uint32_t x0, uint32_t
   const uint32_t cl = x0 >> 8;
   const uint32_t cl1 = (k >= 1) ? (x1 >> 8) : uint32_t(PC_O);
   const uint32_t cl2 = (k >= 2) ? (x2 >> 8) : uint32_t(PC_O);
-  bool in_word;
-  if (cl1 != PC_N && cl1 != PC_A) {        // also k == 0: no left neighbour counts as "other"
-    in_word = (cl1 == PC_U);
-    e.iw_valid = false;
-  } else {
-    if (!e.iw_valid) {
-      uint32_t x = cl2;
-      int j = k - 2;
-      while ((x == PC_N || x == PC_A) && j > 0) {
-        j--;
-        x = class_at(j);
-      }
-      e.iw = (k >= 2) && (x == PC_U);
-      e.iw_valid = true;
+  // inside a capitalised run?  Decided by the left neighbour unless that is a digit / apostrophe;
+  // then one look-back (rare) answers for the whole run of digits / apostrophes
+  const bool run1 = (cl1 == PC_N) | (cl1 == PC_A);
+  if (run1 & !e.iw_valid) {
+    uint32_t x = cl2;
+    int j = k - 2;
+    while ((x == PC_N || x == PC_A) && j > 0) {
+      j--;
+      x = class_at(j);
     }
-    in_word = e.iw;
+    e.iw = (k >= 2) && (x == PC_U);
   }
+  e.iw_valid = run1;
+  const bool in_word = run1 ? e.iw : (cl1 == PC_U);
   const uint32_t idx = cl | (cl1 << 3) | (uint32_t(cl2 == PC_U || cl2 == PC_L) << 6) | (uint32_t(in_word) << 7) |
                        (uint32_t(e.nlo == PC_L) << 8) | (uint32_t(e.has_right && e.clr == PC_U) << 9);
   const uint32_t a = lut[idx];
@@ -138,8 +135,7 @@ TM_HD uint32_t revcap_step(RevCap& e, const uint32_t* lut, uint32_t x0, uint32_t
   *out = (a & 0xFFFFFFu) | (eaten ? 0u : (ch << (8u * np)));
   e.clr = cl;
   e.has_right = true;
-  if (cl == PC_L) e.nlo = PC_L;
-  else if (cl == PC_O || cl == PC_S) e.nlo = PC_O;
+  e.nlo = (cl == PC_L) ? uint32_t(PC_L) : ((cl == PC_O) | (cl == PC_S) ? uint32_t(PC_O) : e.nlo);
   return np + 1u - eaten;
 }
 

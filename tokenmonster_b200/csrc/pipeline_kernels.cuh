@@ -250,10 +250,17 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
     // the raw character at coordinate fcur, with its class: character | class << 8
     auto take = [&]() -> uint32_t {
       const int x = fcur--;
-      if ((x & 15) == 15) pipe_cp_async_wait();   // entering a block: its copy was issued long ago
       uint32_t b;
-      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(ring_b + uint32_t((x >> 2) & 7) * 128u + uint32_t(x & 3)));
-      if (want_ascii && (b & 0x80u)) bad = true;
+      // entering a block (x & 15 == 15): wait for its copy, which was issued long ago; then one byte
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "setp.eq.u32 p, %2, 15;\n\t"
+          "@p cp.async.wait_all;\n\t"
+          "ld.shared.u8 %0, [%1];\n\t}"
+          : "=r"(b)
+          : "r"(ring_b + uint32_t((x >> 2) & 7) * 128u + uint32_t(x & 3)), "r"(uint32_t(x) & 15u)
+          : "memory");
+      bad = bad | (want_ascii & ((b & 0x80u) != 0));
       if (to_lower && b - 'A' < 26u) b |= 0x20u;
       return b | (uint32_t(s_cls[b]) << 8);
     };
@@ -273,7 +280,7 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
     revcap_reset(e);
     ClassTrail tr;
     trail_reset(tr, code0);
-    uint32_t packed = 0, prev = 0, qbytes = 0, qn = 0, dist = 0;
+    uint32_t packed = 0, qbytes = 0, qn = 0, dist = 0;
     uint4 wbuf = make_uint4(0, 0, 0, 0);
 
     while (__any_sync(FULL, active)) {
@@ -328,24 +335,25 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
             A.counts[s] = 0; A.need[s] = 0; A.missing[s] = 0; A.status[s] = 14;
             active = false;
           } else {
-            if (dist == 0) {
-              packed = s_d1[b];
-            } else {
-              packed = dfa_next(packed, prev, b, D.shift, D.mask,
-                                [&](uint32_t i, uint4* kk, uint4* vv) { pipe_load32(D.buckets + 2 * i, kk, vv); },
-                                [&](uint32_t i) { return __ldg(&D.d2[i]); });
-            }
+            packed = dfa_next(packed, b, D.shift, D.mask,
+                              [&](uint32_t i, uint4* kk, uint4* vv) { pipe_load32(D.buckets + 2 * i, kk, vv); },
+                              [&](uint32_t c) { return s_d1[c]; });
             const uint32_t code = s_code[b];
             const uint32_t w = position_word(packed, code, tr, voff);
             trail_push(tr, code);
-            prev = b;
             dist++;
             if (TEXT) tend[-int64_t(dist)] = uint8_t(b);
             wbuf.w = wbuf.z;
             wbuf.z = wbuf.y;
             wbuf.y = wbuf.x;
             wbuf.x = w;
-            if ((dist & 3u) == 0) *reinterpret_cast<uint4*>(wend - dist) = wbuf;
+            // every 4th word: one 16-byte store (predicated, not a branch: the lanes' phases differ)
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.eq.u32 p, %5, 0;\n\t"
+                "@p st.global.v4.u32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(wend - dist),
+                "r"(wbuf.x), "r"(wbuf.y), "r"(wbuf.z), "r"(wbuf.w), "r"(dist & 3u)
+                : "memory");
           }
         }
       }

@@ -1,33 +1,26 @@
-// tokenize_thread_kernel.cuh -- K1/K3, mapping 2: ONE LANE PER STRING, warp-synchronous phases.
+// tokenize_thread_kernel.cuh -- the round-1 trie-walk kernel, kept for ONE job: the speculative
+// chunks of long documents (chunking.cuh; instantiated with CHUNK = true only).  Batches of
+// ordinary strings run the position-table pipeline (pipeline_kernels.cuh), which is 2.8x faster
+// per byte but walks a string with one lane from end to end; a batch of a few huge documents
+// needs parallelism INSIDE a document, and this kernel's step log (position, forward-delete flag
+// per emitted id) is what the stitcher joins chunks on.
 //
-// Why a second mapping.  ncu on the lanes-over-branches kernel (tokenize_kernel.cuh, profiles/
-// r01_v5_g4_*) shows ~330 warp instructions per emitted id with 8.6 of 32 lanes active: every
-// trie walk of a step runs until the LONGEST of the concurrent walks ends, and the tail of that
-// distribution (a 15-byte word) sets the pace while most lanes finished after 3 bytes.  The walks
-// of one string cannot be overlapped with its own next step (the branch chosen at step k fixes
-// the position of step k+1: go/tokenmonster.go:1217-1262), so the only way to keep lanes busy is
-// to give every lane its OWN string and its own little queue of walks, and to let all 32 lanes
-// drain their queues in one shared loop:
-//
-//   per warp iteration (= one token step for each of 32 strings)
+// One lane per chunk, warp-synchronous phases per token step:
 //     FILL   each lane tops up its normalized-text ring (capcode level 2 encoded on the fly by a
 //            branch-free, forward-looking restatement of javascript/tokenmonster.js:900-1005)
 //     WALK 1 one loop, one copy of the trie-step code: a lane pops its next look-ahead position
 //            (after the longest token / alternative 1 / alternative 2: go:1068,1113,1165) the
-//            moment its previous walk ends, so the loop runs for max(sum of a lane's depths), not
-//            for 3 x max(depth)
-//     SCORE  uniform straight-line code for the three plain candidates (go:1075-1133)
+//            moment its previous walk ends; the walks of all 32 lanes go into one pool that idle
+//            lanes take from by ballot rank
+//     SCORE  straight-line code for the three plain candidates (go:1075-1133)
 //     WALK 2 same loop for the " "-prefixed retries that the plain results ask for (go:1088-1107)
 //     PICK   first maximum in the order s1,s2,s3,s1b,s2b,s3b (go:1217-1262), emit, advance
 //
 // Memory system: normalized text lives in shared-memory rings interleaved word-by-word across the
-// lanes of a warp (word w of lane t at ring[w*32+t]: 32 strings read their own bytes with zero
-// bank conflicts); trie edges (8 bytes each, L2-resident table at load factor <= 1/4) are read
-// through the read-only path behind an 8-bit child-byte filter kept in the parent's value, which
-// answers most "no such child" steps without a load (a CTA-shared software cache in shared
-// memory was measured slower: its miss path diverges, profiles/r01_v6_*); first-byte table,
-// beginByte and the character-class table are staged once per CTA by a TMA bulk copy; strings
-// are pulled from a global work counter by each lane.
+// lanes of a warp; trie edges (8 bytes each, L2-resident hashed table at load factor <= 1/4) are
+// read through the read-only path behind an 8-bit child-byte filter kept in the parent's value;
+// first-byte table, beginByte and the character-class table are staged once per CTA by a TMA bulk
+// copy; chunks are pulled from a global work counter by each lane.
 // Reference semantics: go/tokenmonster.go:242-253 + :1017-1279 (ids) / :1281-1543 (count).
 #pragma once
 #include <cuda_runtime.h>
@@ -36,7 +29,7 @@
 
 #include "device_tables.h"
 #include "kernels.h"
-#include "tokenize_kernel.cuh"  // stage_tables_tma, lower4, smem layout constants
+#include "chunk_kernel_helpers.cuh"  // stage_tables_tma, lower4, smem layout constants
 
 namespace tmgpu {
 

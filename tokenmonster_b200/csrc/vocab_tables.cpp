@@ -170,9 +170,6 @@ static int build_dfa(HostTables* t, const std::vector<KeyRef>& keys, const std::
   }
   auto pack = [&](uint32_t s) { return s | (uint32_t(best_len[s]) << 20) | (uint32_t(sp_len[s]) << 26); };
   for (int b = 0; b < 256; b++) t->dfa_d1[b] = pack(d1[b]);
-  t->dfa_d2.assign(65536, 0);
-  for (uint32_t prev = 0; prev < 256; prev++)
-    for (uint32_t b = 0; b < 256; b++) t->dfa_d2[(prev << 8) | b] = pack(delta(d1[prev], b));
   static const int kClassValue[4] = {0, 1, 10, 12};
   t->dfa_hot.assign(size_t(N) * 8, 0);
   for (uint32_t s = 0; s < N; s++) {
@@ -209,11 +206,9 @@ static int build_dfa(HostTables* t, const std::vector<KeyRef>& keys, const std::
     r[4] = pack_i16(score_a(f1, n1, 0), score_a(f1, n1, 1));
     r[5] = pack_i16(score_a(f2, n2, 0), score_a(f2, n2, 1));
   }
-  // ---- hashed transitions to depth >= 3 ----------------------------------------------------
+  // ---- hashed transitions to depth >= 2 (every row entry) -----------------------------------
   size_t n_deep = 0;
-  for (uint32_t s = 1; s < N; s++)
-    for (uint32_t e : row[s])
-      if (nodes[e & 0xFFFFFFu].depth >= 3) n_deep++;
+  for (uint32_t s = 1; s < N; s++) n_deep += row[s].size();
   uint32_t bits = 4;
   while ((size_t(1) << bits) * 2 < n_deep) bits++;   // on average <= 2 of 4 slots used
   t->dfa_bits = bits;
@@ -224,7 +219,6 @@ static int build_dfa(HostTables* t, const std::vector<KeyRef>& keys, const std::
   for (uint32_t s = 1; s < N; s++) {
     for (uint32_t e : row[s]) {
       const uint32_t tgt = e & 0xFFFFFFu;
-      if (nodes[tgt].depth < 3) continue;
       const uint32_t key = (s << 8) | (e >> 24);
       uint32_t h = dfa_hash(key, shift);
       for (;;) {
@@ -250,11 +244,9 @@ int host_dfa_lookup(const HostTables& h, const uint8_t* window, int n, uint32_t*
   const uint4* bk = reinterpret_cast<const uint4*>(h.dfa_buckets.data());
   uint32_t w = 0;
   for (int p = n - 1; p >= 0; p--) {
-    if (p == n - 1) w = h.dfa_d1[window[p]];
-    else
-      w = dfa_next(w, window[p + 1], window[p], 32u - h.dfa_bits, (1u << h.dfa_bits) - 1u,
-                   [&](uint32_t i, uint4* k, uint4* v) { *k = bk[2 * i]; *v = bk[2 * i + 1]; },
-                   [&](uint32_t i) { return h.dfa_d2[i]; });
+    w = dfa_next(w, window[p], 32u - h.dfa_bits, (1u << h.dfa_bits) - 1u,
+                 [&](uint32_t i, uint4* k, uint4* v) { *k = bk[2 * i]; *v = bk[2 * i + 1]; },
+                 [&](uint32_t b) { return h.dfa_d1[b]; });
   }
   const uint32_t* hot = &h.dfa_hot[size_t(w & kDfaStateMask) * 8];
   if (index) *index = hot[0] & 0xFFFFFFu;

@@ -55,10 +55,9 @@ struct HostTables {
   //     best_len = length of the longest key starting here (0 = none)
   //     sp_len   = length of the longest key that prefixes  virtual space + text from here
   //                (the lilbuf retry of go:1088-1107; includes the `off` prefix bytes; 0 = none)
-  //   dfa_d1[b]            first byte of a string (no previous byte)
-  //   dfa_d2[prev<<8 | b]  default: every transition whose target is at depth <= 2 depends only
-  //                        on the previous text byte and this one
-  //   dfa_buckets          hashed (state<<8|b) -> packed target for targets at depth >= 3;
+  //   dfa_d1[b]            default: every transition whose target is at depth <= 1 depends only on
+  //                        the byte (the node one byte below the root, or the root)
+  //   dfa_buckets          hashed (state<<8|b) -> packed target for targets at depth >= 2;
   //                        32-byte buckets of 4 keys + 4 values, bit 31 of key 0 = "overflowed
   //                        into the next bucket", empty key = kDfaEmpty
   //   dfa_hot[state]       state record, what the chain stage reads per look-ahead position (8 x u32):
@@ -74,7 +73,6 @@ struct HostTables {
   uint32_t dfa_states = 0;
   uint32_t dfa_bits = 0;
   std::vector<uint32_t> dfa_buckets;
-  std::vector<uint32_t> dfa_d2;
   uint32_t dfa_d1[256];
   std::vector<uint32_t> dfa_hot;
   std::vector<uint32_t> chain_rec;
