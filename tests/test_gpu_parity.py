@@ -23,11 +23,6 @@ def gold_vocab(name):
 
 def make_vocab(vb, group="1", cta=None):
     from tokenmonster_b200 import Vocab
-    os.environ["TMGPU_GROUP"] = group
-    if cta:
-        os.environ["TMGPU_CTA"] = str(cta)
-    else:
-        os.environ.pop("TMGPU_CTA", None)
     return Vocab(vb, device=0)
 
 

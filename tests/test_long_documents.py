@@ -45,7 +45,6 @@ def check(v, chk, texts, enc=2):
 @pytest.mark.parametrize("name", ["c1", "c2", "c4", "c3"])
 def test_single_megabyte_document(built, name):
     from tokenmonster_b200 import Vocab
-    os.environ["TMGPU_GROUP"] = "1"
     vb = configs.vocab_bytes(name)
     v, chk = Vocab(vb, device=0), oracle.OracleVocab(vb, "port")
     text = doc(41, 1 << 20, 0.3 if name != "c4" else 0.9)
@@ -62,7 +61,6 @@ def test_mixed_lengths_fallbacks_and_unk(built):
     one lane), one with a non-ASCII byte in the middle (-> the non-ASCII pass, whole document),
     and a vocabulary with an unk token and bytes it does not cover (missing counts are stitched)."""
     from tokenmonster_b200 import Vocab
-    os.environ["TMGPU_GROUP"] = "1"
     vb = configs.vocab_bytes("c2")
     v, chk = Vocab(vb, device=0), oracle.OracleVocab(vb, "port")
     long_a, long_b = doc(1, 300_000), doc(2, 50_000, 0.9)
@@ -91,7 +89,6 @@ def test_long_documents_through_wire_and_device_paths(built):
     import torch
     from tokenmonster_b200 import Vocab
     from tokenmonster_b200.device import DeviceWorkspace
-    os.environ["TMGPU_GROUP"] = "1"
     vb = configs.vocab_bytes("c2")
     v, chk = Vocab(vb, device=0), oracle.OracleVocab(vb, "port")
     texts = [doc(11, 200_000), b"tiny", doc(12, 70_000, 0.8)]

@@ -35,7 +35,6 @@ def test_oracle_score_invariants():
 @pytest.mark.parametrize("name", ["c2", "c3", "c4", "c1"])
 def test_training_scores_against_oracle(built, name):
     from tokenmonster_b200 import Vocab
-    os.environ["TMGPU_GROUP"] = "1"
     vb = configs.vocab_bytes(name)
     v, chk = Vocab(vb, device=0), oracle.OracleVocab(vb, "port")
     base = corpus.base_text(77, 1 << 19, 0.4)
@@ -58,7 +57,6 @@ def test_training_scores_missing_bytes_and_non_ascii(built):
     non-ASCII text (set aside before the first pass so that nothing is scored twice)."""
     from oracle import unicode_oracle as uo
     from tokenmonster_b200 import Vocab
-    os.environ["TMGPU_GROUP"] = "1"
     toks = [b" the", b"the", b" a", b"an", b" and", b"nd", b" qu", b"ick", b" brown", b"fox", b"o", b"x", b"D", b"C", b"W",
             b" ", b"e", b"t", b"h", b"\xcc", b"\x81", b"c", b"a", b"f"]
     vb = vocabgen.generate_vocab(toks, capcode=2, charset=1, normflag=1, level=2, reserve=32)

@@ -145,7 +145,6 @@ EDGE = [b"", b"\xff", b"ok \xc3", b"\xc0\xaf", b"\xed\xa0\x80", b"\xf4\x90\x80\x
 @pytest.mark.parametrize("capcode,normflag", [(2, 1), (0, 1), (2, 7), (0, 3), (2, 5)])
 def test_non_ascii_strings_against_oracle(built, capcode, normflag):
     from tokenmonster_b200 import Vocab
-    os.environ["TMGPU_GROUP"] = "1"
     vb = make_unicode_vocab(capcode, normflag)
     v, chk = Vocab(vb, device=0), oracle.OracleVocab(vb, "port")
     texts = unicode_texts(11 + capcode + normflag, 500) + EDGE + [s.encode() for s in SAMPLES]
@@ -173,7 +172,6 @@ def test_non_ascii_batch_large_and_streamed(built):
     """Every third string non-ASCII in a batch big enough for the chunked-upload path; the ASCII
     strings must be untouched by the second pass and the rest must match the oracle (sampled)."""
     from tokenmonster_b200 import Vocab
-    os.environ["TMGPU_GROUP"] = "1"
     vb = make_unicode_vocab(2, 1)
     v, chk = Vocab(vb, device=0), oracle.OracleVocab(vb, "port")
     pool = unicode_texts(5, 3000, 20, 400)
@@ -201,7 +199,6 @@ def test_non_ascii_decode_and_round_trip(built, capcode, normflag):
     """Decode (capcode decoder with Unicode classes and simple upper-casing) against the oracle, the
     NFD round trip, and the streaming decoder fed one id at a time."""
     from tokenmonster_b200 import Vocab
-    os.environ["TMGPU_GROUP"] = "1"
     vb = make_unicode_vocab(capcode, normflag)
     v, chk = Vocab(vb, device=0), oracle.OracleVocab(vb, "port")
     grow = [" ⱯⱯⱯⱯⱯⱯⱯⱯ ⱭⱭⱭ".encode(), "ȾȾȾ ⱯⱭ x".encode(), " ǅ ǄǄ ǆ".encode()]      # capitals longer than their lower case
@@ -263,7 +260,6 @@ def test_oracle_reproduces_committed_unicode_fixtures():
 @pytest.mark.gpu
 def test_device_matches_committed_unicode_fixtures(built):
     from tokenmonster_b200 import Vocab
-    os.environ["TMGPU_GROUP"] = "1"
     cases, vb = _unicode_fixture()
     rows = cases["rows"]
     texts = [bytes.fromhex(r["in"]) for r in rows]

@@ -57,10 +57,6 @@ extern "C" int tmgpu_vocab_create(const uint8_t* file_bytes, size_t n, int devic
     delete v;
     return TMGPU_E_UNSUPPORTED;
   }
-  if (const char* g = getenv("TMGPU_GROUP")) {
-    int gi = atoi(g);
-    if (gi == 1 || gi == 4 || gi == 8 || gi == 16 || gi == 32) v->group = gi;
-  }
   v->device = device;
   if (device < 0) {  // host tables only
     *out = v;

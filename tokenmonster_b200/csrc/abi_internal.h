@@ -51,7 +51,6 @@ struct tmgpu_vocab {
   HostTables host;
   int device = -1;  // -1: host tables only (parser / table self-tests without a GPU)
   int sms = 0;
-  int group = 1;    // 1 = lane-per-string kernel (default); 4/8/16/32 = lanes-over-branches kernel
   VocabDev dev{};
   bool unicode = false;           // non-ASCII strings go through the device normalizer (else status 13)
   UnicodeDev uni{};
