@@ -364,3 +364,43 @@ def test_poisoned_workspace_decode_twice(built):
     r = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "gpu_poison_check.py")], env=env,
                        capture_output=True, text=True, timeout=900)
     assert "__POISON_OK__" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_host_path_streams_ids_out_in_chunks(built):
+    """A batch big enough for the chunked host path (>= 2 x 1024 strings per SM): the ids leave the GPU
+    chunk by chunk.  First call sizes the pinned buffer by guess, the second by the first's yield;
+    a non-ASCII string forces the fallback (one copy at the end).  All three must equal the
+    device-resident single launch and the oracle."""
+    import torch
+    from tokenmonster_b200.device import DeviceWorkspace
+    vb = configs.vocab_bytes("c2")
+    v, chk = make_vocab(vb), oracle.OracleVocab(vb, "port")
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    n = 2 * sms * 1024 + 777
+    base = corpus.base_text(41, 1 << 20, 0.3)
+    data, off = corpus.make_batch(base, n, 0, 160, 9, "cpu")
+    data, off = data.numpy(), off.numpy().astype(np.uint64)
+    ws = DeviceWorkspace(v, n, int(off[-1]))
+    ws.launch_tokenize(torch.from_numpy(data).cuda(), torch.from_numpy(off.astype(np.int64)).cuda(), 2, 0)
+    ref = ws.results()
+    want_tok = ref["tokens_u8"].cpu().numpy().view(np.uint16)
+    want_off = ref["tok_off"].cpu().numpy().astype(np.uint64)
+    for rep in range(2):
+        r = v.tokenize_batch(data, off, 2)
+        assert np.array_equal(r.tok_off, want_off) and np.array_equal(r.tokens, want_tok), f"call {rep}"
+        assert not r.status.any()
+    for s in range(0, n, 4099):
+        want, miss = chk.tokenize(data[int(off[s]):int(off[s + 1])].tobytes())
+        assert np.array_equal(r[s].astype(np.uint32), want) and int(r.missing[s]) == miss
+    # one non-ASCII string in the middle: its ids change the offsets of everything behind it
+    mid = n // 2
+    extra = "Æther café".encode()
+    d2 = np.concatenate([data[:int(off[mid])], np.frombuffer(extra, np.uint8), data[int(off[mid]):]])
+    o2 = np.concatenate([off[:mid + 1], off[mid:] + len(extra)])
+    r2 = v.tokenize_batch(d2, o2, 2)
+    assert v.last_stats()["unicode_strings"] == 1
+    assert np.array_equal(r2.tokens[:int(r2.tok_off[mid])], want_tok[:int(want_off[mid])])
+    k = int(r2.tok_off[mid + 1])
+    assert np.array_equal(r2.tokens[k:], want_tok[int(want_off[mid]):])
+    ws.close()
+    v.close()

@@ -66,6 +66,7 @@ struct tmgpu_vocab {
   size_t h_off_cap = 0;
   cudaStream_t copy_stream = nullptr;
   cudaStream_t d2h_stream = nullptr;
+  double ids_per_byte = 0;        // of the previous host-buffer call (sizes the streamed-out id buffer)
   cudaEvent_t chunk_ev[32] = {};
   cudaEvent_t done_ev[32] = {};
   uint64_t* d_run = nullptr;      // device: running id total + per-chunk {base, total}
@@ -199,6 +200,14 @@ struct ChunkPlan {
   cudaEvent_t ready;     // may be null
 };
 
+// Host destination for ids that leave the GPU chunk by chunk (tokenize_on_stream, host path).
+struct StreamOut {
+  uint8_t* tokens = nullptr;   // pinned
+  uint64_t cap_bytes = 0;
+  bool ok = false;             // every chunk fitted and no later pass changed the counts
+  uint64_t total_ids = 0;
+};
+
 struct ResultPriv {
   std::shared_ptr<PinnedPool> pool;
   std::vector<void*> blocks;
@@ -246,7 +255,7 @@ int rerun_if_overflow(tmgpu_vocab* v, uint32_t n, uint8_t enc_len, std::vector<v
 int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t* d_off, uint32_t n,
                        uint8_t enc_len, int mode, cudaStream_t st, const uint64_t* slab_off, uint32_t* slab,
                        uint8_t* dense, const std::vector<ChunkPlan>* chunks = nullptr,
-                       const int64_t* d_ends = nullptr);
+                       const int64_t* d_ends = nullptr, StreamOut* so = nullptr);
 int ensure_decode_cap(tmgpu_workspace* ws, uint64_t bytes);
 int decode_on_stream(tmgpu_workspace* ws, const uint8_t* d_tokens, const int64_t* d_tok_off, uint32_t n, int enc,
                      cudaStream_t st, const uint8_t** d_bytes, const uint64_t** d_off, uint64_t* total_out);

@@ -311,9 +311,13 @@ static int side_passes(tmgpu_workspace* ws, const TokenizeArgs& first, bool stor
 int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t* d_off, uint32_t n,
                               uint8_t enc_len, int mode, cudaStream_t st, const uint64_t* slab_off,
                               uint32_t* slab, uint8_t* dense, const std::vector<ChunkPlan>* chunks,
-                              const int64_t* d_ends) {
+                              const int64_t* d_ends, StreamOut* so) {
   tmgpu_vocab* v = ws->v;
   ws->last_launches = 0;
+  // ids stream out chunk by chunk only on the plain chunked host path
+  const bool stream_out = so && mode == 0 && chunks && chunks->size() > 1 && !slab_off && n > 0 && v->host.max_len != 0;
+  int streamed_chunks = 0;
+  if (so) so->ok = false;
   CU(cudaMemsetAsync(ws->work_counter, 0, 4 * tmgpu_workspace::kMaxChunks, st));
   CU(cudaMemsetAsync(ws->overflow, 0, 4, st));
   CU(cudaMemsetAsync(ws->counts + n, 0, 4, st));
@@ -374,6 +378,33 @@ int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t
       b.status = ws->status + c.s0;
       int rc = run_pipeline(ws, b, mode == 0, st, 0);
       if (rc) return rc;
+      if (stream_out) {
+        // this chunk's offsets, dense ids and running id total, while the next chunk is still copying in
+        const int ci = streamed_chunks++;
+        if (ci == 0) CU(cudaMemsetAsync(v->d_run, 0, 8, st));
+        CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, b.counts, ws->tok_off + c.s0, b.n, st));
+        CU(launch_chunk_offsets(ws->tok_off + c.s0, b.counts, b.n, reinterpret_cast<unsigned long long*>(v->d_run + ci),
+                                v->sms, st));
+        CU(launch_pack(b.slab, b.off, ws->slab_pad, nullptr, b.counts, ws->tok_off + c.s0, dense, b.n, enc_len, v->sms, st));
+        CU(cudaMemcpyAsync(v->h_info + ci + 1, v->d_run + ci + 1, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(v->done_ev[ci], st));
+        ws->last_launches += 4;
+      }
+    }
+    if (stream_out) {   // everything is queued: hand each chunk's ids to the copy-out stream as it completes
+      bool fits = true;
+      uint64_t prev = 0;
+      for (int ci = 0; ci < streamed_chunks; ci++) {
+        CU(cudaEventSynchronize(v->done_ev[ci]));
+        const uint64_t cum = v->h_info[ci + 1];
+        if (cum * enc_len > so->cap_bytes) fits = false;
+        if (fits && cum > prev)
+          CU(cudaMemcpyAsync(so->tokens + prev * enc_len, dense + prev * enc_len, (cum - prev) * enc_len,
+                             cudaMemcpyDeviceToHost, v->d2h_stream));
+        prev = cum;
+      }
+      so->ok = fits;
+      so->total_ids = prev;
     }
   } else if (n > 0) {
     const int e = ws->ev_head;
@@ -395,7 +426,8 @@ int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t
     int rc = side_passes(ws, a, mode == 0, st);
     if (rc) return rc;
   }
-  if (mode == 0) {
+  if (so && so->ok && (ws->last_unicode || ws->last_overflowed || ck_total)) so->ok = false;   // counts changed after the chunks went out
+  if (mode == 0 && !(stream_out && so->ok)) {
     CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, ws->counts, ws->tok_off, n + 1, st));
     ws->last_launches += 2;  // cub::DeviceScan = init kernel + scan kernel
     if (n > 0) {
@@ -608,18 +640,6 @@ extern "C" int tmgpu_tokenize_batch(tmgpu_vocab* v, const uint8_t* data, const u
   std::vector<ChunkPlan> plan;
   if ((rc = stage_input(v, data, off, n, &total, &plan))) return rc;
   tmgpu_workspace* ws = v->ws;
-  if ((rc = tokenize_on_stream(ws, v->d_in, v->d_off, n, enc_len, 0, v->stream, nullptr, ws->slab, ws->tokens, &plan)))
-    return rc;
-  std::vector<void*> temp;
-  uint8_t* dense = ws->tokens;
-  auto cleanup = [&]() {
-    for (void* p : temp) cudaFree(p);
-    temp.clear();
-  };
-  if ((rc = rerun_if_overflow(v, n, enc_len, &temp, &dense))) {
-    cleanup();
-    return rc;
-  }
   auto* priv = new ResultPriv();
   priv->pool = v->pool;
   auto* r = new tmgpu_result();
@@ -627,11 +647,33 @@ extern "C" int tmgpu_tokenize_batch(tmgpu_vocab* v, const uint8_t* data, const u
   r->priv = priv;
   r->n = n;
   r->enc_len = enc_len;
+  std::vector<void*> temp;
+  auto cleanup = [&]() {
+    for (void* p : temp) cudaFree(p);
+    temp.clear();
+  };
   auto bail = [&](int code) {
     cleanup();
+    cudaStreamSynchronize(v->d2h_stream);
     tmgpu_result_free(r);
     return code;
   };
+  // Big batches: the ids leave the GPU chunk by chunk while later chunks are still being tokenized.
+  // The pinned destination has to exist before the id count is known: room for what the previous
+  // call produced per input byte (+ 12 %), else one id per 3 bytes; a batch that needs more falls
+  // back to one copy at the end.
+  StreamOut so;
+  if (plan.size() > 1) {
+    const double per_byte = v->ids_per_byte > 0 ? v->ids_per_byte * 1.12 : 1.0 / 3.0;
+    so.cap_bytes = (uint64_t(double(total) * per_byte) + n + 4096) * enc_len;
+    if ((rc = pinned_alloc(priv, &so.tokens, so.cap_bytes))) return bail(rc);
+  }
+  if ((rc = tokenize_on_stream(ws, v->d_in, v->d_off, n, enc_len, 0, v->stream, nullptr, ws->slab, ws->tokens, &plan, nullptr,
+                               so.tokens ? &so : nullptr)))
+    return bail(rc);
+  uint8_t* dense = ws->tokens;
+  if ((rc = rerun_if_overflow(v, n, enc_len, &temp, &dense))) return bail(rc);
+  const bool streamed = so.tokens && so.ok && dense == ws->tokens;
   if ((rc = pinned_alloc(priv, &r->tok_off, size_t(n) + 1))) return bail(rc);
   if ((rc = pinned_alloc(priv, &r->missing, size_t(n) + 1))) return bail(rc);
   if ((rc = pinned_alloc(priv, &r->status, size_t(n) + 1))) return bail(rc);
@@ -640,18 +682,24 @@ extern "C" int tmgpu_tokenize_batch(tmgpu_vocab* v, const uint8_t* data, const u
   if (e == cudaSuccess) e = cudaMemcpyAsync(r->missing, ws->missing, size_t(n) * 4, cudaMemcpyDeviceToHost, v->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(r->status, ws->status, size_t(n), cudaMemcpyDeviceToHost, v->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(v->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(v->d2h_stream);
   if (e != cudaSuccess) {
     g_err = std::string("tokenize: ") + cudaGetErrorString(e);
     return bail(TMGPU_E_CUDA);
   }
   r->n_tokens = r->tok_off[n];
-  if ((rc = pinned_alloc(priv, &r->tokens, r->n_tokens * enc_len + 8))) return bail(rc);
-  if (r->n_tokens) {
-    e = cudaMemcpyAsync(r->tokens, dense, r->n_tokens * enc_len, cudaMemcpyDeviceToHost, v->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(v->stream);
-    if (e != cudaSuccess) {
-      g_err = std::string("tokenize D2H: ") + cudaGetErrorString(e);
-      return bail(TMGPU_E_CUDA);
+  if (total) v->ids_per_byte = double(r->n_tokens) / double(total);
+  if (streamed) {
+    r->tokens = so.tokens;
+  } else {
+    if ((rc = pinned_alloc(priv, &r->tokens, r->n_tokens * enc_len + 8))) return bail(rc);
+    if (r->n_tokens) {
+      e = cudaMemcpyAsync(r->tokens, dense, r->n_tokens * enc_len, cudaMemcpyDeviceToHost, v->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(v->stream);
+      if (e != cudaSuccess) {
+        g_err = std::string("tokenize D2H: ") + cudaGetErrorString(e);
+        return bail(TMGPU_E_CUDA);
+      }
     }
   }
   cleanup();

@@ -60,6 +60,31 @@ __global__ void __launch_bounds__(256) pack_tokens_kernel(const uint32_t* __rest
   }
 }
 
+// Chunked host path: the ids of chunk k go to the host while chunk k+1 is still being tokenized, so
+// every chunk turns its local offsets (exclusive scan of its own counts) into global ones itself:
+// base_io[0] = ids before this chunk (written by its predecessor), base_io[1] = ids including it.
+__global__ void __launch_bounds__(256) chunk_offsets_kernel(uint64_t* __restrict__ tok_off,
+                                                            const uint32_t* __restrict__ counts, uint32_t n,
+                                                            unsigned long long* __restrict__ base_io) {
+  const unsigned long long base = base_io[0];
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const unsigned long long local = tok_off[k];
+    tok_off[k] = local + base;
+    if (k == n - 1) {
+      const unsigned long long end = base + local + counts[k];
+      tok_off[n] = end;
+      base_io[1] = end;
+    }
+  }
+}
+
+cudaError_t launch_chunk_offsets(uint64_t* tok_off, const uint32_t* counts, uint32_t n, unsigned long long* base_io,
+                                 int sms, cudaStream_t st) {
+  const long long want = (static_cast<long long>(n) + 255) / 256;
+  chunk_offsets_kernel<<<int(want < sms * 4ll ? (want < 1 ? 1 : want) : sms * 4ll), 256, 0, st>>>(tok_off, counts, n, base_io);
+  return cudaGetLastError();
+}
+
 // Reply framing of the server protocol (training/tokenmonsterserver.go:382-392, :435-445):
 // [u32 n] then, per string, [u64 byte length][payload].  One warp per string; `unit` is the
 // item size of src_off (the encoding length for ids, 1 for decoded bytes).
