@@ -217,8 +217,8 @@ int tmgpu_tokenize_device(tmgpu_workspace* ws, const uint8_t* d_data, const int6
                           uint32_t n, uint8_t enc_len, int mode, void* stream,
                           tmgpu_device_view* view);
 /* Durations (ms) of the stages of the most recent tokenize run on this workspace, from CUDA events
- * on the launching stream: out[0] capcode lengths + scan, out[1] capcode text, out[2] position
- * table, out[3] chain (stages that did not run report 0).  Returns 4, or 0 before the first run. */
+ * on the launching stream: out[0] prep + slot scan + length sort, out[1] capcode encoder +
+ * position table, out[2] chain, out[3] 0.  Returns 4, or 0 before the first run. */
 int tmgpu_workspace_stage_times(tmgpu_workspace* ws, float out[4]);
 /* Number of kernels the last tmgpu_tokenize_device / decode call launched (bench accounting). */
 int tmgpu_last_launch_count(const tmgpu_workspace* ws);

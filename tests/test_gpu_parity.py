@@ -404,3 +404,34 @@ def test_host_path_streams_ids_out_in_chunks(built):
     assert np.array_equal(r2.tokens[k:], want_tok[int(want_off[mid]):])
     ws.close()
     v.close()
+
+
+def test_two_devices_in_one_process(built):
+    """What a cgo server with several GPUs does: vocabularies on device 0 and device 1 in ONE process,
+    used alternately (kernel attributes / occupancy are per device, nothing may be cached per process)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from tokenmonster_b200 import Vocab
+    vb = configs.vocab_bytes("c2")
+    chk = oracle.OracleVocab(vb, "port")
+    base = corpus.base_text(55, 1 << 18, 0.3)
+    data, off = corpus.make_batch(base, 3000, 0, 700, 4, "cpu")
+    data, off = data.numpy(), off.numpy().astype(np.uint64)
+    v0, v1 = Vocab(vb, device=0), Vocab(vb, device=1)
+    for rep in range(2):
+        r0, r1 = v0.tokenize_batch(data, off, 2), v1.tokenize_batch(data, off, 2)
+        assert np.array_equal(r0.tokens, r1.tokens) and np.array_equal(r0.tok_off, r1.tok_off)
+        b1, o1 = v1.decode_batch(r1.raw, r1.tok_off, 2)
+        b0, o0 = v0.decode_batch(r0.raw, r0.tok_off, 2)
+        assert np.array_equal(b0, b1) and np.array_equal(o0, o1)
+    for s in range(0, 3000, 101):
+        want, _ = chk.tokenize(data[int(off[s]):int(off[s + 1])].tobytes())
+        assert np.array_equal(r1[s].astype(np.uint32), want)
+    long_doc = bytes(corpus.base_text(6, 60000, 0.3))     # the chunk kernel needs its shared-memory opt-in on both
+    o2 = np.array([0, len(long_doc)], np.uint64)
+    a = v0.tokenize_batch(np.frombuffer(long_doc, np.uint8), o2, 4)
+    b = v1.tokenize_batch(np.frombuffer(long_doc, np.uint8), o2, 4)
+    assert np.array_equal(a.tokens, b.tokens) and v1.last_stats()["chunks"] > 10
+    v0.close()
+    v1.close()

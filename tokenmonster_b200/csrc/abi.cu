@@ -193,6 +193,11 @@ extern "C" void tmgpu_vocab_destroy(tmgpu_vocab* v) {
     if (e) cudaEventDestroy(e);
   if (v->d_run) cudaFree(v->d_run);
   if (v->h_info) cudaFreeHost(v->h_info);
+  v->copy_pool.reset();
+  for (auto& b : v->stage_buf)
+    if (b) cudaFreeHost(b);
+  for (auto& e : v->stage_free)
+    if (e) cudaEventDestroy(e);
   {  // results cut from the pool may still be alive: free what is idle, leave the rest to them
     std::lock_guard<std::mutex> lock(v->pool->mu);
     v->pool->orphaned = true;

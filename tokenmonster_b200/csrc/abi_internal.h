@@ -10,7 +10,10 @@
 #include <cstring>
 #include <fstream>
 #include <memory>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -47,6 +50,69 @@ struct PinnedPool {
   }
 };
 
+// Helper threads that copy slices of a pageable host buffer into pinned staging memory (a cgo
+// caller passes ordinary Go slices; cudaMemcpyAsync from pageable memory goes through one driver
+// thread at a fraction of the PCIe rate).
+class CopyPool {
+ public:
+  explicit CopyPool(int workers) {
+    for (int i = 0; i < workers; i++) th_.emplace_back([this] { loop(); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  // dst[0..len) = src[0..len), split over the workers and the calling thread
+  void copy(uint8_t* dst, const uint8_t* src, size_t len) {
+    const size_t parts = th_.size() + 1, slice = (len / parts + 4095) & ~size_t(4095);
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      dst_ = dst; src_ = src; len_ = len; slice_ = slice ? slice : len;
+      next_ = 1;                 // part 0 is the caller's
+      parts_ = slice_ ? (len + slice_ - 1) / slice_ : 0;
+      pending_ = parts_ > 1 ? parts_ - 1 : 0;
+      gen_++;
+    }
+    cv_.notify_all();
+    if (len) std::memcpy(dst, src, slice_ < len ? slice_ : len);
+    std::unique_lock<std::mutex> l(mu_);
+    done_.wait(l, [this] { return pending_ == 0; });
+  }
+
+ private:
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      size_t part;
+      {
+        std::unique_lock<std::mutex> l(mu_);
+        cv_.wait(l, [&] { return stop_ || (gen_ != seen && next_ < parts_) || (gen_ != seen && next_ >= parts_); });
+        if (stop_) return;
+        if (next_ >= parts_) { seen = gen_; continue; }
+        part = next_++;
+      }
+      const size_t a = part * slice_, b = a + slice_ < len_ ? a + slice_ : len_;
+      std::memcpy(dst_ + a, src_ + a, b - a);
+      {
+        std::lock_guard<std::mutex> l(mu_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  uint8_t* dst_ = nullptr;
+  const uint8_t* src_ = nullptr;
+  size_t len_ = 0, slice_ = 0, parts_ = 0, next_ = 0, pending_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
 struct tmgpu_vocab {
   HostTables host;
   int device = -1;  // -1: host tables only (parser / table self-tests without a GPU)
@@ -72,6 +138,12 @@ struct tmgpu_vocab {
   uint64_t* d_run = nullptr;      // device: running id total + per-chunk {base, total}
   uint64_t* h_info = nullptr;     // pinned mirror of the per-chunk {base, total}
   std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
+  // pageable inputs: pinned staging ring + helper threads (created on first use)
+  static constexpr int kStageSlots = 3;
+  static constexpr size_t kStageBytes = size_t(16) << 20;
+  uint8_t* stage_buf[kStageSlots] = {};
+  cudaEvent_t stage_free[kStageSlots] = {};
+  std::unique_ptr<CopyPool> copy_pool;
 };
 
 struct tmgpu_workspace {
@@ -198,6 +270,9 @@ struct ChunkPlan {
   uint32_t s0, s1;       // strings [s0, s1)
   uint64_t slab_base;    // (off[s0] - off[0]) + slab_pad * s0
   cudaEvent_t ready;     // may be null
+  std::function<int()> stage;   // optional: called right before the chunk's kernels are queued (pageable
+                                // input: stages + uploads this chunk, so that the host-side memcpy of
+                                // chunk k+1 overlaps the kernels of chunk k)
 };
 
 // Host destination for ids that leave the GPU chunk by chunk (tokenize_on_stream, host path).

@@ -3,6 +3,8 @@
 // documents (chunking.cuh) and non-ASCII strings (unicode_normalize.cuh), the overflow re-run.
 #include "abi_internal.h"
 
+#include <chrono>
+
 // ---- the position-table pipeline (pipeline_kernels.cuh) ------------------------------------------
 static int grow_device(void** p, uint64_t* cap, uint64_t want, size_t unit, const char* what) {
   if (*cap >= want) return TMGPU_OK;
@@ -316,6 +318,15 @@ int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t
   ws->last_launches = 0;
   // ids stream out chunk by chunk only on the plain chunked host path
   const bool stream_out = so && mode == 0 && chunks && chunks->size() > 1 && !slab_off && n > 0 && v->host.max_len != 0;
+  auto stage_all = [&]() -> int {   // upload whatever the plan has not uploaded yet
+    for (const ChunkPlan& c : *chunks)
+      if (c.stage) {
+        int rc = c.stage();
+        const_cast<ChunkPlan&>(c).stage = nullptr;
+        if (rc) return rc;
+      }
+    return TMGPU_OK;
+  };
   int streamed_chunks = 0;
   if (so) so->ok = false;
   CU(cudaMemsetAsync(ws->work_counter, 0, 4 * tmgpu_workspace::kMaxChunks, st));
@@ -343,9 +354,12 @@ int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t
     a.miss_hist = ws->score_buf + v->host.n_reverse;
     CU(cudaMemsetAsync(ws->score_buf, 0, (size_t(v->host.n_reverse) + 256) * 8, st));
     if (v->unicode) {
-      if (chunks)
+      if (chunks) {
+        int rc = stage_all();
+        if (rc) return rc;
         for (const ChunkPlan& c : *chunks)
           if (c.ready) CU(cudaStreamWaitEvent(st, c.ready, 0));
+      }
       CU(launch_flag_non_ascii(d_data, d_off, d_ends, n, ws->ck_skip, ws->status, ws->counts, ws->missing, v->sms, st));
       a.skip = ws->ck_skip;
       ws->last_launches++;
@@ -353,6 +367,10 @@ int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t
   }
   uint32_t ck_total = 0;   // long documents of a small batch are tokenized in chunks (chunking.cuh)
   if (n > 0 && (!chunks || chunks->size() == 1)) {
+    if (chunks) {
+      int rc = stage_all();
+      if (rc) return rc;
+    }
     if (chunks && (*chunks)[0].ready) CU(cudaStreamWaitEvent(st, (*chunks)[0].ready, 0));
     int rc = chunk_plan(ws, a, st, &ck_total);
     if (rc) return rc;
@@ -364,6 +382,11 @@ int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t
     CU(cudaMemsetAsync(ws->status, 0, n, st));
   } else if (n > 0 && chunks && !slab_off) {
     for (const ChunkPlan& c : *chunks) {
+      if (c.stage) {   // (not yet uploaded: pageable input is staged chunk by chunk)
+        int rc = c.stage();
+        const_cast<ChunkPlan&>(c).stage = nullptr;
+        if (rc) return rc;
+      }
       if (c.s1 <= c.s0) continue;
       if (c.ready) CU(cudaStreamWaitEvent(st, c.ready, 0));
       TokenizeArgs b = a;
@@ -572,6 +595,26 @@ int stage_copy(tmgpu_vocab* v, const uint8_t* src, uint32_t n, uint64_t total_by
   if (want > 8) want = 8;
   if (want < 1) want = 1;
   if (plan) plan->clear();
+  // is the source ordinary (pageable) memory?  Then big batches are staged through pinned memory
+  bool pageable = false;
+  if (plan && total_bytes >= (8u << 20)) {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, src) != cudaSuccess) {
+      cudaGetLastError();
+      pageable = true;
+    } else {
+      pageable = attr.type == cudaMemoryTypeUnregistered;
+    }
+    if (pageable && !v->copy_pool) {
+      for (int k = 0; k < tmgpu_vocab::kStageSlots; k++) {
+        CU(cudaMallocHost(&v->stage_buf[k], tmgpu_vocab::kStageBytes));
+        CU(cudaEventCreateWithFlags(&v->stage_free[k], cudaEventDisableTiming));
+      }
+      unsigned hw = std::thread::hardware_concurrency();
+      v->copy_pool.reset(new CopyPool(hw >= 16 ? 7 : (hw >= 4 ? 3 : 1)));
+    }
+  }
+  uint64_t piece = 0;
   uint32_t s0 = 0;
   const uint32_t pad = v->ws->slab_pad;
   for (int c = 0; c < want && s0 < n; c++) {
@@ -586,9 +629,29 @@ int stage_copy(tmgpu_vocab* v, const uint8_t* src, uint32_t n, uint64_t total_by
       s1 = lo + 1 > n ? n : lo + 1;
     }
     const uint64_t b0 = uint64_t(v->h_off[s0]), b1 = uint64_t(v->h_off[s1]);
-    if (b1 > b0) CU(cudaMemcpyAsync(v->d_in + b0, src + b0, b1 - b0, cudaMemcpyHostToDevice, v->copy_stream));
-    CU(cudaEventRecord(v->chunk_ev[c], v->copy_stream));
-    if (plan) plan->push_back({s0, s1, (b0 - uint64_t(v->h_off[0])) + uint64_t(pad) * s0, v->chunk_ev[c]});
+    cudaEvent_t ready = v->chunk_ev[c];
+    if (!pageable || !plan) {
+      if (b1 > b0) CU(cudaMemcpyAsync(v->d_in + b0, src + b0, b1 - b0, cudaMemcpyHostToDevice, v->copy_stream));
+      CU(cudaEventRecord(ready, v->copy_stream));
+      if (plan) plan->push_back({s0, s1, (b0 - uint64_t(v->h_off[0])) + uint64_t(pad) * s0, ready, nullptr});
+    } else {
+      // pageable source: helper threads copy 16 MB pieces into a pinned ring, each piece goes up as
+      // soon as it is staged; done lazily, chunk by chunk, from the launch loop
+      auto stage = [v, src, b0, b1, ready, piece]() mutable -> int {
+        for (uint64_t at = b0; at < b1; at += tmgpu_vocab::kStageBytes) {
+          const uint64_t len = b1 - at < tmgpu_vocab::kStageBytes ? b1 - at : tmgpu_vocab::kStageBytes;
+          const int slot = int(piece++ % tmgpu_vocab::kStageSlots);
+          CU(cudaEventSynchronize(v->stage_free[slot]));
+          v->copy_pool->copy(v->stage_buf[slot], src + at, len);
+          CU(cudaMemcpyAsync(v->d_in + at, v->stage_buf[slot], len, cudaMemcpyHostToDevice, v->copy_stream));
+          CU(cudaEventRecord(v->stage_free[slot], v->copy_stream));
+        }
+        CU(cudaEventRecord(ready, v->copy_stream));
+        return TMGPU_OK;
+      };
+      piece += (b1 - b0 + tmgpu_vocab::kStageBytes - 1) / tmgpu_vocab::kStageBytes;
+      plan->push_back({s0, s1, (b0 - uint64_t(v->h_off[0])) + uint64_t(pad) * s0, ready, stage});
+    }
     s0 = s1;
   }
   if (!plan) CU(cudaStreamSynchronize(v->copy_stream));
@@ -634,11 +697,15 @@ extern "C" int tmgpu_tokenize_batch(tmgpu_vocab* v, const uint8_t* data, const u
     return TMGPU_E_ARG;
   }
   std::lock_guard<std::mutex> lock(v->mu);
+  static const bool trace = getenv("TMGPU_TRACE") != nullptr;   // diagnostic: host-side phase times on stderr
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
   int rc = ensure_host_path(v, n, off[n] - off[0]);
   if (rc) return rc;
   uint64_t total = 0;
   std::vector<ChunkPlan> plan;
   if ((rc = stage_input(v, data, off, n, &total, &plan))) return rc;
+  const double t_staged = since();
   tmgpu_workspace* ws = v->ws;
   auto* priv = new ResultPriv();
   priv->pool = v->pool;
@@ -671,8 +738,10 @@ extern "C" int tmgpu_tokenize_batch(tmgpu_vocab* v, const uint8_t* data, const u
   if ((rc = tokenize_on_stream(ws, v->d_in, v->d_off, n, enc_len, 0, v->stream, nullptr, ws->slab, ws->tokens, &plan, nullptr,
                                so.tokens ? &so : nullptr)))
     return bail(rc);
+  const double t_queued = since();
   uint8_t* dense = ws->tokens;
   if ((rc = rerun_if_overflow(v, n, enc_len, &temp, &dense))) return bail(rc);
+  const double t_computed = since();
   const bool streamed = so.tokens && so.ok && dense == ws->tokens;
   if ((rc = pinned_alloc(priv, &r->tok_off, size_t(n) + 1))) return bail(rc);
   if ((rc = pinned_alloc(priv, &r->missing, size_t(n) + 1))) return bail(rc);
@@ -703,6 +772,10 @@ extern "C" int tmgpu_tokenize_batch(tmgpu_vocab* v, const uint8_t* data, const u
     }
   }
   cleanup();
+  if (trace)
+    fprintf(stderr, "[tmgpu] tokenize_batch: %u strings, %.1f MB, %zu chunk(s)%s: offsets + copies queued %.2f ms, kernels queued / "
+            "chunks drained %.2f ms, compute done %.2f ms, results on the host %.2f ms\n", n, double(total) / 1e6, plan.size(),
+            streamed ? " (ids streamed out)" : "", t_staged, t_queued, t_computed, since());
   *out = r;
   return TMGPU_OK;
 }

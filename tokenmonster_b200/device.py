@@ -74,7 +74,7 @@ class DeviceWorkspace:
         return [float(buf[i]) for i in range(k)]
 
     def stage_times_ms(self):
-        """CUDA-event durations of the last run's stages: capcode lengths+scan, capcode text, table, chain."""
+        """CUDA-event durations of the last run's stages: prep + scan + sort, table, chain (, 0)."""
         buf = (C.c_float * 4)()
         k = lib().tmgpu_workspace_stage_times(self._h, buf)
         return [float(buf[i]) for i in range(k)]
