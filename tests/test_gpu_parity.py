@@ -367,7 +367,7 @@ def test_poisoned_workspace_decode_twice(built):
 
 
 def test_host_path_streams_ids_out_in_chunks(built):
-    """A batch big enough for the chunked host path (>= 2 x 1024 strings per SM): the ids leave the GPU
+    """A batch big enough for the chunked host path (>= 2 x 2048 strings per SM): the ids leave the GPU
     chunk by chunk.  First call sizes the pinned buffer by guess, the second by the first's yield;
     a non-ASCII string forces the fallback (one copy at the end).  All three must equal the
     device-resident single launch and the oracle."""
@@ -376,7 +376,7 @@ def test_host_path_streams_ids_out_in_chunks(built):
     vb = configs.vocab_bytes("c2")
     v, chk = make_vocab(vb), oracle.OracleVocab(vb, "port")
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    n = 2 * sms * 1024 + 777
+    n = 4 * sms * 1024 + 777
     base = corpus.base_text(41, 1 << 20, 0.3)
     data, off = corpus.make_batch(base, n, 0, 160, 9, "cpu")
     data, off = data.numpy(), off.numpy().astype(np.uint64)
