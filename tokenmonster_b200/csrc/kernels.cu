@@ -65,23 +65,24 @@ __global__ void __launch_bounds__(256) pack_tokens_kernel(const uint32_t* __rest
 // base_io[0] = ids before this chunk (written by its predecessor), base_io[1] = ids including it.
 __global__ void __launch_bounds__(256) chunk_offsets_kernel(uint64_t* __restrict__ tok_off,
                                                             const uint32_t* __restrict__ counts, uint32_t n,
-                                                            unsigned long long* __restrict__ base_io) {
+                                                            unsigned long long* __restrict__ base_io, int write_end) {
   const unsigned long long base = base_io[0];
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const unsigned long long local = tok_off[k];
     tok_off[k] = local + base;
     if (k == n - 1) {
       const unsigned long long end = base + local + counts[k];
-      tok_off[n] = end;
+      if (write_end) tok_off[n] = end;   // (an inner chunk's end is the next chunk's first entry, which that chunk writes)
       base_io[1] = end;
     }
   }
 }
 
 cudaError_t launch_chunk_offsets(uint64_t* tok_off, const uint32_t* counts, uint32_t n, unsigned long long* base_io,
-                                 int sms, cudaStream_t st) {
+                                 bool write_end, int sms, cudaStream_t st) {
   const long long want = (static_cast<long long>(n) + 255) / 256;
-  chunk_offsets_kernel<<<int(want < sms * 4ll ? (want < 1 ? 1 : want) : sms * 4ll), 256, 0, st>>>(tok_off, counts, n, base_io);
+  chunk_offsets_kernel<<<int(want < sms * 4ll ? (want < 1 ? 1 : want) : sms * 4ll), 256, 0, st>>>(tok_off, counts, n, base_io,
+                                                                                                 write_end ? 1 : 0);
   return cudaGetLastError();
 }
 

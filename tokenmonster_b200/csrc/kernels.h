@@ -90,7 +90,7 @@ cudaError_t launch_pack(const uint32_t* slab, const int64_t* off, uint32_t slab_
                         const uint32_t* counts, const uint64_t* tok_off, uint8_t* out, uint32_t n, int enc,
                         int sms, cudaStream_t st);
 cudaError_t launch_chunk_offsets(uint64_t* tok_off, const uint32_t* counts, uint32_t n, unsigned long long* base_io,
-                                 int sms, cudaStream_t st);
+                                 bool write_end, int sms, cudaStream_t st);
 // reply framing of the server protocol: [u32 n] then per string [u64 byte length][unit * items]
 cudaError_t launch_wire_frame(const uint8_t* src, const uint64_t* src_off, uint32_t unit, uint32_t n, uint8_t* dst,
                               int sms, cudaStream_t st);
