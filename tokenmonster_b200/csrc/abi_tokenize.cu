@@ -386,7 +386,8 @@ int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t
     CU(cudaMemsetAsync(ws->status, 0, n, st));
   } else if (n > 0 && chunks && !slab_off) {
     // chunk k on stream k & 1: the tail of one chunk (few warps left) overlaps the head of the next
-    const bool two = chunks->size() > 1 && st == v->stream;
+    static const bool one_stream = getenv("TMGPU_ONE_STREAM") != nullptr;   // diagnostic: A/B of the two-stream schedule
+    const bool two = chunks->size() > 1 && st == v->stream && !one_stream;
     cudaStream_t sts[2] = {st, two ? v->stream2 : st};
     if (two) {   // the second stream starts behind the resets queued above
       CU(cudaEventRecord(v->join_ev, st));

@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(256) capcode_decode_ascii_kernel(const uint8_t
                                                                    uint32_t* __restrict__ out_len,
                                                                    const uint32_t* __restrict__ len_in,
                                                                    uint8_t* __restrict__ state, int wide,
+                                                                   const uint32_t* __restrict__ order,
                                                                    uint32_t* __restrict__ counter) {
   constexpr unsigned FULL = 0xFFFFFFFFu;
   __shared__ __align__(16) uint32_t s_ring[256 * 8];
@@ -283,8 +284,9 @@ __global__ void __launch_bounds__(256) capcode_decode_ascii_kernel(const uint8_t
     if (lane == 0) g = atomicAdd(counter, 1u);
     g = __shfl_sync(FULL, g, 0);
     if (uint64_t(g) * 32u >= n) break;
-    const uint32_t s = g * 32u + uint32_t(lane);
-    bool active = s < n, wide_text = false;
+    const uint32_t slot_i = g * 32u + uint32_t(lane);
+    bool active = slot_i < n, wide_text = false;
+    const uint32_t s = active ? order[slot_i] : 0u;   // strings by descending length: the 32 of a warp end together
     const uint8_t* ga = nullptr;
     uint8_t* out = nullptr;
     int galign = 0, total_c = 0, cur = 0, hi_blk = 0;
@@ -375,6 +377,16 @@ __global__ void __launch_bounds__(256) capcode_decode_ascii_kernel(const uint8_t
         o++;
       }
     }
+  }
+}
+
+__global__ void __launch_bounds__(256) decode_sort_keys_kernel(const uint64_t* __restrict__ raw_off,
+                                                               const uint32_t* __restrict__ len_in, uint32_t n,
+                                                               uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    const uint32_t len = len_in ? len_in[s] : uint32_t(raw_off[s + 1] - raw_off[s]);
+    key[s] = min((len >> 3) + 1u, 0xFFFFu);
+    val[s] = s;
   }
 }
 
@@ -665,13 +677,18 @@ cudaError_t launch_decode_copy(const VocabDev& v, const uint8_t* tokens, const i
 
 cudaError_t launch_capcode_decode(const uint8_t* src, const uint64_t* raw_off, uint32_t n, uint8_t* dst,
                                   uint32_t* out_len, int sms, cudaStream_t st, const uint32_t* len_in,
-                                  uint8_t* state, const UnicodeDev* uni, uint32_t* counter) {
-  // ASCII strings by the lane-per-string kernel; the rest (flagged out_len = 0xFFFFFFFF) per code point
-  cudaError_t e = cudaMemsetAsync(counter, 0, 4, st);
+                                  uint8_t* state, const UnicodeDev* uni, const SortScratch& sc) {
+  // ASCII strings by the lane-per-string kernel, longest first, 32 of equal length per warp; the
+  // rest (flagged out_len = 0xFFFFFFFF) per code point
+  cudaError_t e = cudaMemsetAsync(sc.counter, 0, 4, st);
   if (e != cudaSuccess) return e;
   const long long want = (static_cast<long long>(n) + 255) / 256;
   const int grid = int(want < sms * 4ll ? (want < 1 ? 1 : want) : sms * 4ll);
-  capcode_decode_ascii_kernel<<<grid, 256, 0, st>>>(src, raw_off, n, dst, out_len, len_in, state, uni ? 1 : 0, counter);
+  decode_sort_keys_kernel<<<grid, 256, 0, st>>>(raw_off, len_in, n, sc.key, sc.val);
+  e = sort_items_by_length(sc.temp, sc.temp_bytes, sc.key, sc.key2, sc.val, sc.order, n, st);
+  if (e != cudaSuccess) return e;
+  capcode_decode_ascii_kernel<<<grid, 256, 0, st>>>(src, raw_off, n, dst, out_len, len_in, state, uni ? 1 : 0, sc.order,
+                                                    sc.counter);
   capcode_decode_kernel<<<sms * 8, 256, 0, st>>>(src, raw_off, n, dst, out_len, len_in, state,
                                                  uni ? *uni : UnicodeDev{}, uni ? 1 : 0, 1);
   return cudaGetLastError();
