@@ -86,16 +86,6 @@ extern "C" int tmgpu_vocab_create(const uint8_t* file_bytes, size_t n, int devic
     g_err = "cudaStreamCreate failed";
     return fail(TMGPU_E_CUDA);
   }
-  if (cudaStreamCreateWithFlags(&v->stream2, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&v->join_ev, cudaEventDisableTiming) != cudaSuccess) {
-    g_err = "cudaStreamCreate failed";
-    return fail(TMGPU_E_CUDA);
-  }
-  for (auto& e : v->off_ev)
-    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
-      g_err = "cudaEventCreate failed";
-      return fail(TMGPU_E_CUDA);
-    }
   if (cudaStreamCreateWithFlags(&v->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) {
     g_err = "cudaStreamCreate failed";
     return fail(TMGPU_E_CUDA);
@@ -195,10 +185,6 @@ extern "C" void tmgpu_vocab_destroy(tmgpu_vocab* v) {
   if (v->d_off) cudaFree(v->d_off);
   if (v->h_off) cudaFreeHost(v->h_off);
   if (v->stream) cudaStreamDestroy(v->stream);
-  if (v->stream2) cudaStreamDestroy(v->stream2);
-  if (v->join_ev) cudaEventDestroy(v->join_ev);
-  for (auto& e : v->off_ev)
-    if (e) cudaEventDestroy(e);
   if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
   if (v->d2h_stream) cudaStreamDestroy(v->d2h_stream);
   for (auto& e : v->chunk_ev)
@@ -364,17 +350,6 @@ extern "C" int tmgpu_workspace_create(tmgpu_vocab* v, uint32_t max_strings, uint
   A(reinterpret_cast<uint8_t**>(&ws->p_sort_temp), ws->p_sort_bytes);
   A(&ws->p_flag, n1);
   A(&ws->p_counters, 4);
-  A(&ws->q_nlen, n1);
-  A(&ws->q_npad, n1);
-  A(&ws->q_toff, n1);
-  A(&ws->q_key, n1);
-  A(&ws->q_key2, n1);
-  A(&ws->q_val, n1);
-  A(&ws->q_order, n1);
-  A(reinterpret_cast<uint8_t**>(&ws->q_sort_temp), ws->p_sort_bytes);
-  A(&ws->q_flag, n1);
-  A(&ws->q_counters, 4);
-  A(reinterpret_cast<uint8_t**>(&ws->q_scan_temp), ws->scan_bytes);
   A(&ws->ov_list, n1);
   A(&ws->ov_begin, n1);
   A(&ws->ov_end, n1);

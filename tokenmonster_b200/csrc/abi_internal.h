@@ -130,9 +130,6 @@ struct tmgpu_vocab {
   size_t d_off_cap = 0;
   int64_t* h_off = nullptr;       // pinned, same layout
   size_t h_off_cap = 0;
-  cudaStream_t stream2 = nullptr;      // second compute stream of the chunked host path
-  cudaEvent_t off_ev[32] = {};         // chunk k's id offsets are final (chunk k+1 adds to them)
-  cudaEvent_t join_ev = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaStream_t d2h_stream = nullptr;
   double ids_per_byte = 0;        // of the previous host-buffer call (sizes the streamed-out id buffer)
@@ -183,13 +180,6 @@ struct tmgpu_workspace {
   size_t p_sort_bytes = 0;
   uint8_t* p_flag = nullptr;             // n + 1
   uint32_t* p_counters = nullptr;        // 4
-  // a second set of the per-item scratch: the chunked host path alternates two compute streams, so
-  // that the tail of chunk k (few warps left) overlaps the head of chunk k+1
-  uint32_t *q_nlen = nullptr, *q_npad = nullptr, *q_key = nullptr, *q_key2 = nullptr, *q_val = nullptr, *q_order = nullptr;
-  uint64_t* q_toff = nullptr;
-  uint8_t* q_flag = nullptr;
-  uint32_t* q_counters = nullptr;
-  void *q_sort_temp = nullptr, *q_scan_temp = nullptr;
   // strings whose normalized text did not fit the optimistic slot: redone with full-size slots
   uint32_t* ov_list = nullptr;           // n
   int64_t* ov_begin = nullptr;           // n

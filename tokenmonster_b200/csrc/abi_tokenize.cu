@@ -26,7 +26,7 @@ static int grow_device(void** p, uint64_t* cap, uint64_t want, size_t unit, cons
 // of the items' slots (0: a full batch, which the workspace was created for); the stream must be
 // idle when the buffers have to grow (every caller with need_words != 0 has just synchronised).
 static int run_pipeline(tmgpu_workspace* ws, TokenizeArgs a, bool store, cudaStream_t st, uint64_t need_words,
-                        bool slot_full = false, int set = 0, uint64_t words_base = 0, uint64_t words_len = 0) {
+                        bool slot_full = false) {
   tmgpu_vocab* v = ws->v;
   if (a.n == 0) return TMGPU_OK;
   const bool cap = !a.prenorm && v->host.capcode == 2;
@@ -37,28 +37,24 @@ static int run_pipeline(tmgpu_workspace* ws, TokenizeArgs a, bool store, cudaStr
     rc = grow_device(reinterpret_cast<void**>(&ws->p_text), &ws->p_text_cap, ws->p_words_cap, 1, "normalized text");
   }
   if (rc) return rc;
-  // `set` picks one of two sets of per-item scratch, [words_base, +words_len) the part of the word
-  // buffer this run may use: two runs on two streams then do not meet
-  a.text = text ? ws->p_text + words_base : nullptr;
-  a.words = ws->p_words + words_base;
-  a.words_cap = words_len ? words_len : ws->p_words_cap - words_base;
-  a.nlen = set ? ws->q_nlen : ws->p_nlen;
-  a.npad = set ? ws->q_npad : ws->p_npad;
-  a.toff = set ? ws->q_toff : ws->p_toff;
-  a.sort_key = set ? ws->q_key : ws->p_key;
-  a.sort_val = set ? ws->q_val : ws->p_val;
-  uint32_t* order = set ? ws->q_order : ws->p_order;
-  a.sort_order = order;
-  a.pflag = set ? ws->q_flag : ws->p_flag;
-  a.pipe_counters = set ? ws->q_counters : ws->p_counters;
+  a.text = text ? ws->p_text : nullptr;
+  a.words = ws->p_words;
+  a.words_cap = ws->p_words_cap;
+  a.nlen = ws->p_nlen;
+  a.npad = ws->p_npad;
+  a.toff = ws->p_toff;
+  a.sort_key = ws->p_key;
+  a.sort_val = ws->p_val;
+  a.sort_order = ws->p_order;
+  a.pflag = ws->p_flag;
+  a.pipe_counters = ws->p_counters;
   CU(cudaMemsetAsync(a.pipe_counters, 0, 16, st));
   ws->stage_valid = true;
   CU(cudaEventRecord(ws->stage_ev[0], st));
   CU(launch_prep(a, cap, slot_full, v->sms, st));
   CU(cudaMemsetAsync(a.npad + a.n, 0, 4, st));
-  CU(exclusive_scan_u32_to_u64(set ? ws->q_scan_temp : ws->scan_temp, ws->scan_bytes, a.npad, a.toff, a.n + 1, st));
-  CU(sort_items_by_length(set ? ws->q_sort_temp : ws->p_sort_temp, ws->p_sort_bytes, a.sort_key, set ? ws->q_key2 : ws->p_key2,
-                          a.sort_val, order, a.n, st));
+  CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, a.npad, a.toff, a.n + 1, st));
+  CU(sort_items_by_length(ws->p_sort_temp, ws->p_sort_bytes, ws->p_key, ws->p_key2, ws->p_val, ws->p_order, a.n, st));
   CU(cudaEventRecord(ws->stage_ev[1], st));
   CU(launch_table(a, cap, text, v->sms, st));
   CU(cudaEventRecord(ws->stage_ev[2], st));
@@ -385,19 +381,10 @@ int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t
     CU(cudaMemsetAsync(ws->missing, 0, size_t(n) * 4, st));
     CU(cudaMemsetAsync(ws->status, 0, n, st));
   } else if (n > 0 && chunks && !slab_off) {
-    // chunk k on stream k & 1: the tail of one chunk (few warps left) overlaps the head of the next
-    static const bool one_stream = getenv("TMGPU_ONE_STREAM") != nullptr;   // diagnostic: A/B of the two-stream schedule
-    const bool two = chunks->size() > 1 && st == v->stream && !one_stream;
-    cudaStream_t sts[2] = {st, two ? v->stream2 : st};
-    if (two) {   // the second stream starts behind the resets queued above
-      CU(cudaEventRecord(v->join_ev, st));
-      CU(cudaStreamWaitEvent(v->stream2, v->join_ev, 0));
-    }
-    const bool cap2 = v->host.capcode == 2;
-    auto word_bound = [&](uint64_t bytes, uint64_t strings) {   // words a run of strings may need (as at workspace creation)
-      return cap2 ? bytes + bytes / 4 + 64 * strings : bytes + 16 * strings;
-    };
-    int ck = 0;
+    // One compute stream: alternating chunks between two streams (so that the tail of chunk k
+    // overlaps the head of chunk k+1) was measured SLOWER -- 29.5 ms against 16.0 ms per 512 MB call
+    // on the same box: two persistent kernels fight over the SM slots and the chunk that is needed
+    // first (its ids are waited for) finishes later.
     for (const ChunkPlan& c : *chunks) {
       if (c.stage) {   // (not yet uploaded: pageable input is staged chunk by chunk)
         int rc = c.stage();
@@ -405,9 +392,7 @@ int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t
         if (rc) return rc;
       }
       if (c.s1 <= c.s0) continue;
-      const int set = two ? (ck & 1) : 0;
-      cudaStream_t cs = sts[set];
-      ck++;
+      cudaStream_t cs = st;
       if (c.ready) CU(cudaStreamWaitEvent(cs, c.ready, 0));
       TokenizeArgs b = a;
       b.off = d_off + c.s0;
@@ -419,28 +404,20 @@ int tokenize_on_stream(tmgpu_workspace* ws, const uint8_t* d_data, const int64_t
       b.need = ws->need + c.s0;
       b.missing = ws->missing + c.s0;
       b.status = ws->status + c.s0;
-      const uint64_t byte0 = c.slab_base - uint64_t(ws->slab_pad) * c.s0;
-      const uint64_t wbase = two ? (word_bound(byte0, c.s0) + 15) & ~uint64_t(15) : 0;
-      int rc = run_pipeline(ws, b, mode == 0, cs, 0, false, set, wbase, 0);
+      int rc = run_pipeline(ws, b, mode == 0, cs, 0);
       if (rc) return rc;
       if (stream_out) {
         // this chunk's offsets, dense ids and running id total, while the next chunk is still copying in
         const int ci = streamed_chunks++;
         if (ci == 0) CU(cudaMemsetAsync(v->d_run, 0, 8, cs));
-        CU(exclusive_scan_u32_to_u64(set ? ws->q_scan_temp : ws->scan_temp, ws->scan_bytes, b.counts, ws->tok_off + c.s0, b.n, cs));
-        if (ci > 0) CU(cudaStreamWaitEvent(cs, v->off_ev[ci - 1], 0));   // the running total of the chunk before
+        CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, b.counts, ws->tok_off + c.s0, b.n, cs));
         CU(launch_chunk_offsets(ws->tok_off + c.s0, b.counts, b.n, reinterpret_cast<unsigned long long*>(v->d_run + ci),
                                 c.s1 == n, v->sms, cs));
-        CU(cudaEventRecord(v->off_ev[ci], cs));
         CU(launch_pack(b.slab, b.off, ws->slab_pad, nullptr, b.counts, ws->tok_off + c.s0, dense, b.n, enc_len, v->sms, cs));
         CU(cudaMemcpyAsync(v->h_info + ci + 1, v->d_run + ci + 1, 8, cudaMemcpyDeviceToHost, cs));
         CU(cudaEventRecord(v->done_ev[ci], cs));
         ws->last_launches += 4;
       }
-    }
-    if (two) {   // everything after the chunks is queued on `st`
-      CU(cudaEventRecord(v->join_ev, v->stream2));
-      CU(cudaStreamWaitEvent(st, v->join_ev, 0));
     }
     if (stream_out) {   // everything is queued: hand each chunk's ids to the copy-out stream as it completes
       bool fits = true;

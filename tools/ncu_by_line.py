@@ -1,3 +1,9 @@
+"""Executed warp instructions, stall samples and active lanes per source LINE of one kernel.
+
+    cuobjdump -xelf all libtmgpu.so; for f in *.cubin; do nvdisasm -g -c $f; done > /tmp/all.sass
+    ncu -i report.ncu-rep --page source --csv --kernel-name regex:<kernel> > src.csv
+    python tools/ncu_by_line.py <mangled kernel name> src.csv [min percent]
+Joins the n-th SASS instruction of the kernel (nvdisasm order) with the n-th row of the source page."""
 import re,csv,sys
 from collections import defaultdict
 kname=sys.argv[1]; srccsv=sys.argv[2]; thr=float(sys.argv[3]) if len(sys.argv)>3 else 0.6
