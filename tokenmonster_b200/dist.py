@@ -262,6 +262,16 @@ class RootPipeline:
         return torch.cuda.stream(s) if self.cuda else contextlib.nullcontext()
 
     def run(self, data, off, off_cpu=None):
+        import os
+        import time
+        trace = bool(os.environ.get("TMGPU_TRACE")) and self.cuda
+        marks = []
+
+        def mark(what):   # diagnostic: wall-clock phase times with the device drained at every mark
+            if trace:
+                torch.cuda.synchronize(self.dev)
+                marks.append((what, time.perf_counter()))
+        mark("start")
         W, C, root, rank, dev = self.world, self.chunks, self.root, self.rank, self.dev
         P = W * C
         # ---- plan: one broadcast, one small D2H ------------------------------------------------
@@ -278,6 +288,7 @@ class RootPipeline:
         mine = range(rank * C, (rank + 1) * C)
         self.compute.prepare([pieces[p] for p in mine])
         cur = torch.cuda.current_stream(dev) if self.cuda else None
+        mark("plan")
         # ---- staging for the result messages (root: all pieces; others: their own) --------------
         keep = range(P) if rank == root else mine
         sizes = {p: layouts[p][1] for p in keep}
@@ -324,6 +335,7 @@ class RootPipeline:
                     a, b = bcuts[p] - bcuts[rank * C], bcuts[p + 1] - bcuts[rank * C]
                     recv_in.append(dist.irecv(self.in_data[a:b], root, group=self.g_in) if b > a else None)
             my_data, my_off, origin = self.in_data, self.in_off, cuts[rank * C]
+        mark("scatter posted")
         # ---- the root posts every gather receive up front --------------------------------------
         recv_out = []
         if rank == root:
@@ -347,12 +359,14 @@ class RootPipeline:
                     self.s_out.wait_stream(cur)
                 with self._stream(getattr(self, "s_out", None)):
                     sent.append(dist.isend(msg[p], root, group=self.g_out))
+        mark("computed")
         for w in sent:
             w.wait()
         for _, w in sends:
             w.wait()
         if self.cuda and rank == root:
             cur.wait_stream(self.s_in)
+        mark("sends done")
         # ---- overflow check (a chunk with more ids than its message has room for) ---------------
         tot = torch.stack([msg[p][0:8].view(torch.int64)[0] for p in mine]) if C else torch.zeros(0, dtype=torch.int64, device=dev)
         over = torch.stack([(tot[k] > ids_bound(pieces[rank * C + k][1], pieces[rank * C + k][0])).to(torch.int64)
@@ -364,6 +378,7 @@ class RootPipeline:
             return None
         for w in recv_out:
             w.wait()
+        mark("gathered")
         if int(over.item()):
             return self._exact(data, off)
         # ---- assemble: one D2H of the P totals, then slices ------------------------------------
@@ -380,7 +395,13 @@ class RootPipeline:
         all_counts = torch.cat(counts)
         tok_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
         tok_off[1:] = torch.cumsum(all_counts.to(torch.int64), 0)
-        return torch.cat(toks), tok_off, self.enc, torch.cat(missing), torch.cat(status)
+        out = torch.cat(toks), tok_off, self.enc, torch.cat(missing), torch.cat(status)
+        mark("assembled")
+        if trace:
+            import sys
+            print("[RootPipeline] " + ", ".join(f"{b[0]} +{(b[1] - a[1]) * 1e3:.2f} ms" for a, b in zip(marks, marks[1:])),
+                  file=sys.stderr, flush=True)
+        return out
 
     def _exact(self, data, off):
         """Fallback with exact message sizes (the synchronous scatterv / gatherv)."""
