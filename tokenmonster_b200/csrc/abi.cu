@@ -119,6 +119,12 @@ extern "C" int tmgpu_vocab_create(const uint8_t* file_bytes, size_t n, int devic
   if ((rc = upload(v, h.rev_off.data(), h.rev_off.size(), &d.rev_off))) return fail(rc);
   if ((rc = upload(v, h.rev_len.data(), h.rev_len.size(), &d.rev_len))) return fail(rc);
   if ((rc = upload(v, h.rev_blob.data(), h.rev_blob.size(), &d.rev_blob))) return fail(rc);
+  if ((rc = upload(v, h.rev_pack.data(), h.rev_pack.size(), &d.rev_pack))) return fail(rc);
+  {
+    const uint64_t* b8 = nullptr;
+    if ((rc = upload(v, h.rev_blob8.data(), h.rev_blob8.size(), &b8))) return fail(rc);
+    d.rev_blob8 = reinterpret_cast<const unsigned long long*>(b8);
+  }
   {
     const uint32_t* bk = nullptr;
     const uint32_t* hot = nullptr;

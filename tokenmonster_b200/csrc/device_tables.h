@@ -68,6 +68,8 @@ struct VocabDev {
   const uint32_t* rev_off;     // decode: reverse[id] offset into rev_blob
   const uint8_t* rev_len;      // 0xFF = nil
   const uint8_t* rev_blob;
+  const uint32_t* rev_pack;    // decode: offset into rev_blob8 (8-byte units) | length << 24, 0 = nothing
+  const unsigned long long* rev_blob8;
   uint32_t n_info, n_reverse;
   uint32_t unk, delete_token;  // ids or 0xFFFFFF
   uint32_t space_start;        // trie state after the virtual space prefix, or kNoVal

@@ -115,13 +115,11 @@ __device__ __forceinline__ uint32_t load_id(const uint8_t* t, uint64_t k, int en
   return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16);
 }
 
-// length of reverse[id], 0 for out-of-range / nil ids.  The 16-bit path compares against
-// uint16(len(reverse) - 1) like go/tokenmonster.go:861-864.
-__device__ __forceinline__ uint32_t rev_length(const VocabDev& V, uint32_t id, int enc) {
-  bool ok = (enc == 2) ? (V.n_reverse != 0 && id <= ((V.n_reverse - 1) & 0xFFFFu)) : (id < V.n_reverse);
-  if (!ok) return 0;
-  uint32_t l = V.rev_len[id];
-  return l == 0xFF ? 0 : l;
+// reverse[id] as one word: offset into rev_blob8 | length << 24; 0 for out-of-range / nil ids.  The
+// 16-bit path compares against uint16(len(reverse) - 1) like go/tokenmonster.go:861-864.
+__device__ __forceinline__ uint32_t rev_entry(const VocabDev& V, uint32_t id, int enc) {
+  const bool ok = (enc == 2) ? (V.n_reverse != 0 && id <= ((V.n_reverse - 1) & 0xFFFFu)) : (id < V.n_reverse);
+  return ok ? __ldg(&V.rev_pack[id]) : 0u;
 }
 
 __global__ void __launch_bounds__(256) decode_size_kernel(VocabDev V, const uint8_t* __restrict__ tokens,
@@ -133,21 +131,26 @@ __global__ void __launch_bounds__(256) decode_size_kernel(VocabDev V, const uint
   for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n; s += warps) {
     const uint64_t t0 = uint64_t(tok_off[s]), t1 = uint64_t(tok_off[s + 1]);
     uint32_t sum = 0;
-    for (uint64_t k = t0 + lane; k < t1; k += 32) sum += rev_length(V, load_id(tokens, k, enc), enc);
+    for (uint64_t k = t0 + lane; k < t1; k += 32) sum += rev_entry(V, load_id(tokens, k, enc), enc) >> 24;
 #pragma unroll
     for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
     if (lane == 0) raw_len[s] = sum + (prefix_off ? uint32_t(prefix_off[s + 1] - prefix_off[s]) : 0u);
   }
 }
 
+// One warp per string, 32 ids per round: every lane looks its id up (one word), a warp prefix sum
+// places the keys, each lane drops its key -- read 8 bytes at a time -- into a shared-memory window,
+// and the warp writes the window out with consecutive lanes on consecutive bytes.
 __global__ void __launch_bounds__(256) decode_copy_kernel(VocabDev V, const uint8_t* __restrict__ tokens,
                                                           const int64_t* __restrict__ tok_off, uint32_t n, int enc,
                                                           const uint64_t* __restrict__ raw_off,
                                                           uint8_t* __restrict__ out,
                                                           const uint64_t* __restrict__ prefix_off,
                                                           const uint8_t* __restrict__ prefix) {
+  __shared__ uint8_t s_win[8][32 * 40];
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
+  uint8_t* win = s_win[threadIdx.x >> 5];
   for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n; s += warps) {
     const uint64_t t0 = uint64_t(tok_off[s]), t1 = uint64_t(tok_off[s + 1]);
     uint64_t at = raw_off[s];
@@ -158,23 +161,30 @@ __global__ void __launch_bounds__(256) decode_copy_kernel(VocabDev V, const uint
     }
     for (uint64_t kb = t0; kb < t1; kb += 32) {
       const uint64_t k = kb + lane;
-      uint32_t id = 0, l = 0;
-      if (k < t1) {
-        id = load_id(tokens, k, enc);
-        l = rev_length(V, id, enc);
-      }
+      const uint32_t e = (k < t1) ? rev_entry(V, load_id(tokens, k, enc), enc) : 0u;
+      const uint32_t l = e >> 24;
       uint32_t incl = l;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
         if (lane >= d) incl += t;
       }
       const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
       if (l) {
-        const uint8_t* src = V.rev_blob + V.rev_off[id];
-        uint8_t* dst = out + at + (incl - l);
-        for (uint32_t b = 0; b < l; b++) dst[b] = src[b];
+        const unsigned long long* src = V.rev_blob8 + (e & 0xFFFFFFu);
+        uint8_t* dst = win + (incl - l);
+        for (uint32_t b = 0; b < l; b += 8) {
+          unsigned long long w = __ldg(src + (b >> 3));
+          const uint32_t m = l - b < 8u ? l - b : 8u;
+          for (uint32_t j = 0; j < m; j++) {
+            dst[b + j] = uint8_t(w);
+            w >>= 8;
+          }
+        }
       }
+      __syncwarp();
+      for (uint32_t b = lane; b < total; b += 32) out[at + b] = win[b];
+      __syncwarp();
       at += total;
     }
   }

@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(256) select_overflowed_kernel(const uint8_t* _
 // normalized byte: if its byte queue is empty it first encodes the next raw character (0..4 bytes,
 // one table read decides), then the automaton takes one byte and the position word goes out (16
 // bytes at a time, right aligned in the string's slot, so the slot's start need not be known).
+// (Splitting the loop into two phases -- encode 8 characters into a shared-memory buffer, then the
+// automaton over their bytes -- was measured slower: 6.6 against 5.6 ms.)
 // Raw text comes in through a 32-byte ring per lane in shared memory, filled 16 bytes at a time
 // by cp.async (SASS: LDGSTS) -- no registers, no wait: the copy is issued when the cursor is
 // still 8+ characters away, and by all lanes of the warp in the same iteration.
@@ -177,13 +179,11 @@ __device__ __forceinline__ void pipe_cp_async_wait() { asm volatile("cp.async.wa
 template <bool CAP, bool TEXT>
 __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A) {
   constexpr unsigned FULL = 0xFFFFFFFFu;
-  constexpr int kBatch = 8;                    // raw characters encoded per round
   __shared__ __align__(128) uint8_t s_img[kPipeImageBytes];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint8_t s_cls[256];
   __shared__ uint32_t s_lut[CAP ? kCapLutSize : 1];
-  __shared__ __align__(16) uint32_t s_ring[kPipeBlock * 16];  // raw text: word w of lane l at [warp * 512 + w * 32 + l]
-  __shared__ __align__(16) uint32_t s_norm[kPipeBlock * 8];   // normalized bytes of one round, same interleaving
+  __shared__ __align__(16) uint32_t s_ring[kPipeBlock * 8];   // word w of lane l: [warp * 256 + w * 32 + l]
   pipe_stage_tma(s_img, A.v.pipe_image, &s_bar);
   s_cls[threadIdx.x & 255] = uint8_t((threadIdx.x & 255) < 128 ? pc_class_sp(threadIdx.x & 255) : uint32_t(PC_O));
   if (CAP)
@@ -198,8 +198,7 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
   const uint32_t code0 = s_code[0];
   const int lane = threadIdx.x & 31;
   uint32_t* counter = A.pipe_counters + 2;
-  const uint32_t ring_b = pipe_smem_u32(s_ring + (threadIdx.x >> 5) * 512 + lane);   // byte address of word 0
-  const uint32_t norm_b = pipe_smem_u32(s_norm + (threadIdx.x >> 5) * 256 + lane);
+  const uint32_t ring_b = pipe_smem_u32(s_ring + (threadIdx.x >> 5) * 256 + lane);   // byte address of word 0
 
   for (;;) {
     uint32_t g = 0;
@@ -212,7 +211,7 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
     uint32_t item = 0, s = 0, slot = 0;
     int k = -1, galign = 0, total_c = 0;
     int fcur = -1;       // aligned coordinate of the next raw byte the read-ahead takes
-    int lo_blk = 0;      // lowest 16-byte block in the ring (up to four blocks from lo_blk on are there)
+    int lo_blk = 0;      // lowest 16-byte block in the ring (blocks lo_blk and lo_blk + 1 are there)
     const uint8_t* ga = nullptr;
     uint32_t* wend = nullptr;
     uint8_t* tend = nullptr;
@@ -243,7 +242,7 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
     // 16 raw bytes of block blk -> the ring (bytes behind the end of the string read as 0)
     auto load_block = [&](int blk) {
       const int c0 = blk << 4;
-      const uint32_t dst = ring_b + uint32_t((blk & 3) * 4) * 128u;
+      const uint32_t dst = ring_b + uint32_t((blk & 1) * 4) * 128u;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const int left = total_c - (c0 + 4 * j);
@@ -254,14 +253,14 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
     auto take = [&]() -> uint32_t {
       const int x = fcur--;
       uint32_t b;
-      // entering a block (x & 15 == 15): wait for its copy, which was issued 16+ characters ago
+      // entering a block (x & 15 == 15): wait for its copy, which was issued long ago; then one byte
       asm volatile(
           "{\n\t.reg .pred p;\n\t"
           "setp.eq.u32 p, %2, 15;\n\t"
           "@p cp.async.wait_all;\n\t"
           "ld.shared.u8 %0, [%1];\n\t}"
           : "=r"(b)
-          : "r"(ring_b + uint32_t((x >> 2) & 15) * 128u + uint32_t(x & 3)), "r"(uint32_t(x) & 15u)
+          : "r"(ring_b + uint32_t((x >> 2) & 7) * 128u + uint32_t(x & 3)), "r"(uint32_t(x) & 15u)
           : "memory");
       bad = bad | (want_ascii & ((b & 0x80u) != 0));
       if (to_lower && b - 'A' < 26u) b |= 0x20u;
@@ -270,9 +269,9 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
     uint32_t x0 = 0, x1 = 0, x2 = 0;   // read-ahead: characters k, k-1, k-2
     if (active && k >= 0) {
       const int top = (total_c - 1) >> 4;
-      lo_blk = top;
       load_block(top);
-      for (int j = 0; j < 2 && lo_blk > 0; j++) load_block(--lo_blk);
+      if (top > 0) load_block(top - 1);
+      lo_blk = top > 0 ? top - 1 : 0;
       pipe_cp_async_wait();
       fcur = total_c - 1;
       x0 = take();
@@ -283,89 +282,82 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
     revcap_reset(e);
     ClassTrail tr;
     trail_reset(tr, code0);
-    uint32_t packed = 0, dist = 0;
+    uint32_t packed = 0, qbytes = 0, qn = 0, dist = 0;
     uint4 wbuf = make_uint4(0, 0, 0, 0);
 
     while (__any_sync(FULL, active)) {
-      // ---- ring refill: the block behind the lowest one, as soon as the cursor is within the last two
-      if (active && lo_blk > 0 && (fcur >> 4) <= lo_blk + 1) load_block(--lo_blk);
-      // ---- phase A: encode up to kBatch raw characters into this lane's byte buffer, in the order
-      //      the automaton takes them (a character's bytes last byte first) --------------------------
-      uint32_t nn = 0;
-#pragma unroll 1
-      for (int c = 0; c < kBatch; c++) {
-        if (!active || k < 0 || bad) break;
-        uint32_t bytes, cnt;
-        if (CAP) {
-          cnt = revcap_step(e, s_lut, x0, x1, x2, k,
-                            [&](int j) -> uint32_t {
-                              uint32_t ch = ga[galign + j];
-                              if (to_lower && ch - 'A' < 26u) ch |= 0x20u;
-                              return s_cls[ch];
-                            },
-                            &bytes);
-          x0 = x1;
-          x1 = x2;
-          x2 = (k >= 3) ? take() : 0u;
-        } else {
-          bytes = x0 & 0xFFu;
-          cnt = 1;
-          x0 = (k >= 1) ? take() : 0u;
-        }
-        k--;
-        for (uint32_t j = cnt; j > 0; j--) {   // bytes of this character, last first
-          const uint32_t v = (bytes >> (8u * (j - 1u))) & 0xFFu;
-          asm volatile("st.shared.u8 [%0], %1;" ::"r"(norm_b + (nn >> 2) * 128u + (nn & 3u)), "r"(v) : "memory");
-          nn++;
+      // ---- ring refill, all lanes of the warp together ----------------------------------------
+      const bool want = active && lo_blk > 0 && fcur >= galign && (fcur >> 4) <= lo_blk;
+      if (__any_sync(FULL, want && (fcur & 15) <= 8)) {
+        if (want) {
+          lo_blk--;
+          load_block(lo_blk);
         }
       }
-      // ---- phase B: the automaton over those bytes -----------------------------------------------
-      const uint32_t rounds = __reduce_max_sync(FULL, (active && !bad) ? nn : 0u);
-#pragma unroll 1
-      for (uint32_t j = 0; j < rounds; j++) {
-        if (!active || bad || j >= nn) continue;
-        uint32_t b;
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(norm_b + (j >> 2) * 128u + (j & 3u)) : "memory");
-        if (dist >= slot) {   // more text than the slot holds: redone with a full-size slot
-          A.nlen[item] = 0;
-          A.pflag[item] = 3;
-          A.counts[s] = 0; A.need[s] = 0; A.missing[s] = 0; A.status[s] = 14;
-          active = false;
-          continue;
+      if (active) {
+        if (qn == 0 || bad) {
+          if (k < 0 || bad) {
+            // ---- the string is done: the last (partial) group of words, the verdict ------------
+            const uint32_t r = dist & 3u;
+            if (!bad && r) {
+              uint32_t* d = wend - dist;
+              d[0] = wbuf.x;
+              if (r > 1) d[1] = wbuf.y;
+              if (r > 2) d[2] = wbuf.z;
+            }
+            A.nlen[item] = bad ? 0u : dist;
+            A.pflag[item] = bad ? 1 : 0;
+            if (bad) { A.counts[s] = 0; A.need[s] = 0; A.missing[s] = 0; A.status[s] = 13; }
+            active = false;
+          } else if (CAP) {
+            qn = revcap_step(e, s_lut, x0, x1, x2, k,
+                             [&](int j) -> uint32_t {
+                               uint32_t c = ga[galign + j];
+                               if (to_lower && c - 'A' < 26u) c |= 0x20u;
+                               return s_cls[c];
+                             },
+                             &qbytes);
+            x0 = x1;
+            x1 = x2;
+            x2 = (k >= 3) ? take() : 0u;
+            k--;
+          } else {
+            qbytes = x0 & 0xFFu;
+            qn = 1;
+            x0 = (k >= 1) ? take() : 0u;
+            k--;
+          }
         }
-        packed = dfa_next(packed, b, D.shift, D.mask,
-                          [&](uint32_t i, uint4* kk, uint4* vv) { pipe_load32(D.buckets + 2 * i, kk, vv); },
-                          [&](uint32_t c) { return s_d1[c]; });
-        const uint32_t code = s_code[b];
-        const uint32_t w = position_word(packed, code, tr, voff);
-        trail_push(tr, code);
-        dist++;
-        if (TEXT) tend[-int64_t(dist)] = uint8_t(b);
-        wbuf.w = wbuf.z;
-        wbuf.z = wbuf.y;
-        wbuf.y = wbuf.x;
-        wbuf.x = w;
-        // every 4th word: one 16-byte store (predicated, not a branch: the lanes' phases differ)
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.eq.u32 p, %5, 0;\n\t"
-            "@p st.global.v4.u32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(wend - dist),
-            "r"(wbuf.x), "r"(wbuf.y), "r"(wbuf.z), "r"(wbuf.w), "r"(dist & 3u)
-            : "memory");
-      }
-      // ---- the string is done: the last (partial) group of words, the verdict ---------------------
-      if (active && (k < 0 || bad)) {
-        const uint32_t r = dist & 3u;
-        if (!bad && r) {
-          uint32_t* d = wend - dist;
-          d[0] = wbuf.x;
-          if (r > 1) d[1] = wbuf.y;
-          if (r > 2) d[2] = wbuf.z;
+        if (active && qn != 0 && !bad) {
+          const uint32_t b = (qbytes >> (8u * (qn - 1u))) & 0xFFu;
+          qn--;
+          if (dist >= slot) {   // more text than the slot holds: redone with a full-size slot
+            A.nlen[item] = 0;
+            A.pflag[item] = 3;
+            A.counts[s] = 0; A.need[s] = 0; A.missing[s] = 0; A.status[s] = 14;
+            active = false;
+          } else {
+            packed = dfa_next(packed, b, D.shift, D.mask,
+                              [&](uint32_t i, uint4* kk, uint4* vv) { pipe_load32(D.buckets + 2 * i, kk, vv); },
+                              [&](uint32_t c) { return s_d1[c]; });
+            const uint32_t code = s_code[b];
+            const uint32_t w = position_word(packed, code, tr, voff);
+            trail_push(tr, code);
+            dist++;
+            if (TEXT) tend[-int64_t(dist)] = uint8_t(b);
+            wbuf.w = wbuf.z;
+            wbuf.z = wbuf.y;
+            wbuf.y = wbuf.x;
+            wbuf.x = w;
+            // every 4th word: one 16-byte store (predicated, not a branch: the lanes' phases differ)
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.eq.u32 p, %5, 0;\n\t"
+                "@p st.global.v4.u32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(wend - dist),
+                "r"(wbuf.x), "r"(wbuf.y), "r"(wbuf.z), "r"(wbuf.w), "r"(dist & 3u)
+                : "memory");
+          }
         }
-        A.nlen[item] = bad ? 0u : dist;
-        A.pflag[item] = bad ? 1 : 0;
-        if (bad) { A.counts[s] = 0; A.need[s] = 0; A.missing[s] = 0; A.status[s] = 13; }
-        active = false;
       }
     }
   }

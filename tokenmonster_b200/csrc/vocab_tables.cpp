@@ -354,6 +354,16 @@ int parse_vocab(const uint8_t* file, size_t n, HostTables* t, std::string* err) 
     t->rev_len[id[i]] = keys[i].len;
   }
   t->rev_blob = blob;
+  t->rev_pack.assign(t->n_reverse, 0);
+  for (uint32_t id = 0; id < t->n_reverse; id++) {
+    const uint32_t l = t->rev_len[id];
+    if (l == 0xFF || l == 0) continue;
+    const uint32_t at = uint32_t(t->rev_blob8.size());
+    t->rev_blob8.resize(at + (l + 7) / 8, 0);
+    std::memcpy(&t->rev_blob8[at], &blob[t->rev_off[id]], l);
+    t->rev_pack[id] = at | (l << 24);
+  }
+  t->rev_blob8.push_back(0);
 
   // ---- prefix trie ---------------------------------------------------------------------
   std::unordered_map<std::string_view, uint32_t> node_of;

@@ -82,6 +82,10 @@ struct HostTables {
   std::vector<uint32_t> rev_off; // n_reverse, offset into rev_blob
   std::vector<uint8_t> rev_len;  // n_reverse, 0xFF = nil
   std::vector<uint8_t> rev_blob;
+  // the same, laid out for the decode kernels: one word per id = offset into rev_blob8 in 8-byte
+  // units | length << 24 (0 = nil / no bytes); every key starts on an 8-byte boundary
+  std::vector<uint32_t> rev_pack;
+  std::vector<uint64_t> rev_blob8;
 };
 
 // returns 0 or a TMGPU_E_* code; err receives a message

@@ -168,15 +168,14 @@ def ids_bound(n_bytes: int, n_strings: int) -> int:
 
 def plan_pieces(off_cpu: torch.Tensor, pieces: int):
     """Byte-balanced cuts of the batch into `pieces` contiguous runs of strings (host arithmetic on
-    the offsets; no device work)."""
-    rel = (off_cpu - off_cpu[0]).to(torch.int64)
-    n = rel.numel() - 1
-    total = int(rel[-1])
-    targets = torch.tensor([total * p // pieces for p in range(1, pieces)], dtype=torch.int64)
-    inner = torch.searchsorted(rel, targets, right=False) if pieces > 1 else torch.zeros(0, dtype=torch.int64)
+    the offsets: `pieces` binary searches, no pass over the array, no device work)."""
+    n = off_cpu.numel() - 1
+    off0, total = int(off_cpu[0]), int(off_cpu[-1]) - int(off_cpu[0])
+    targets = torch.tensor([off0 + total * p // pieces for p in range(1, pieces)], dtype=off_cpu.dtype)
+    inner = torch.searchsorted(off_cpu, targets, right=False) if pieces > 1 else torch.zeros(0, dtype=torch.int64)
     cuts = torch.cat([torch.zeros(1, dtype=torch.int64), torch.clamp(inner, 0, n), torch.tensor([n])])
     cuts = torch.cummax(cuts, 0).values
-    return cuts, rel[cuts]
+    return cuts, off_cpu[cuts].to(torch.int64) - off0
 
 
 def _msg_layout(n_strings: int, n_bytes: int, enc: int):
@@ -302,24 +301,29 @@ class RootPipeline:
         # ---- scatter ---------------------------------------------------------------------------
         recv_in, sends = [], []
         if rank == root:
-            rel = (off - off[0]).to(torch.int64)
-            base = off[:1]
+            b0 = int(off_cpu[0]) if off_cpu is not None else int(off[:1].item())
             if self.cuda:
                 self.s_in.wait_stream(cur)
             with self._stream(getattr(self, "s_in", None)):
-                for r in range(W):
+                ops, keep = [], []
+                for r in range(W):   # every rank's offsets, rebased to the start of its share
                     if r == root:
                         continue
-                    o = (rel[cuts[r * C]: cuts[(r + 1) * C] + 1] - bcuts[r * C]).contiguous()
-                    sends.append((o, dist.isend(o, r, group=self.g_in)))
-                b0 = int(off_cpu[0]) if off_cpu is not None else int(base.item())
-                for k in range(C):
+                    o = (off[cuts[r * C]: cuts[(r + 1) * C] + 1] - (b0 + bcuts[r * C])).contiguous()
+                    keep.append(o)
+                    ops.append(dist.P2POp(dist.isend, o, r, self.g_in))
+                for w in (dist.batch_isend_irecv(ops) if ops else []):
+                    sends.append((keep, w))
+                for k in range(C):   # then the bytes, chunk by chunk: ONE grouped NCCL launch per chunk
+                    ops = []
                     for r in range(W):
                         p = r * C + k
                         if r == root or pieces[p][1] == 0:
                             continue
                         d = data[b0 + bcuts[p]: b0 + bcuts[p + 1]]
-                        sends.append((d, dist.isend(d, r, group=self.g_in)))
+                        ops.append(dist.P2POp(dist.isend, d, r, self.g_in))
+                    for w in (dist.batch_isend_irecv(ops) if ops else []):
+                        sends.append((data, w))
             my_data, my_off, origin = data, off, 0
         else:
             nb = bcuts[(rank + 1) * C] - bcuts[rank * C]
@@ -341,9 +345,9 @@ class RootPipeline:
         if rank == root:
             with self._stream(getattr(self, "s_out", None)):
                 for k in range(C):
-                    for r in range(W):
-                        if r != root:
-                            recv_out.append(dist.irecv(msg[r * C + k], r, group=self.g_out))
+                    ops = [dist.P2POp(dist.irecv, msg[r * C + k], r, self.g_out) for r in range(W) if r != root]
+                    if ops:
+                        recv_out += dist.batch_isend_irecv(ops)
         # ---- compute chunk by chunk; each result goes out as soon as it exists ------------------
         sent = []
         if rank != root:
