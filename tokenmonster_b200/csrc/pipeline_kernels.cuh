@@ -174,6 +174,17 @@ __global__ void __launch_bounds__(256) select_overflowed_kernel(const uint8_t* _
 __device__ __forceinline__ void pipe_cp_async4(uint32_t smem_addr, const void* gptr, int src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_addr), "l"(gptr), "r"(src_bytes) : "memory");
 }
+// one 4-byte word of a string into the ring: asynchronous when the whole word belongs to the string,
+// byte by byte for the last partial word (nothing behind the end of the string is ever read)
+__device__ __forceinline__ void pipe_ring_word(uint32_t smem_addr, const uint8_t* g, int left) {
+  if (left >= 4) {
+    pipe_cp_async4(smem_addr, g, 4);
+  } else {
+    uint32_t w = 0;
+    for (int t = 0; t < left; t++) w |= uint32_t(g[t]) << (8 * t);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(smem_addr), "r"(w) : "memory");
+  }
+}
 __device__ __forceinline__ void pipe_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <bool CAP, bool TEXT>
@@ -244,10 +255,7 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
       const int c0 = blk << 4;
       const uint32_t dst = ring_b + uint32_t((blk & 1) * 4) * 128u;
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int left = total_c - (c0 + 4 * j);
-        pipe_cp_async4(dst + uint32_t(j) * 128u, ga + c0 + 4 * j, left >= 4 ? 4 : (left > 0 ? left : 0));
-      }
+      for (int j = 0; j < 4; j++) pipe_ring_word(dst + uint32_t(j) * 128u, ga + c0 + 4 * j, total_c - (c0 + 4 * j));
     };
     // the raw character at coordinate fcur, with its class: character | class << 8
     auto take = [&]() -> uint32_t {
