@@ -256,7 +256,6 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
       const uint32_t dst = ring_b + uint32_t((blk & 1) * 4) * 128u;
 #pragma unroll
       if (c0 + 16 <= total_c) {   // the whole block belongs to the string: four asynchronous 4-byte copies
-#pragma unroll
         for (int j = 0; j < 4; j++) pipe_cp_async4(dst + uint32_t(j) * 128u, ga + c0 + 4 * j, 4);
       } else {                    // the string's last block (once per string)
         for (int j = 0; j < 4; j++) pipe_ring_word(dst + uint32_t(j) * 128u, ga + c0 + 4 * j, total_c - (c0 + 4 * j));

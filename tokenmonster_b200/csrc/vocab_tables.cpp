@@ -216,24 +216,32 @@ static int build_dfa(HostTables* t, const std::vector<KeyRef>& keys, const std::
   t->dfa_buckets.assign((size_t(1) << bits) * 8, 0);
   for (size_t b = 0; b < (size_t(1) << bits); b++)
     for (int k = 0; k < 4; k++) t->dfa_buckets[b * 8 + k] = kDfaEmpty;
-  for (uint32_t s = 1; s < N; s++) {
-    for (uint32_t e : row[s]) {
-      const uint32_t tgt = e & 0xFFFFFFu;
-      const uint32_t key = (s << 8) | (e >> 24);
-      uint32_t h = dfa_hash(key, shift);
-      for (;;) {
-        uint32_t* bk = &t->dfa_buckets[size_t(h) * 8];
-        int slot = -1;
-        for (int k = 0; k < 4; k++)
-          if ((bk[k] & ~kDfaOverflow) == kDfaEmpty) { slot = k; break; }
-        if (slot >= 0) {
-          bk[slot] = (bk[slot] & kDfaOverflow) | key;
-          bk[4 + slot] = pack(tgt);
-          break;
-        }
-        bk[0] |= kDfaOverflow;
-        h = (h + 1) & mask;
+  // Insert the transitions to SHALLOW targets first: a full bucket pushes later keys into the next
+  // one (a second dependent probe for the whole warp), and short suffixes are what text visits most,
+  // so the keys that end up displaced should be the deep, rare ones.
+  std::vector<std::pair<uint32_t, uint32_t>> trans;   // key, packed target -- bucketed by target depth
+  trans.reserve(n_deep);
+  for (uint32_t depth = 2; depth <= 41; depth++)
+    for (uint32_t s = 1; s < N; s++)
+      for (uint32_t e : row[s]) {
+        const uint32_t tgt = e & 0xFFFFFFu;
+        if (nodes[tgt].depth == depth) trans.emplace_back((s << 8) | (e >> 24), pack(tgt));
       }
+  for (const auto& kv : trans) {
+    const uint32_t key = kv.first;
+    uint32_t h = dfa_hash(key, shift);
+    for (;;) {
+      uint32_t* bk = &t->dfa_buckets[size_t(h) * 8];
+      int slot = -1;
+      for (int k = 0; k < 4; k++)
+        if ((bk[k] & ~kDfaOverflow) == kDfaEmpty) { slot = k; break; }
+      if (slot >= 0) {
+        bk[slot] = (bk[slot] & kDfaOverflow) | key;
+        bk[4 + slot] = kv.second;
+        break;
+      }
+      bk[0] |= kDfaOverflow;
+      h = (h + 1) & mask;
     }
   }
   return TMGPU_OK;
