@@ -316,8 +316,8 @@ __global__ void __launch_bounds__(256) capcode_decode_ascii_kernel(const uint8_t
     auto load_block = [&](int blk) {
       const int c0 = blk << 4;
       const uint32_t d = ring_b + uint32_t((blk & 1) * 4) * 128u;
-#pragma unroll
       if (c0 + 16 <= total_c) {
+#pragma unroll
         for (int j = 0; j < 4; j++) pipe_cp_async4(d + uint32_t(j) * 128u, ga + c0 + 4 * j, 4);
       } else {
         for (int j = 0; j < 4; j++) pipe_ring_word(d + uint32_t(j) * 128u, ga + c0 + 4 * j, total_c - (c0 + 4 * j));
