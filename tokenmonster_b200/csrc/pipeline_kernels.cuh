@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
   __shared__ uint8_t s_cls[256];
   __shared__ uint32_t s_lut[CAP ? kCapLutSize : 1];
   __shared__ __align__(16) uint32_t s_ring[kPipeBlock * 8];   // word w of lane l: [warp * 256 + w * 32 + l]
+  __shared__ uint4 s_stash[kPipeBlock];                       // four position words per lane, see the store below
   pipe_stage_tma(s_img, A.v.pipe_image, &s_bar);
   s_cls[threadIdx.x & 255] = uint8_t((threadIdx.x & 255) < 128 ? pc_class_sp(threadIdx.x & 255) : uint32_t(PC_O));
   if (CAP)
@@ -210,6 +211,7 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
   const int lane = threadIdx.x & 31;
   uint32_t* counter = A.pipe_counters + 2;
   const uint32_t ring_b = pipe_smem_u32(s_ring + (threadIdx.x >> 5) * 256 + lane);   // byte address of word 0
+  const uint32_t stash_b = pipe_smem_u32(s_stash + threadIdx.x);
 
   for (;;) {
     uint32_t g = 0;
@@ -310,10 +312,14 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
         if (qn == 0 || bad) {
           if (k < 0 || bad) {
             // ---- the string is done: the last (partial) group of words, the verdict ------------
-            const uint32_t r = dist & 3u;
+            uint32_t r = dist & 7u;
             if (!bad && r) {
               uint32_t* d = wend - dist;
-              d[0] = wbuf.x;
+              if (r >= 4) {   // the waiting upper half of the last sector (for r == 4 it is wbuf itself)
+                *reinterpret_cast<uint4*>(d + (r - 4)) = r == 4 ? wbuf : s_stash[threadIdx.x];
+                r -= 4;
+              }
+              if (r > 0) d[0] = wbuf.x;
               if (r > 1) d[1] = wbuf.y;
               if (r > 2) d[2] = wbuf.z;
             }
@@ -361,12 +367,17 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
             wbuf.z = wbuf.y;
             wbuf.y = wbuf.x;
             wbuf.x = w;
-            // every 4th word: one 16-byte store (predicated, not a branch: the lanes' phases differ)
+            // every 8th word: one 32-byte store of a whole sector (SASS: STG.256) -- the upper four
+            // words wait in shared memory in between, because a 16-byte store makes L2 fetch the rest
+            // of its sector from DRAM.  Predicated, not a branch: the lanes' phases differ.
             asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "setp.eq.u32 p, %5, 0;\n\t"
-                "@p st.global.v4.u32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(wend - dist),
-                "r"(wbuf.x), "r"(wbuf.y), "r"(wbuf.z), "r"(wbuf.w), "r"(dist & 3u)
+                "{\n\t.reg .pred p, q;\n\t.reg .b32 t0, t1, t2, t3;\n\t"
+                "setp.eq.u32 p, %5, 4;\n\t"
+                "setp.eq.u32 q, %5, 0;\n\t"
+                "@p st.shared.v4.u32 [%6], {%1, %2, %3, %4};\n\t"
+                "@q ld.shared.v4.u32 {t0, t1, t2, t3}, [%6];\n\t"
+                "@q st.global.v8.u32 [%0], {%1, %2, %3, %4, t0, t1, t2, t3};\n\t}" ::"l"(wend - dist),
+                "r"(wbuf.x), "r"(wbuf.y), "r"(wbuf.z), "r"(wbuf.w), "r"(dist & 7u), "r"(stash_b)
                 : "memory");
           }
         }
