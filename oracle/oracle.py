@@ -71,6 +71,7 @@ def _bind(path: str, p: str):
                                             C.POINTER(C.c_uint64)])
         api["longest_prefix"] = f("longest_prefix", C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32)])
         api["capcode_encode"] = f("capcode_encode", C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)])
+        api["capcode_decode"] = f("capcode_decode", C.c_size_t, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p])
         api["incomplete_utf8"] = f("incomplete_utf8", C.c_int, [C.c_char_p, C.c_size_t])
         api["incomplete_utf16"] = f("incomplete_utf16", C.c_int, [C.c_char_p, C.c_size_t])
         api["ids_checksum"] = f("ids_checksum", C.c_uint64, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32])
@@ -229,6 +230,16 @@ def capcode_encode(data: bytes) -> bytes:
     out = C.string_at(p.value, n.value) if n.value else b""
     api["free"](p.value)
     return out
+
+
+def capcode_decode(data: bytes, state: int = 0) -> tuple[bytes, int]:
+    """Stateful capcode level-2 decode of one piece of text (tmo_capcode_decode).  `state` packs the
+    decoder's flags as the device does: 1 inWord, 2 inChar, 4 delete, 8 ignore.  Returns (bytes, state)."""
+    api = _api("port")
+    st = (C.c_uint8 * 4)(state & 1, (state >> 1) & 1, (state >> 2) & 1, (state >> 3) & 1)
+    out = C.create_string_buffer(len(data) + 1)
+    n = api["capcode_decode"](st, data, len(data), out)
+    return out.raw[:n], int(st[0]) | (int(st[1]) << 1) | (int(st[2]) << 2) | (int(st[3]) << 3)
 
 
 def ids_checksum(tokens_u8: np.ndarray, enc_len: int, tok_off: np.ndarray, n: int) -> int:

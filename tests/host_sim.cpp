@@ -13,6 +13,7 @@
 
 #include "../tokenmonster_b200/csrc/pipeline_core.h"
 #include "../tokenmonster_b200/csrc/vocab_tables.h"
+#include "../tokenmonster_b200/csrc/capdec_tables.inc"   // the decode kernel's transducer tables (host copy)
 
 using namespace tmgpu;
 
@@ -175,6 +176,54 @@ long hs_tokenize(void* h, const uint8_t* data, size_t n, int prenorm, int count_
   while (z.i < L) chain_step(T, cs, z, count_mode == 0, load32, emit, on_miss);
   *missing = z.miss;
   return long(count_mode ? z.cnt : cnt);
+}
+
+// The warp algorithm of capcode_decode_scan_kernel (csrc/capcode_decode_scan.cuh) for one string,
+// lane by lane, on the kernel's own tables: 512-byte rounds from the 16-byte aligned address below
+// the string (galign = the string's offset from it), 16 bytes per lane, bytes outside the string
+// read as 0xFF; a monoid id per lane, the scan, the second pass from the scanned start state.
+// Returns the output length, -1 for text with a byte >= 0x80; *st_io = decoder flags in / out.
+long hs_capdec_scan(const uint8_t* in, size_t len, int galign, uint8_t* st_io, uint8_t* out) {
+  const long long total_c = (long long)galign + (long long)len;
+  uint32_t st = *st_io & 15u;
+  size_t o = 0;
+  for (long long base_c = 0; base_c < total_c; base_c += 512) {
+    uint8_t bytes[32][16];
+    uint32_t m[32], incl[32];
+    for (int lane = 0; lane < 32; lane++) {
+      m[lane] = 0;
+      for (int j = 0; j < 16; j++) {
+        const long long c = base_c + lane * 16 + j;
+        uint8_t b = 0xFF;
+        if (c >= galign && c < total_c) {
+          b = in[c - galign];
+          if (b & 0x80) return -1;
+        }
+        bytes[lane][j] = b;
+        m[lane] = kCapdecComp[m[lane] * 256u + b];
+      }
+    }
+    for (int lane = 0; lane < 32; lane++) incl[lane] = m[lane];
+    for (int d = 1; d < 32; d <<= 1) {   // the shuffle scan, all lanes at once
+      uint32_t nxt[32];
+      for (int lane = 0; lane < 32; lane++)
+        nxt[lane] = lane >= d ? kCapdecMul[incl[lane - d] * 64u + incl[lane]] : incl[lane];
+      for (int lane = 0; lane < 32; lane++) incl[lane] = nxt[lane];
+    }
+    for (int lane = 0; lane < 32; lane++) {
+      const uint32_t excl = lane ? incl[lane - 1] : 0u;
+      uint32_t cur = kCapdecApply[excl * 16u + st];
+      for (int j = 0; j < 16; j++) {
+        const uint32_t b = bytes[lane][j];
+        const uint32_t e = kCapdecStep[cur * 256u + b];
+        cur = e & 15u;
+        if (e & 16u) out[o++] = uint8_t(b - (e & 32u));
+      }
+    }
+    st = kCapdecApply[incl[31] * 16u + st];
+  }
+  *st_io = uint8_t(st);
+  return long(o);
 }
 
 }  // extern "C"

@@ -160,3 +160,39 @@ def test_pipeline_logic_on_normalized_non_ascii_text(sim):
         got, gmiss = s.tokenize(norm, prenorm=True)
         assert np.array_equal(got, want) and gmiss == wmiss
     s.close()
+
+
+def test_capcode_decode_scan_equals_oracle(sim):
+    """The warp-scan capcode decoder (csrc/capcode_decode_scan.cuh: transition-monoid tables from
+    gen_capdec_tables.py + the lane / round decomposition, simulated by tests/host_sim.cpp) against the
+    oracle's sequential decoder: encoder output, adversarial marker soup, every start state (the
+    streaming decoder resumes in any of them), every alignment, lengths across several rounds."""
+    sim.hs_capdec_scan.restype = C.c_long
+    sim.hs_capdec_scan.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_uint8), C.c_char_p]
+
+    def run(data, galign, st):
+        out = C.create_string_buffer(len(data) + 1)
+        s = C.c_uint8(st)
+        n = sim.hs_capdec_scan(data, len(data), galign, C.byref(s), out)
+        return (None, None) if n < 0 else (out.raw[:n], s.value)
+
+    rng = random.Random(77)
+    base = corpus.base_text(41, 300_000, 0.4)
+    cases = [b"", b"C", b"W", b"D", b"DC", b"DW hello", b"Wabc def", b"Chello", b"D Chello Wworld's 12ab, x", b"DDD   ", b"WCWCD a"]
+    for _ in range(200):
+        a = rng.randrange(len(base) - 3000)
+        cases.append(oracle.capcode_encode(bytes(base[a:a + rng.randrange(0, 2500)])))
+    alpha = b"CWD  aazZ9'.,\n"
+    for _ in range(1500):
+        cases.append(bytes(rng.choice(alpha) for _ in range(rng.randrange(0, 1200 if rng.random() < 0.1 else 40))))
+    for t in cases:
+        for st in (0, rng.randrange(16)):
+            want, wst = oracle.capcode_decode(t, st)
+            got, gst = run(t, rng.randrange(16), st)
+            assert got == want and gst == wst, (t[:60], st)
+    for st in range(16):   # every state x every byte, one step
+        for b in range(128):
+            want, wst = oracle.capcode_decode(bytes([b]), st)
+            got, gst = run(bytes([b]), 0, st)
+            assert got == want and gst == wst, (b, st)
+    assert run(b"abc\xc3\xa9", 3, 0) == (None, None)   # non-ASCII text is left to the per-code-point kernel

@@ -50,7 +50,7 @@ int decode_on_stream(tmgpu_workspace* ws, const uint8_t* d_tokens, const int64_t
   if (n) {
     CU(launch_capcode_decode(ws->raw, ws->raw_off, n, ws->dec, ws->out_len, v->sms, st, nullptr, nullptr,
                              v->unicode ? &v->uni : nullptr,
-                             SortScratch{ws->p_key, ws->p_key2, ws->p_val, ws->p_order, ws->p_sort_temp, ws->p_sort_bytes, ws->p_counters}));
+                             ws->p_counters));
     ws->last_launches++;
   }
   CU(exclusive_scan_u32_to_u64(ws->scan_temp, ws->scan_bytes, ws->out_len, ws->out_off, n + 1, st));
@@ -264,7 +264,7 @@ extern "C" int tmgpu_decoder_decode(tmgpu_decoder* d, const uint8_t* tokens, con
     if (v->host.capcode == 2) {
       CU(launch_capcode_decode(ws->raw, ws->raw_off, n, ws->dec, ws->out_len, v->sms, st, d->keep_len, d->cc_state,
                                v->unicode ? &v->uni : nullptr,
-                             SortScratch{ws->p_key, ws->p_key2, ws->p_val, ws->p_order, ws->p_sort_temp, ws->p_sort_bytes, ws->p_counters}));
+                             ws->p_counters));
       src = ws->dec;
       lens = ws->out_len;
     }

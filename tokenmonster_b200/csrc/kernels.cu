@@ -12,7 +12,8 @@
 //   wire_frame_kernel             reply framing of the server protocol
 //   K2 decode_size / decode_copy  reverse[id] gather (go/tokenmonster.go:813-948)
 //   capcode_decode_*_kernel       capcode level-2 decoder (javascript/tokenmonster.js:1007-1065):
-//                                 ASCII strings one lane per string, the rest per code point
+//                                 ASCII strings as a warp scan over the decoder's transition monoid
+//                                 (capcode_decode_scan.cuh), the rest per code point
 //   stream_tail / copy_tail       the streaming decoder's incomplete-sequence remainder
 #include "kernels.h"
 
@@ -25,6 +26,7 @@
 #include "tokenize_thread_kernel.cuh"
 #include "unicode_normalize.cuh"
 #include "chunking.cuh"
+#include "capcode_decode_scan.cuh"
 
 namespace tmgpu {
 
@@ -270,134 +272,6 @@ __global__ void __launch_bounds__(256) capcode_decode_kernel(const uint8_t* __re
     }
     out_len[s] = o;
     if (state) state[s] = uint8_t((in_word ? 1u : 0u) | (in_char ? 2u : 0u) | (del ? 4u : 0u) | (ignore ? 8u : 0u));
-  }
-}
-
-// The same decoder for pure-ASCII text, one lane per string with every lane of a warp doing one
-// byte per iteration: input through a 32-byte shared-memory ring filled by cp.async (as in
-// table_kernel), the state machine as straight-line predicated code, output in 8-byte stores.
-// A string that holds a byte >= 0x80 is left to capcode_decode_kernel (out_len = 0xFFFFFFFF).
-__global__ void __launch_bounds__(256) capcode_decode_ascii_kernel(const uint8_t* __restrict__ src,
-                                                                   const uint64_t* __restrict__ raw_off, uint32_t n,
-                                                                   uint8_t* __restrict__ dst,
-                                                                   uint32_t* __restrict__ out_len,
-                                                                   const uint32_t* __restrict__ len_in,
-                                                                   uint8_t* __restrict__ state, int wide,
-                                                                   const uint32_t* __restrict__ order,
-                                                                   uint32_t* __restrict__ counter) {
-  constexpr unsigned FULL = 0xFFFFFFFFu;
-  __shared__ __align__(16) uint32_t s_ring[256 * 8];
-  const int lane = threadIdx.x & 31;
-  const uint32_t ring_b = pipe_smem_u32(s_ring + (threadIdx.x >> 5) * 256 + lane);
-  for (;;) {
-    uint32_t g = 0;
-    if (lane == 0) g = atomicAdd(counter, 1u);
-    g = __shfl_sync(FULL, g, 0);
-    if (uint64_t(g) * 32u >= n) break;
-    const uint32_t slot_i = g * 32u + uint32_t(lane);
-    bool active = slot_i < n, wide_text = false;
-    const uint32_t s = active ? order[slot_i] : 0u;   // strings by descending length: the 32 of a warp end together
-    const uint8_t* ga = nullptr;
-    uint8_t* out = nullptr;
-    int galign = 0, total_c = 0, cur = 0, hi_blk = 0;
-    bool in_word = false, in_char = false, del = false, ignore = false;
-    if (active) {
-      const uint64_t o0 = raw_off[s];
-      const uint8_t* in = src + o0;
-      const uint32_t len = len_in ? len_in[s] : uint32_t(raw_off[s + 1] - o0);
-      galign = int(reinterpret_cast<uintptr_t>(in) & 15);
-      ga = in - galign;
-      total_c = galign + int(len);
-      cur = galign;
-      out = dst + o0 + (wide ? ((o0 + 1) >> 1) : 0ull);
-      const uint32_t st0 = state ? state[s] : 0u;
-      in_word = st0 & 1u; in_char = st0 & 2u; del = st0 & 4u; ignore = st0 & 8u;
-    }
-    auto load_block = [&](int blk) {
-      const int c0 = blk << 4;
-      const uint32_t d = ring_b + uint32_t((blk & 1) * 4) * 128u;
-      if (c0 + 16 <= total_c) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) pipe_cp_async4(d + uint32_t(j) * 128u, ga + c0 + 4 * j, 4);
-      } else {
-        for (int j = 0; j < 4; j++) pipe_ring_word(d + uint32_t(j) * 128u, ga + c0 + 4 * j, total_c - (c0 + 4 * j));
-      }
-    };
-    if (active && total_c > galign) {
-      load_block(0);
-      if (total_c > 16) load_block(1);
-      hi_blk = total_c > 16 ? 1 : 0;
-      pipe_cp_async_wait();
-    }
-    unsigned long long acc = 0;
-    uint32_t o = 0, na = 0;                   // bytes produced; bytes in the accumulator
-    uint32_t head = active ? uint32_t((8u - (reinterpret_cast<uintptr_t>(out) & 7u)) & 7u) : 0u;   // bytes until 8-aligned
-    while (__any_sync(FULL, active)) {
-      const int last_blk = (total_c - 1) >> 4;
-      const bool want = active && hi_blk < last_blk && (cur >> 4) >= hi_blk;
-      if (__any_sync(FULL, want && (cur & 15) >= 7)) {
-        if (want) {
-          hi_blk++;
-          load_block(hi_blk);
-        }
-      }
-      if (!active) continue;
-      if (cur >= total_c || wide_text) {
-        // flush the accumulator, report
-        for (uint32_t j = 0; j < na; j++) out[o - na + j] = uint8_t(acc >> (8 * j));
-        if (wide_text) {
-          out_len[s] = 0xFFFFFFFFu;
-        } else {
-          out_len[s] = o;
-          if (state) state[s] = uint8_t((in_word ? 1u : 0u) | (in_char ? 2u : 0u) | (del ? 4u : 0u) | (ignore ? 8u : 0u));
-        }
-        active = false;
-        continue;
-      }
-      const int x = cur++;
-      if ((x & 15) == 0 && x > galign) pipe_cp_async_wait();   // entering a block
-      uint32_t r;
-      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(ring_b + uint32_t((x >> 2) & 7) * 128u + uint32_t(x & 3)));
-      if (r & 0x80u) { wide_text = true; continue; }
-      const bool isC = r == 'C', isW = r == 'W', isD = r == 'D';
-      const bool marker = isC | isW | isD, space = r == ' ';
-      const bool lower = (r - 'a') < 26u;
-      const bool keep = ((r - 'A') < 26u) | ((r - '0') < 10u) | (r == '\'');
-      const bool emit = !marker & !del;
-      const bool text = emit & !space;
-      const uint32_t outc = (lower & (in_char | in_word)) ? r - 32u : r;
-      const bool n_in_word = isW ? true : (isC ? false : ((emit & space & !ignore) | (text & !in_char & in_word & !(lower | keep))) ? false : in_word);
-      const bool n_in_char = isC ? true : (isW ? false : (text ? false : in_char));
-      del = isD ? true : (marker ? del : false);
-      ignore = isW ? true : (marker ? ignore : false);
-      in_word = n_in_word;
-      in_char = n_in_char;
-      if (emit) {
-        if (head) {
-          out[o] = uint8_t(outc);
-          head--;
-        } else {
-          acc |= static_cast<unsigned long long>(outc) << (8u * na);
-          na++;
-          if (na == 8) {
-            *reinterpret_cast<unsigned long long*>(out + o - 7) = acc;
-            acc = 0;
-            na = 0;
-          }
-        }
-        o++;
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) decode_sort_keys_kernel(const uint64_t* __restrict__ raw_off,
-                                                               const uint32_t* __restrict__ len_in, uint32_t n,
-                                                               uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
-  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
-    const uint32_t len = len_in ? len_in[s] : uint32_t(raw_off[s + 1] - raw_off[s]);
-    key[s] = min((len >> 3) + 1u, 0xFFFFu);
-    val[s] = s;
   }
 }
 
@@ -688,18 +562,20 @@ cudaError_t launch_decode_copy(const VocabDev& v, const uint8_t* tokens, const i
 
 cudaError_t launch_capcode_decode(const uint8_t* src, const uint64_t* raw_off, uint32_t n, uint8_t* dst,
                                   uint32_t* out_len, int sms, cudaStream_t st, const uint32_t* len_in,
-                                  uint8_t* state, const UnicodeDev* uni, const SortScratch& sc) {
-  // ASCII strings by the lane-per-string kernel, longest first, 32 of equal length per warp; the
+                                  uint8_t* state, const UnicodeDev* uni, uint32_t* counter) {
+  // ASCII strings by the warp-per-string scan kernel (strings are pulled from a work counter); the
   // rest (flagged out_len = 0xFFFFFFFF) per code point
-  cudaError_t e = cudaMemsetAsync(sc.counter, 0, 4, st);
+  cudaError_t e = cudaMemsetAsync(counter, 0, 4, st);
   if (e != cudaSuccess) return e;
-  const long long want = (static_cast<long long>(n) + 255) / 256;
-  const int grid = int(want < sms * 4ll ? (want < 1 ? 1 : want) : sms * 4ll);
-  decode_sort_keys_kernel<<<grid, 256, 0, st>>>(raw_off, len_in, n, sc.key, sc.val);
-  e = sort_items_by_length(sc.temp, sc.temp_bytes, sc.key, sc.key2, sc.val, sc.order, n, st);
-  if (e != cudaSuccess) return e;
-  capcode_decode_ascii_kernel<<<grid, 256, 0, st>>>(src, raw_off, n, dst, out_len, len_in, state, uni ? 1 : 0, sc.order,
-                                                    sc.counter);
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, capcode_decode_scan_kernel, 256, 0) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  const long long want = (static_cast<long long>(n) + 7) / 8;   // eight warps = eight strings per CTA
+  const long long full = static_cast<long long>(sms) * per_sm;
+  const int grid = int(want < full ? (want < 1 ? 1 : want) : full);
+  capcode_decode_scan_kernel<<<grid, 256, 0, st>>>(src, raw_off, n, dst, out_len, len_in, state, uni ? 1 : 0, counter);
   capcode_decode_kernel<<<sms * 8, 256, 0, st>>>(src, raw_off, n, dst, out_len, len_in, state,
                                                  uni ? *uni : UnicodeDev{}, uni ? 1 : 0, 1);
   return cudaGetLastError();

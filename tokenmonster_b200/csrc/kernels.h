@@ -156,15 +156,9 @@ cudaError_t launch_decode_copy(const VocabDev& v, const uint8_t* tokens, const i
                                const uint64_t* raw_off, uint8_t* out, int sms, cudaStream_t st,
                                const uint64_t* prefix_off = nullptr, const uint8_t* prefix = nullptr);
 // scratch for ordering work items by length (a warp wants 32 strings of equal length)
-struct SortScratch {
-  uint32_t *key, *key2, *val, *order;
-  void* temp;
-  size_t temp_bytes;
-  uint32_t* counter;   // one zeroed work counter
-};
 cudaError_t launch_capcode_decode(const uint8_t* src, const uint64_t* raw_off, uint32_t n, uint8_t* dst,
                                   uint32_t* out_len, int sms, cudaStream_t st, const uint32_t* len_in,
-                                  uint8_t* state, const UnicodeDev* uni, const SortScratch& sc);
+                                  uint8_t* state, const UnicodeDev* uni, uint32_t* counter /* one work counter, zeroed by the launcher */);
 cudaError_t launch_stream_tail(const uint8_t* raw, const uint64_t* raw_off, uint32_t n, int charset,
                                uint32_t* keep_len, uint32_t* rem_len, int sms, cudaStream_t st);
 cudaError_t launch_copy_tail(const uint8_t* raw, const uint64_t* raw_off, const uint32_t* keep_len,
