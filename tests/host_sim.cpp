@@ -53,16 +53,27 @@ Tabled table(const Sim& S, const uint8_t* raw, int n, bool cap, bool to_lower, b
   revcap_reset(e);
   uint32_t packed = 0, qbytes = 0, qn = 0;
   int k = n - 1;
+  auto xc = [&](int j) -> uint32_t { return j >= 0 ? revcap_char(at(j)) : 0u; };   // the kernel's s_chr[] entry
+  if (cap) {   // the read-ahead: characters k, k-1, k-2
+    revcap_push(e, xc(k));
+    revcap_push(e, xc(k - 1));
+    revcap_push(e, xc(k - 2));
+  }
   while (k >= 0 || qn) {
     if (qn == 0) {
-      auto xc = [&](int j) -> uint32_t { const uint32_t c = at(j); return c | (pc_class_sp(c) << 8); };
-      if (cap) qn = revcap_step(e, S.lut, xc(k), k >= 1 ? xc(k - 1) : 0u, k >= 2 ? xc(k - 2) : 0u, k,
-                                [&](int j) -> uint32_t { return pc_class_sp(at(j)); }, &qbytes);
-      else { qbytes = at(k); qn = 1; }
+      if (cap) {
+        qn = revcap_step(e, [&](uint32_t i) -> uint32_t { return S.lut[i]; }, k,
+                         [&](int j) -> uint32_t { return revcap_char(at(j)) >> 8; }, &qbytes);
+        revcap_push(e, xc(k - 3));
+      } else {
+        qbytes = at(k);
+        qn = 1;
+      }
       k--;
       if (qn == 0) continue;   // a space replaced by a marker emits nothing
     }
-    const uint32_t b = (qbytes >> (8 * (qn - 1))) & 0xFFu;
+    const uint32_t b = qbytes & 0xFFu;   // the queue leaves lowest byte first
+    qbytes >>= 8;
     qn--;
     packed = dfa_next(packed, b, 32u - t.dfa_bits, (1u << t.dfa_bits) - 1u,
                       [&](uint32_t i, uint4* kk, uint4* v) { *kk = bk[2 * i]; *v = bk[2 * i + 1]; },

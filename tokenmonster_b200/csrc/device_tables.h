@@ -37,23 +37,24 @@ struct DfaDev {
 // One transition: the packed state after consuming byte b from the state in `packed`.
 // load_bucket(h, &keys, &vals) reads the 32-byte bucket h; d1(b) = the packed state one byte below
 // the root (every transition whose target is at depth <= 1 depends on the byte alone).
-// Straight-line code: the four key compares are selects; the loop only runs again for a key that
-// was pushed into the next bucket at build time (~1 % of the buckets are full).
+// Straight-line code: one probe, the four key compares are selects; the loop only runs for a key
+// that was pushed into the next bucket at build time (~1 % of the buckets are full).  The root
+// (state 0) probes like any other state: it has no transition to depth >= 2, and its keys (< 256)
+// equal no stored key (>= 256), so the probe misses and d1 stands.
 template <class LoadBucket, class LoadD1>
 TM_HD uint32_t dfa_next(uint32_t packed, uint32_t b, uint32_t shift, uint32_t mask, LoadBucket load_bucket, LoadD1 d1) {
-  const uint32_t s = packed & kDfaStateMask;
-  const uint32_t key = (s << 8) | b;
+  const uint32_t key = ((packed & kDfaStateMask) << 8) | b;
   uint32_t h = dfa_hash(key, shift);
   uint32_t res = d1(b);
-  bool more = (s != 0);   // the root has no transition to depth >= 2
-  while (more) {
+  bool more;
+  do {
     uint4 k, v;
     load_bucket(h, &k, &v);
     const bool h0 = (k.x & ~kDfaOverflow) == key, h1 = k.y == key, h2 = k.z == key, h3 = k.w == key;
     res = h0 ? v.x : (h1 ? v.y : (h2 ? v.z : (h3 ? v.w : res)));
     more = !(h0 | h1 | h2 | h3) & ((k.x & kDfaOverflow) != 0);
     h = (h + 1) & mask;
-  }
+  } while (more);
   return res;
 }
 

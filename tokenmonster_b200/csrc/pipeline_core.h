@@ -26,7 +26,10 @@ namespace tmgpu {
 // ------------------------------------------------------------------------------------------
 // stage 1: capcode level 2 encoder
 // ------------------------------------------------------------------------------------------
-enum : uint32_t { PC_O = 0, PC_U = 1, PC_L = 2, PC_N = 3, PC_A = 4 };   // other, upper, lower, digit, apostrophe
+// character classes.  The numbering is chosen for the encoder's table index: letters are the
+// classes with bit 2 set.  other, digit, apostrophe, space (behaves as "other" except where the
+// encoder asks for a space), upper, lower
+enum : uint32_t { PC_O = 0, PC_N = 1, PC_A = 2, PC_S = 3, PC_U = 4, PC_L = 5 };
 
 TM_HD uint32_t pc_class(uint32_t c) {
   if (c - 'a' < 26u) return PC_L;
@@ -35,6 +38,10 @@ TM_HD uint32_t pc_class(uint32_t c) {
   if (c == '\'') return PC_A;
   return PC_O;
 }
+TM_HD uint32_t pc_class_sp(uint32_t c) { return c == ' ' ? uint32_t(PC_S) : pc_class(c); }
+// what the encoder keeps of a raw character: the byte it will emit for it (capitals lower-cased)
+// | class << 8.  The table kernel reads this from a 256-entry shared-memory table.
+TM_HD uint32_t revcap_char(uint32_t c) { return (c - 'A' < 26u ? (c | 0x20u) : c) | (pc_class_sp(c) << 8); }
 
 // ------------------------------------------------------------------------------------------
 // stage 1, right to left: the encoder (a forward-looking restatement of js:900-1005: the marker
@@ -43,41 +50,29 @@ TM_HD uint32_t pc_class(uint32_t c) {
 // per call.  This is what the table kernel runs (the automaton consumes the normalized text back
 // to front, so producing it back to front lets both live in one loop and the normalized text never
 // exists in memory).  Everything the encoder knows about a character is local:
-//   * the two characters to its LEFT are read directly (c1, c2);
+//   * the two characters to its LEFT are read ahead (their classes sit in a shift register);
 //   * "inside a capitalised run" = the nearest character to the left that is not a digit or an
 //     apostrophe is a capital: it is the left neighbour itself unless that is a digit / apostrophe,
-//     in which case one look-back over the run answers for every character of the run;
+//     in which case one look-back over the run answers for every character of the run (iw);
 //   * "the run is mixed case" = the nearest lower-case-or-other character to the RIGHT is
-//     lower-case, which a right-to-left pass carries along (nlo);
-//   * the class of the character to the right (clr) decides whether a space is replaced by a marker.
+//     lower-case, which a right-to-left pass carries along (mixed);
+//   * whether the character to the right is a capital decides whether a space is replaced by a
+//     marker (capf).
+// The decision AND the carried bits of the next step are one table read:
+//   index = (class k-2 is a letter) | class k-1 << 1 | class k << 4 | iw << 7 | mixed << 8 | capf << 9
+//   entry = bytes to emit (<= 4) | iw << 3 | next mixed << 4 | next capf << 5 | (k-1 is a digit /
+//           apostrophe) << 6 | the bytes IN FRONT of the character, last one first, from bit 8
+// so that the emitted bytes, character included, leave the queue lowest byte first -- the order the
+// right-to-left automaton wants them in.
 // ------------------------------------------------------------------------------------------
-struct RevCap {
-  uint32_t clr;          // class of the character to the right
-  uint32_t nlo;          // class of the nearest lower-case-or-other character to the right (other if none)
-  bool has_right;        // there is a character to the right
-  bool iw_valid, iw;     // cached answer for the current run of digits / apostrophes
-};
-
-TM_HD void revcap_reset(RevCap& e) {
-  e.clr = PC_O;
-  e.nlo = PC_O;
-  e.has_right = false;
-  e.iw_valid = false;
-  e.iw = false;
-}
-
-// The encoder's decision is a function of ten bits, so the kernels read it from a table:
-//   index = cl | cl1 << 3 | (cl2 is a letter) << 6 | in_word << 7 | mixed << 8 | (a capital follows) << 9
-//   (classes as PC_*, with the space as a class of its own, PC_S)
-//   entry = bytes in front of the character (<= 3, little endian) | count << 24 | eaten << 26 | lower << 27
-constexpr uint32_t PC_S = 5;       // ' ' -- behaves as PC_O except where the encoder asks for a space
 constexpr int kCapLutSize = 1024;
 
-TM_HD uint32_t pc_class_sp(uint32_t c) { return c == ' ' ? PC_S : pc_class(c); }
-
 TM_HD uint32_t revcap_lut_entry(uint32_t idx) {
-  const uint32_t cl = idx & 7u, cl1 = (idx >> 3) & 7u;
-  const bool cl2_letter = (idx >> 6) & 1u, in_word = (idx >> 7) & 1u, mixed = (idx >> 8) & 1u, cap_follows = (idx >> 9) & 1u;
+  const bool cl2_letter = idx & 1u;
+  const uint32_t cl1 = (idx >> 1) & 7u, cl = (idx >> 4) & 7u;
+  const bool iw = (idx >> 7) & 1u, mixed = (idx >> 8) & 1u, cap_follows = (idx >> 9) & 1u;
+  const bool run1 = (cl1 == PC_N) || (cl1 == PC_A);
+  const bool in_word = run1 ? iw : (cl1 == PC_U);
   const bool sp1 = (cl1 == PC_S);
   const bool letter1 = (cl1 == PC_U) || (cl1 == PC_L);
   const bool glue1 = letter1 || (cl1 == PC_A);
@@ -88,55 +83,67 @@ TM_HD uint32_t revcap_lut_entry(uint32_t idx) {
                         (cl == PC_U && in_word && !mixed && !glue1);
   const bool k_dcs = (cl == PC_U) && in_word && mixed;
   const uint32_t marker = mixed ? 'C' : 'W';
-  uint32_t pre = 0, np = 0;
-  if (k_dspace) { pre = 'D' | (' ' << 8); np = 2; }
-  if (k_dcs) { pre = 'D' | ('C' << 8) | (' ' << 16); np = 3; }
+  // the bytes in front of the character, LAST ONE FIRST from bit 8 (the order they leave the queue)
+  uint32_t rev = 0, np = 0;
+  if (k_dspace) { rev = (uint32_t(' ') << 8) | (uint32_t('D') << 16); np = 2; }
+  if (k_dcs) { rev = (uint32_t(' ') << 8) | (uint32_t('C') << 16) | (uint32_t('D') << 24); np = 3; }
   if (start) {
-    pre = sp1 ? (marker | (' ' << 8)) : ('D' | (marker << 8) | (' ' << 16));
-    np = sp1 ? 2 : 3;
+    if (sp1) { rev = (uint32_t(' ') << 8) | (marker << 16); np = 2; }
+    else { rev = (uint32_t(' ') << 8) | (marker << 16) | (uint32_t('D') << 24); np = 3; }
   }
   // a space right before the first letter of a capitalised word is replaced by the marker
   // (js:976-979): the capital emits "<marker> x" and the space emits nothing
   const bool eaten = (cl == PC_S) && cap_follows;
-  return pre | (np << 24) | (uint32_t(eaten) << 26) | (uint32_t(cl == PC_U) << 27);
+  const bool next_mixed = (cl == PC_L) ? true : ((cl == PC_O || cl == PC_S) ? false : mixed);
+  return (eaten ? 0u : np + 1u) | (uint32_t(iw) << 3) | (uint32_t(next_mixed) << 4) | (uint32_t(cl == PC_U) << 5) |
+         (uint32_t(run1) << 6) | rev;
 }
 
-// Encodes the raw character at index k.  x0 / x1 / x2 = character | class << 8 (pc_class_sp) of the
-// characters at k / k-1 / k-2 (x1, x2 ignored where they do not exist); class_at(j) = class of
-// character j (rare deeper look-back); lut = the kCapLutSize entries of revcap_lut_entry().
-// Returns the number of bytes (0..4) placed in *out in FORWARD order, little endian -- the caller
-// feeds them to the automaton last byte first (checked against the oracle's encoder,
-// tests/test_host_sim.py).
-template <class ClassAt>
-TM_HD uint32_t revcap_step(RevCap& e, const uint32_t* lut, uint32_t x0, uint32_t x1, uint32_t x2, int k, ClassAt class_at,
-                           uint32_t* out) {
-  const uint32_t cl = x0 >> 8;
-  const uint32_t cl1 = (k >= 1) ? (x1 >> 8) : uint32_t(PC_O);
-  const uint32_t cl2 = (k >= 2) ? (x2 >> 8) : uint32_t(PC_O);
-  // inside a capitalised run?  Decided by the left neighbour unless that is a digit / apostrophe;
-  // then one look-back (rare) answers for the whole run of digits / apostrophes
-  const bool run1 = (cl1 == PC_N) | (cl1 == PC_A);
-  if (run1 & !e.iw_valid) {
-    uint32_t x = cl2;
+struct RevCap {
+  uint32_t cls;     // classes of the characters k-2 (bits 0-2), k-1 (3-5), k (6-8); older ones above
+  uint32_t chr;     // their bytes (capitals lower-cased): k (bits 0-7), k-1, k-2
+  uint32_t carry;   // iw << 7 | mixed << 8 | capf << 9: the table index bits carried from the right
+  bool iw_valid;    // iw answers for the current run of digits / apostrophes
+};
+
+TM_HD void revcap_reset(RevCap& e) {
+  e.cls = 0;
+  e.chr = 0;
+  e.carry = 0;
+  e.iw_valid = false;
+}
+// The read-ahead takes one more character to the left: x = revcap_char() of it, 0 when the string
+// has none left (class "other").  Three pushes position the first character.
+TM_HD void revcap_push(RevCap& e, uint32_t x) {
+  e.cls = (e.cls << 3) + (x >> 8);
+  e.chr = (e.chr >> 8) | ((x & 0xFFu) << 16);
+}
+
+// Encodes the raw character at index k (the lowest of the three characters pushed last).
+// class_at(j) = class of character j (rare deeper look-back); lut(i) = entry i of the kCapLutSize
+// entries of revcap_lut_entry().  Returns the number of bytes (0..4) placed in *out, FIRST TO LEAVE in the
+// lowest byte: the character itself, then the bytes in front of it back to front (checked against
+// the oracle's encoder, tests/test_host_sim.py).  The caller pushes the next character afterwards.
+template <class Lut, class ClassAt>
+TM_HD uint32_t revcap_step(RevCap& e, Lut lut, int k, ClassAt class_at, uint32_t* out) {
+  const uint32_t base = (e.cls >> 2) & 0x7Fu;
+  uint32_t a = lut(base | e.carry);
+  // the left neighbour is a digit / apostrophe and nothing is known about the run yet: one
+  // look-back (rare) answers for the whole run -- is the nearest other character a capital?
+  if (((a >> 6) & 1u) && !e.iw_valid) {
+    uint32_t x = e.cls & 7u;
     int j = k - 2;
     while ((x == PC_N || x == PC_A) && j > 0) {
       j--;
       x = class_at(j);
     }
-    e.iw = (k >= 2) && (x == PC_U);
+    e.carry = (e.carry & ~0x80u) | (((k >= 2) && (x == PC_U)) ? 0x80u : 0u);
+    a = lut(base | e.carry);
   }
-  e.iw_valid = run1;
-  const bool in_word = run1 ? e.iw : (cl1 == PC_U);
-  const uint32_t idx = cl | (cl1 << 3) | (uint32_t(cl2 == PC_U || cl2 == PC_L) << 6) | (uint32_t(in_word) << 7) |
-                       (uint32_t(e.nlo == PC_L) << 8) | (uint32_t(e.has_right && e.clr == PC_U) << 9);
-  const uint32_t a = lut[idx];
-  const uint32_t np = (a >> 24) & 3u, eaten = (a >> 26) & 1u;
-  const uint32_t ch = (x0 & 0xFFu) | (((a >> 27) & 1u) << 5);
-  *out = (a & 0xFFFFFFu) | (eaten ? 0u : (ch << (8u * np)));
-  e.clr = cl;
-  e.has_right = true;
-  e.nlo = (cl == PC_L) ? uint32_t(PC_L) : ((cl == PC_O) | (cl == PC_S) ? uint32_t(PC_O) : e.nlo);
-  return np + 1u - eaten;
+  e.iw_valid = ((a >> 6) & 1u) != 0;
+  *out = (a & 0xFFFFFF00u) | (e.chr & 0xFFu);
+  e.carry = (a << 4) & 0x380u;
+  return a & 7u;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -150,33 +157,35 @@ TM_HD uint32_t pw_nbb(uint32_t w) { return w >> 30; }
 // beginByte value of a 2-bit class code (vocab_tables.h: class_code)
 TM_HD int class_value(uint32_t code) { return int((0x0C0A0100u >> (8 * code)) & 0xFFu); }
 
-// Classes of the bytes to the right of the current position, 2 bits each, nearest first; bytes
-// behind the end of the string are the pad byte 0 (defined as 0).  48 positions
-// are kept (a key has at most 40 bytes).
+// Classes of the bytes to the right of the current position, 2 bits each: the byte at distance d
+// (1 <= d <= 47; a key has at most 40 bytes) sits at bits 2d, 2d+1 of a 96-bit shift register, and
+// bits 0, 1 stay zero, so that "distance 0" (no match) reads as class 0 without a test.  Bytes
+// behind the end of the string are the pad byte 0 (defined as 0).
 struct ClassTrail {
-  unsigned long long lo;   // positions +1..+32
-  uint32_t hi;             // positions +33..+48
+  uint32_t w0, w1, w2;   // distances 0..15, 16..31, 32..47
 };
 TM_HD void trail_reset(ClassTrail& t, uint32_t code0) {
-  t.lo = code0 * 0x5555555555555555ull;
-  t.hi = code0 * 0x55555555u;
+  t.w0 = code0 * 0x55555554u;
+  t.w1 = code0 * 0x55555555u;
+  t.w2 = code0 * 0x55555555u;
 }
 TM_HD void trail_push(ClassTrail& t, uint32_t code) {
-  t.hi = (t.hi << 2) | uint32_t(t.lo >> 62);
-  t.lo = (t.lo << 2) | code;
+  t.w2 = (t.w2 << 2) | (t.w1 >> 30);
+  t.w1 = (t.w1 << 2) | (t.w0 >> 30);
+  t.w0 = (t.w0 << 2) | (code << 2);
 }
-// class of the byte d positions to the right (d >= 1)
+// class of the byte d positions to the right; 0 for d == 0
 TM_HD uint32_t trail_at(const ClassTrail& t, uint32_t d) {
-  const uint32_t k = d - 1u;
-  return (k < 32u ? uint32_t(t.lo >> (2u * k)) : (t.hi >> (2u * (k - 32u)))) & 3u;
+  const uint32_t w = d < 16u ? t.w0 : (d < 32u ? t.w1 : t.w2);
+  return (w >> ((2u * d) & 31u)) & 3u;
 }
 
 // The word of the position whose byte (class code `code`) was just consumed into `packed`.
 // `off` = bytes of the virtual space (1, or 2 for UTF-16).
 TM_HD uint32_t position_word(uint32_t packed, uint32_t code, const ClassTrail& t, uint32_t off) {
   const uint32_t l = dfa_len(packed), sl = dfa_splen(packed);
-  const uint32_t nb = l ? trail_at(t, l) : 0u;
-  const uint32_t nbb = (sl > off) ? trail_at(t, sl - off) : 0u;
+  const uint32_t nb = trail_at(t, l);                              // l == 0: no match, class 0
+  const uint32_t nbb = trail_at(t, sl - (sl < off ? sl : off));    // distance 0 unless sl > off
   return (packed & (kDfaStateMask | (63u << 20))) | (nb << 26) | (code << 28) | (nbb << 30);
 }
 

@@ -187,31 +187,71 @@ __device__ __forceinline__ void pipe_ring_word(uint32_t smem_addr, const uint8_t
 }
 __device__ __forceinline__ void pipe_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Shared memory of one CTA, ONE object: every table is read with "ld.shared [base + constant +
+// index]" from a single base register (reading separate __shared__ arrays through C++ made the
+// compiler rebuild each array's window address -- S2R / MOV / LEA -- at every use in the loop).
+struct __align__(128) TableShared {
+  uint8_t img[kPipeImageBytes];      // dfa_d1[256] (u32), class_code[256], 256 spare: one TMA bulk copy
+  uint32_t lut[kCapLutSize];         // revcap_lut_entry
+  uint16_t chr[256];                 // raw byte -> byte to emit | class << 8 (revcap_char)
+  uint32_t ring[kPipeBlock * 8];     // raw text: word w of lane l at [warp * 256 + w * 32 + l]
+  uint32_t rows[kPipeBlock * 12];    // eight position words per lane waiting for their sector (48-byte rows)
+  uint64_t bar;
+};
+constexpr uint32_t kTsD1 = 0, kTsCode = 1024;
+constexpr uint32_t kTsLut = kPipeImageBytes;
+constexpr uint32_t kTsChr = kTsLut + 4 * kCapLutSize;
+constexpr uint32_t kTsRing = kTsChr + 2 * 256;
+constexpr uint32_t kTsRows = kTsRing + 4 * kPipeBlock * 8;
+constexpr uint32_t kTsRowBytes = 48;   // 3 x 16: the 128-bit reads of eight lanes fall into eight different bank groups
+static_assert(kTsRing % 16 == 0 && kTsRows % 16 == 0, "ring / rows are read and written 16 bytes at a time");
+
+template <uint32_t OFF>
+__device__ __forceinline__ uint32_t pipe_lds_u32(uint32_t addr) {   // read-only tables: plain (movable) asm
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
+template <uint32_t OFF>
+__device__ __forceinline__ uint32_t pipe_lds_u16(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u16 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
+template <uint32_t OFF>
+__device__ __forceinline__ uint32_t pipe_lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
+
 template <bool CAP, bool TEXT>
 __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A) {
   constexpr unsigned FULL = 0xFFFFFFFFu;
-  __shared__ __align__(128) uint8_t s_img[kPipeImageBytes];
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ uint8_t s_cls[256];
-  __shared__ uint32_t s_lut[CAP ? kCapLutSize : 1];
-  __shared__ __align__(16) uint32_t s_ring[kPipeBlock * 8];   // word w of lane l: [warp * 256 + w * 32 + l]
-  __shared__ uint4 s_stash[kPipeBlock];                       // four position words per lane, see the store below
-  pipe_stage_tma(s_img, A.v.pipe_image, &s_bar);
-  s_cls[threadIdx.x & 255] = uint8_t((threadIdx.x & 255) < 128 ? pc_class_sp(threadIdx.x & 255) : uint32_t(PC_O));
-  if (CAP)
-    for (int i = threadIdx.x; i < kCapLutSize; i += kPipeBlock) s_lut[i] = revcap_lut_entry(uint32_t(i));
-  __syncthreads();
-  const uint32_t* s_d1 = reinterpret_cast<const uint32_t*>(s_img);
-  const uint8_t* s_code = s_img + 1024;
-  const DfaDev D = A.v.dfa;
-  const uint32_t voff = uint32_t(A.v.off);
+  __shared__ TableShared sm;
+  static_assert(offsetof(TableShared, lut) == kTsLut && offsetof(TableShared, chr) == kTsChr &&
+                    offsetof(TableShared, ring) == kTsRing && offsetof(TableShared, rows) == kTsRows,
+                "the constants above are the struct's layout");
+  pipe_stage_tma(sm.img, A.v.pipe_image, &sm.bar);
   const bool want_ascii = CAP || (!A.prenorm && (A.v.normflag != 0));
   const bool to_lower = !A.prenorm && (A.v.normflag & 2) != 0;
-  const uint32_t code0 = s_code[0];
+  if (CAP)
+    for (int i = threadIdx.x; i < kCapLutSize; i += kPipeBlock) sm.lut[i] = revcap_lut_entry(uint32_t(i));
+  {
+    uint32_t c = threadIdx.x & 255u;
+    if (to_lower && c - 'A' < 26u) c |= 0x20u;
+    sm.chr[threadIdx.x & 255] = uint16_t(CAP ? revcap_char(c) : c);
+  }
+  __syncthreads();
+  const DfaDev D = A.v.dfa;
+  const uint32_t voff = uint32_t(A.v.off);
+  uint32_t sb = pipe_smem_u32(&sm);
+  asm volatile("mov.u32 %0, %0;" : "+r"(sb));   // opaque: keeps the base in a register (the compiler would rebuild it at every use)
+  const uint32_t code0 = pipe_lds_u8<kTsCode>(sb);
   const int lane = threadIdx.x & 31;
   uint32_t* counter = A.pipe_counters + 2;
-  const uint32_t ring_b = pipe_smem_u32(s_ring + (threadIdx.x >> 5) * 256 + lane);   // byte address of word 0
-  const uint32_t stash_b = pipe_smem_u32(s_stash + threadIdx.x);
+  const uint32_t ring_b = sb + kTsRing + uint32_t((threadIdx.x >> 5) * 256 + lane) * 4u;   // byte address of word 0
+  const uint32_t row_b = sb + kTsRows + uint32_t(threadIdx.x) * kTsRowBytes;
 
   for (;;) {
     uint32_t g = 0;
@@ -220,11 +260,16 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
     if (uint64_t(g) * 32u >= A.n) break;
     const uint32_t slot_i = g * 32u + uint32_t(lane);
     // ---- this lane's string ---------------------------------------------------------------
-    bool active = false, bad = false;
+    bool active = false;
+    uint32_t seen = 0;   // OR of the bytes read so far (bit 7: a byte >= 0x80)
     uint32_t item = 0, s = 0, slot = 0;
     int k = -1, galign = 0, total_c = 0;
     int fcur = -1;       // aligned coordinate of the next raw byte the read-ahead takes
-    int lo_blk = 0;      // lowest 16-byte block in the ring (blocks lo_blk and lo_blk + 1 are there)
+    // The ring holds the 16-byte blocks lo_blk and lo_blk + 1.  Block lo_blk - 1 is fetched once the
+    // cursor is 8 bytes into block lo_blk: trig = 16 * lo_blk + 8 while a lower block exists, else
+    // far below any cursor (so "fcur <= trig" is the whole test).
+    constexpr int kNoRefill = -(1 << 30);
+    int trig = kNoRefill;
     const uint8_t* ga = nullptr;
     uint32_t* wend = nullptr;
     uint8_t* tend = nullptr;
@@ -263,91 +308,91 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
         for (int j = 0; j < 4; j++) pipe_ring_word(dst + uint32_t(j) * 128u, ga + c0 + 4 * j, total_c - (c0 + 4 * j));
       }
     };
-    // the raw character at coordinate fcur, with its class: character | class << 8
-    auto take = [&]() -> uint32_t {
-      const int x = fcur--;
+    // the raw character at coordinate fcur: byte to emit | class << 8 (revcap_char); 0 = "no
+    // character" when the string has none left (`has` false: nothing is read, byte 0 maps to 0)
+    auto take = [&](bool has) -> uint32_t {
+      const int x = fcur;
+      fcur -= has ? 1 : 0;
       uint32_t b;
       // entering a block (x & 15 == 15): wait for its copy, which was issued long ago; then one byte
       asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "setp.eq.u32 p, %2, 15;\n\t"
+          "{\n\t.reg .pred p, h;\n\t"
+          "setp.ne.u32 h, %3, 0;\n\t"
+          "setp.eq.and.u32 p, %2, 15, h;\n\t"
           "@p cp.async.wait_all;\n\t"
-          "ld.shared.u8 %0, [%1];\n\t}"
+          "mov.u32 %0, 0;\n\t"
+          "@h ld.shared.u8 %0, [%1];\n\t}"
           : "=r"(b)
-          : "r"(ring_b + uint32_t((x >> 2) & 7) * 128u + uint32_t(x & 3)), "r"(uint32_t(x) & 15u)
+          : "r"(ring_b + uint32_t((x >> 2) & 7) * 128u + uint32_t(x & 3)), "r"(uint32_t(x) & 15u), "r"(uint32_t(has))
           : "memory");
-      bad = bad | (want_ascii & ((b & 0x80u) != 0));
-      if (to_lower && b - 'A' < 26u) b |= 0x20u;
-      return b | (uint32_t(s_cls[b]) << 8);
+      const uint32_t t = pipe_lds_u16<kTsChr>(sb + 2u * b);
+      seen |= t;
+      return t;
     };
-    uint32_t x0 = 0, x1 = 0, x2 = 0;   // read-ahead: characters k, k-1, k-2
+    uint32_t x0 = 0;   // capcode 0: the character at k
+    RevCap e;          // capcode 2: the encoder, with its read-ahead of the characters k, k-1, k-2
+    revcap_reset(e);
     if (active && k >= 0) {
       const int top = (total_c - 1) >> 4;
       load_block(top);
       if (top > 0) load_block(top - 1);
-      lo_blk = top > 0 ? top - 1 : 0;
+      trig = top > 1 ? 16 * (top - 1) + 8 : kNoRefill;
       pipe_cp_async_wait();
       fcur = total_c - 1;
-      x0 = take();
-      if (CAP && k >= 1) x1 = take();
-      if (CAP && k >= 2) x2 = take();
+      x0 = take(true);
+      if (CAP) {
+        revcap_push(e, x0);
+        revcap_push(e, take(k >= 1));
+        revcap_push(e, take(k >= 2));
+      }
     }
-    RevCap e;
-    revcap_reset(e);
     ClassTrail tr;
     trail_reset(tr, code0);
     uint32_t packed = 0, qbytes = 0, qn = 0, dist = 0;
-    uint4 wbuf = make_uint4(0, 0, 0, 0);
 
     while (__any_sync(FULL, active)) {
       // ---- ring refill, all lanes of the warp together ----------------------------------------
-      const bool want = active && lo_blk > 0 && fcur >= galign && (fcur >> 4) <= lo_blk;
-      if (__any_sync(FULL, want && (fcur & 15) <= 8)) {
-        if (want) {
-          lo_blk--;
-          load_block(lo_blk);
+      if (__any_sync(FULL, active && fcur <= trig)) {
+        if (active && fcur <= trig + 7) {   // every lane whose cursor is inside its lowest block joins in
+          const int blk = (trig >> 4) - 1;
+          trig = blk > 0 ? trig - 16 : kNoRefill;
+          load_block(blk);
         }
       }
       if (active) {
+        const bool bad = want_ascii & ((seen & 0x80u) != 0);
         if (qn == 0 || bad) {
           if (k < 0 || bad) {
             // ---- the string is done: the last (partial) group of words, the verdict ------------
-            uint32_t r = dist & 7u;
-            if (!bad && r) {
-              uint32_t* d = wend - dist;
-              if (r >= 4) {   // the waiting upper half of the last sector (for r == 4 it is wbuf itself)
-                *reinterpret_cast<uint4*>(d + (r - 4)) = r == 4 ? wbuf : s_stash[threadIdx.x];
-                r -= 4;
+            if (!bad) {
+              const uint32_t r = dist & 7u;   // they wait in the row: word of distance d at row[(-d) & 7]
+              for (uint32_t j = 0; j < r; j++) {
+                const uint32_t d1 = dist - j;
+                uint32_t w;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(row_b + ((0u - d1) & 7u) * 4u) : "memory");
+                *(wend - d1) = w;
               }
-              if (r > 0) d[0] = wbuf.x;
-              if (r > 1) d[1] = wbuf.y;
-              if (r > 2) d[2] = wbuf.z;
             }
             A.nlen[item] = bad ? 0u : dist;
             A.pflag[item] = bad ? 1 : 0;
             if (bad) { A.counts[s] = 0; A.need[s] = 0; A.missing[s] = 0; A.status[s] = 13; }
             active = false;
           } else if (CAP) {
-            qn = revcap_step(e, s_lut, x0, x1, x2, k,
-                             [&](int j) -> uint32_t {
-                               uint32_t c = ga[galign + j];
-                               if (to_lower && c - 'A' < 26u) c |= 0x20u;
-                               return s_cls[c];
-                             },
-                             &qbytes);
-            x0 = x1;
-            x1 = x2;
-            x2 = (k >= 3) ? take() : 0u;
+            qn = revcap_step(
+                e, [&](uint32_t i) -> uint32_t { return pipe_lds_u32<kTsLut>(sb + 4u * i); }, k,
+                [&](int j) -> uint32_t { return pipe_lds_u16<kTsChr>(sb + 2u * uint32_t(ga[galign + j])) >> 8; }, &qbytes);
+            revcap_push(e, take(k >= 3));
             k--;
           } else {
             qbytes = x0 & 0xFFu;
             qn = 1;
-            x0 = (k >= 1) ? take() : 0u;
+            x0 = take(k >= 1);
             k--;
           }
         }
         if (active && qn != 0 && !bad) {
-          const uint32_t b = (qbytes >> (8u * (qn - 1u))) & 0xFFu;
+          const uint32_t b = qbytes & 0xFFu;   // the queue leaves lowest byte first
+          qbytes >>= 8;
           qn--;
           if (dist >= slot) {   // more text than the slot holds: redone with a full-size slot
             A.nlen[item] = 0;
@@ -357,27 +402,25 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
           } else {
             packed = dfa_next(packed, b, D.shift, D.mask,
                               [&](uint32_t i, uint4* kk, uint4* vv) { pipe_load32(D.buckets + 2 * i, kk, vv); },
-                              [&](uint32_t c) { return s_d1[c]; });
-            const uint32_t code = s_code[b];
+                              [&](uint32_t c) { return pipe_lds_u32<kTsD1>(sb + 4u * c); });
+            const uint32_t code = pipe_lds_u8<kTsCode>(sb + b);
             const uint32_t w = position_word(packed, code, tr, voff);
             trail_push(tr, code);
             dist++;
             if (TEXT) tend[-int64_t(dist)] = uint8_t(b);
-            wbuf.w = wbuf.z;
-            wbuf.z = wbuf.y;
-            wbuf.y = wbuf.x;
-            wbuf.x = w;
-            // every 8th word: one 32-byte store of a whole sector (SASS: STG.256) -- the upper four
-            // words wait in shared memory in between, because a 16-byte store makes L2 fetch the rest
-            // of its sector from DRAM.  Predicated, not a branch: the lanes' phases differ.
+            // The word of distance d waits at row[(-d) & 7] of the lane's shared-memory row; every
+            // 8th word the row is a whole 32-byte sector and leaves with ONE store (SASS: STG.256 --
+            // a narrower store makes L2 fetch the rest of its sector from DRAM).  Predicated, not a
+            // branch: the lanes' phases differ.
+            const uint32_t ph = (0u - dist) & 7u;
             asm volatile(
-                "{\n\t.reg .pred p, q;\n\t.reg .b32 t0, t1, t2, t3;\n\t"
-                "setp.eq.u32 p, %5, 4;\n\t"
-                "setp.eq.u32 q, %5, 0;\n\t"
-                "@p st.shared.v4.u32 [%6], {%1, %2, %3, %4};\n\t"
-                "@q ld.shared.v4.u32 {t0, t1, t2, t3}, [%6];\n\t"
-                "@q st.global.v8.u32 [%0], {%1, %2, %3, %4, t0, t1, t2, t3};\n\t}" ::"l"(wend - dist),
-                "r"(wbuf.x), "r"(wbuf.y), "r"(wbuf.z), "r"(wbuf.w), "r"(dist & 7u), "r"(stash_b)
+                "{\n\t.reg .pred q;\n\t.reg .b32 t0, t1, t2, t3, t4, t5, t6, t7;\n\t"
+                "st.shared.u32 [%2], %1;\n\t"
+                "setp.eq.u32 q, %3, 0;\n\t"
+                "@q ld.shared.v4.u32 {t0, t1, t2, t3}, [%4];\n\t"
+                "@q ld.shared.v4.u32 {t4, t5, t6, t7}, [%4+16];\n\t"
+                "@q st.global.v8.u32 [%0], {t0, t1, t2, t3, t4, t5, t6, t7};\n\t}" ::"l"(wend - dist),
+                "r"(w), "r"(row_b + ph * 4u), "r"(ph), "r"(row_b)
                 : "memory");
           }
         }
