@@ -25,15 +25,34 @@ namespace tmgpu {
 #include "capdec_tables.inc"
 #undef TM_CAPDEC_QUAL
 
-constexpr int kCapdecCompBytes = TM_CAPDEC_ELEMS * 256;
+// The byte-indexed tables sit in shared memory with rows of 260 bytes instead of 256: text is mostly
+// lower-case letters, whose 26 codes fall into 7 of the 32 banks, and with 256-byte rows every row
+// starts in bank 0 -- lanes in different rows (states) then collide on those few banks.  The skew
+// moves row r by r banks.
+constexpr int kCapdecRow = 260;
+constexpr int kCapdecCompBytes = TM_CAPDEC_ELEMS * kCapdecRow;
 constexpr int kCapdecMulBytes = TM_CAPDEC_ELEMS * 64;
 constexpr int kCapdecApplyBytes = TM_CAPDEC_ELEMS * 16;
-constexpr int kCapdecStepBytes = 16 * 256;
+constexpr int kCapdecStepBytes = 16 * kCapdecRow;
 constexpr int kCapdecPrivStride = 20;   // bytes per lane in the private strip (5 words: conflict-free across lanes)
 
 __device__ __forceinline__ void capdec_copy_table(uint8_t* dst, const uint8_t* src, int bytes) {
   for (int i = threadIdx.x * 16; i < bytes; i += blockDim.x * 16)
     *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(src + i);
+}
+// rows of 256 bytes -> rows of kCapdecRow bytes, word by word
+__device__ __forceinline__ void capdec_copy_rows(uint8_t* dst, const uint8_t* src, int rows) {
+  for (int i = threadIdx.x; i < rows * 64; i += blockDim.x)
+    *reinterpret_cast<uint32_t*>(dst + (i >> 6) * kCapdecRow + (i & 63) * 4) = *reinterpret_cast<const uint32_t*>(src + i * 4);
+}
+// mask of the bytes [lo, hi) of a 16-byte block that fall into its 32-bit word wi (little endian)
+__device__ __forceinline__ uint32_t capdec_word_mask(int lo, int hi, int wi) {
+  int a = lo - 4 * wi, b = hi - 4 * wi;
+  a = a < 0 ? 0 : a;
+  b = b > 4 ? 4 : b;
+  if (b <= a) return 0u;
+  const uint32_t upto = b >= 4 ? 0xFFFFFFFFu : ((1u << (8 * b)) - 1u);
+  return upto & (0xFFFFFFFFu << (8 * a));   // a < b <= 4
 }
 
 __device__ __forceinline__ uint32_t capdec_byte(const uint4& w, int j) {
@@ -55,11 +74,14 @@ __global__ void __launch_bounds__(256) capcode_decode_scan_kernel(const uint8_t*
   __shared__ __align__(16) uint8_t s_step[kCapdecStepBytes];
   __shared__ __align__(16) uint8_t s_priv[8][32 * kCapdecPrivStride];
   __shared__ __align__(16) uint8_t s_win[8][512 + 16];
-  capdec_copy_table(s_comp, kCapdecComp, kCapdecCompBytes);
+  capdec_copy_rows(s_comp, kCapdecComp, TM_CAPDEC_ELEMS);
   capdec_copy_table(s_mul, kCapdecMul, kCapdecMulBytes);
   capdec_copy_table(s_apply, kCapdecApply, kCapdecApplyBytes);
-  capdec_copy_table(s_step, kCapdecStep, kCapdecStepBytes);
+  capdec_copy_rows(s_step, kCapdecStep, 16);
   __syncthreads();
+  // the text buffer is read 16 aligned bytes at a time wherever those 16 bytes lie inside it: before
+  // a string's first byte and behind its last one they belong to its neighbours
+  const uint64_t text_end = raw_off[n];
   const int lane = threadIdx.x & 31;
   uint8_t* priv = s_priv[threadIdx.x >> 5] + lane * kCapdecPrivStride;
   uint8_t* win = s_win[threadIdx.x >> 5];
@@ -88,7 +110,16 @@ __global__ void __launch_bounds__(256) capcode_decode_scan_kernel(const uint8_t*
       if (c0 >= galign && c0 + 16 <= total_c) {
         w = __ldg(reinterpret_cast<const uint4*>(ga + c0));
         hi = ((w.x | w.y | w.z | w.w) & 0x80808080u) != 0;
-      } else if (c0 < total_c) {
+      } else if (c0 < total_c && o0 >= uint64_t(galign) && (o0 - uint64_t(galign)) + uint64_t(c0) + 16u <= text_end) {
+        // the string's first / last block, its neighbours' bytes masked out (they read as 0xFF)
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(ga + c0));
+        const int lo = galign > c0 ? int(galign - c0) : 0;
+        const int hi_b = total_c - c0 < 16 ? int(total_c - c0) : 16;
+        const uint32_t m0 = capdec_word_mask(lo, hi_b, 0), m1 = capdec_word_mask(lo, hi_b, 1);
+        const uint32_t m2 = capdec_word_mask(lo, hi_b, 2), m3 = capdec_word_mask(lo, hi_b, 3);
+        hi = (((v.x & m0) | (v.y & m1) | (v.z & m2) | (v.w & m3)) & 0x80808080u) != 0;
+        w = make_uint4(v.x | ~m0, v.y | ~m1, v.z | ~m2, v.w | ~m3);
+      } else if (c0 < total_c) {   // the last bytes of the whole buffer
         uint32_t t[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
         for (int j = 0; j < 16; j++) {
           const long long c = c0 + j;
@@ -107,7 +138,7 @@ __global__ void __launch_bounds__(256) capcode_decode_scan_kernel(const uint8_t*
       // ---- 2. the effect of the 16 bytes on the state, as a monoid id ---------------------------
       uint32_t m = 0;   // identity
 #pragma unroll
-      for (int j = 0; j < 16; j++) m = s_comp[m * 256u + capdec_byte(w, j)];
+      for (int j = 0; j < 16; j++) m = s_comp[m * uint32_t(kCapdecRow) + capdec_byte(w, j)];
       // ---- 3. inclusive scan over the lanes: incl = (bytes of lanes 0..lane) -------------------
       uint32_t incl = m;
 #pragma unroll
@@ -124,7 +155,7 @@ __global__ void __launch_bounds__(256) capcode_decode_scan_kernel(const uint8_t*
 #pragma unroll
       for (int j = 0; j < 16; j++) {
         const uint32_t b = capdec_byte(w, j);
-        const uint32_t e = s_step[cur * 256u + b];
+        const uint32_t e = s_step[cur * uint32_t(kCapdecRow) + b];
         cur = e & 15u;
         if (e & 16u) {
           priv[cnt] = uint8_t(b - (e & 32u));   // upper-case bit = 32 = 'a' - 'A'
@@ -141,7 +172,15 @@ __global__ void __launch_bounds__(256) capcode_decode_scan_kernel(const uint8_t*
       // the window starts at the output's own alignment, so that whole words can be stored
       const uint32_t a = uint32_t(reinterpret_cast<uintptr_t>(out + o) & 3u);
       uint8_t* wd = win + a + (pre - cnt);
-      for (uint32_t j = 0; j < cnt; j++) wd[j] = priv[j];
+      // Byte by byte into the window.  Lanes that emitted all 16 bytes sit 16 bytes apart, i.e. lanes
+      // l, l+8, l+16, l+24 in the same banks: each group of eight starts at a different byte (0, 4,
+      // 8, 12) and wraps, so that they write different banks at every step.
+      uint32_t j = uint32_t(lane >> 3) * 4u;
+      j = j < cnt ? j : 0u;
+      for (uint32_t t = 0; t < cnt; t++) {
+        wd[j] = priv[j];
+        j = j + 1u < cnt ? j + 1u : 0u;
+      }
       __syncwarp();
       uint8_t* gout = out + o - a;   // 4-byte aligned
       const uint32_t end = a + total;

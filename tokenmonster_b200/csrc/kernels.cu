@@ -339,7 +339,11 @@ __global__ void __launch_bounds__(256) copy_tail_kernel(const uint8_t* __restric
   }
 }
 
-// dense copy of variable-length segments: src segments at src_off[s] (length len[s]) -> dst_off[s]
+// dense copy of variable-length segments: src segments at src_off[s] (length len[s]) -> dst_off[s].
+// One warp per segment, one aligned 32-bit store per lane and step: the source word that lands in
+// it straddles two aligned source words, joined by a funnel shift (source and destination are
+// misaligned against each other by the bytes the earlier segments lost).  Only bytes of the
+// segment itself are ever read.
 __global__ void __launch_bounds__(256) compact_bytes_kernel(const uint8_t* __restrict__ src,
                                                             const uint64_t* __restrict__ src_off,
                                                             const uint32_t* __restrict__ len,
@@ -351,7 +355,29 @@ __global__ void __launch_bounds__(256) compact_bytes_kernel(const uint8_t* __res
     const uint8_t* a = src + src_off[s] + (wide ? ((src_off[s] + 1) >> 1) : 0ull);
     uint8_t* b = dst + dst_off[s];
     const uint32_t l = len[s];
-    for (uint32_t k = lane; k < l; k += 32) b[k] = a[k];
+    uint32_t head = uint32_t((4u - (reinterpret_cast<uintptr_t>(b) & 3u)) & 3u);   // bytes until b is word aligned
+    head = head < l ? head : l;
+    const uint8_t* sa = a + head;
+    const uint32_t sh = uint32_t(reinterpret_cast<uintptr_t>(sa) & 3u);
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(sa - sh);   // aligned word holding sa[0]
+    uint32_t* dw = reinterpret_cast<uint32_t*>(b + head);
+    // destination word i needs source bytes [4i, 4i + 4) of sa = aligned words i and (sh ? i + 1 : none):
+    // whole words from the first whose aligned source word starts inside the segment to the last
+    // whose second source word ends inside it; the (<= 7 + 7) bytes around them one by one
+    const uint32_t rest = l - head;
+    const uint32_t i0 = (sh > head) ? 1u : 0u;
+    const uint32_t nw = sh ? (rest + sh >= 8u ? (rest + sh - 4u) >> 2 : 0u) : rest >> 2;
+    uint32_t first_end = head + 4u * i0;
+    first_end = first_end < l ? first_end : l;
+    if (lane < first_end) b[lane] = a[lane];
+    for (uint32_t i = i0 + lane; i < nw; i += 32) {
+      const uint32_t w0 = __ldg(sw + i);
+      const uint32_t w1 = sh ? __ldg(sw + i + 1) : 0u;
+      dw[i] = __funnelshift_r(w0, w1, 8u * sh);
+    }
+    uint32_t last = head + 4u * nw;
+    last = last > first_end ? last : first_end;
+    for (uint32_t k = last + lane; k < l; k += 32) b[k] = a[k];
   }
 }
 
