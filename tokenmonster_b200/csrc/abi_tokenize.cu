@@ -597,8 +597,8 @@ int stage_copy(tmgpu_vocab* v, const uint8_t* src, uint32_t n, uint64_t total_by
   // lane works on one string and a warp's 32 strings end together, so a chunk must be a few
   // "waves" of the GPU (~1000 resident lanes per SM) for the longest-first order to balance it:
   // chunks of ~1.1 waves were measured at 2 waves' time each (17.3 ms per 512 MB batch instead of 14).
-  static const uint32_t lanes_per_sm = getenv("TMGPU_CHUNK_LANES") ? uint32_t(atoi(getenv("TMGPU_CHUNK_LANES"))) : 2048u;   // experiment
-  int want = int(n / (uint32_t(v->sms) * (lanes_per_sm ? lanes_per_sm : 2048u)));
+  static const uint32_t lanes_per_sm = getenv("TMGPU_CHUNK_LANES") ? uint32_t(atoi(getenv("TMGPU_CHUNK_LANES"))) : 1280u;   // diagnostic: strings per SM and chunk
+  int want = int(n / (uint32_t(v->sms) * (lanes_per_sm ? lanes_per_sm : 1280u)));
   if (want > 8) want = 8;
   if (want < 1) want = 1;
   if (plan) plan->clear();

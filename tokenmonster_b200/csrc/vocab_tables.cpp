@@ -4,6 +4,7 @@
 #include "vocab_tables.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string_view>
 #include <unordered_map>
@@ -210,7 +211,8 @@ static int build_dfa(HostTables* t, const std::vector<KeyRef>& keys, const std::
   size_t n_deep = 0;
   for (uint32_t s = 1; s < N; s++) n_deep += row[s].size();
   uint32_t bits = 4;
-  while ((size_t(1) << bits) * 2 < n_deep) bits++;   // on average <= 2 of 4 slots used
+  static const size_t per_bucket = getenv("TMGPU_DFA_PER_BUCKET") ? size_t(atoi(getenv("TMGPU_DFA_PER_BUCKET"))) : 2;   // experiment
+  while ((size_t(1) << bits) * (per_bucket ? per_bucket : 2) < n_deep) bits++;   // on average <= 2 of 4 slots used
   t->dfa_bits = bits;
   const uint32_t mask = (1u << bits) - 1u, shift = 32u - bits;
   t->dfa_buckets.assign((size_t(1) << bits) * 8, 0);
