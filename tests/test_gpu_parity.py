@@ -367,7 +367,7 @@ def test_poisoned_workspace_decode_twice(built):
 
 
 def test_host_path_streams_ids_out_in_chunks(built):
-    """A batch big enough for the chunked host path (>= 2 x 2048 strings per SM): the ids leave the GPU
+    """A batch big enough for the chunked host path (several chunks of 1280 strings per SM): the ids leave the GPU
     chunk by chunk.  First call sizes the pinned buffer by guess, the second by the first's yield;
     a non-ASCII string forces the fallback (one copy at the end).  All three must equal the
     device-resident single launch and the oracle."""

@@ -594,10 +594,12 @@ int stage_copy(tmgpu_vocab* v, const uint8_t* src, uint32_t n, uint64_t total_by
                        v->copy_stream));
   CU(cudaEventRecord(v->chunk_ev[31], v->copy_stream));
   // Chunks of ~equal bytes: the kernels of chunk k run while chunk k+1 is still on the wire.  One
-  // lane works on one string and a warp's 32 strings end together, so a chunk must be a few
-  // "waves" of the GPU (~1000 resident lanes per SM) for the longest-first order to balance it:
-  // chunks of ~1.1 waves were measured at 2 waves' time each (17.3 ms per 512 MB batch instead of 14).
-  static const uint32_t lanes_per_sm = getenv("TMGPU_CHUNK_LANES") ? uint32_t(atoi(getenv("TMGPU_CHUNK_LANES"))) : 1280u;   // diagnostic: strings per SM and chunk
+  // lane works on one string and a warp's 32 strings end together, so a chunk must be more than a
+  // "wave" of the GPU (1024 resident lanes per SM) for the longest-first order to balance it, while
+  // the call ends with the last chunk's kernels and ids, which want it small.  Measured per 512 MB
+  // call (1 M strings, pinned input) with 2048 / 1536 / 1280 / 1024 strings per SM and chunk, i.e.
+  // 3 / 4 / 5 / 6 chunks: 15.8 / 15.4 / 14.95 ms on one box, 15.4 (1280) / 16.5-17.1 (1024) on another.
+  static const uint32_t lanes_per_sm = getenv("TMGPU_CHUNK_LANES") ? uint32_t(atoi(getenv("TMGPU_CHUNK_LANES"))) : 1280u;   // diagnostic override
   int want = int(n / (uint32_t(v->sms) * (lanes_per_sm ? lanes_per_sm : 1280u)));
   if (want > 8) want = 8;
   if (want < 1) want = 1;

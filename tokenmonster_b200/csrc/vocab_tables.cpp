@@ -211,8 +211,10 @@ static int build_dfa(HostTables* t, const std::vector<KeyRef>& keys, const std::
   size_t n_deep = 0;
   for (uint32_t s = 1; s < N; s++) n_deep += row[s].size();
   uint32_t bits = 4;
-  static const size_t per_bucket = getenv("TMGPU_DFA_PER_BUCKET") ? size_t(atoi(getenv("TMGPU_DFA_PER_BUCKET"))) : 2;   // experiment
-  while ((size_t(1) << bits) * (per_bucket ? per_bucket : 2) < n_deep) bits++;   // on average <= 2 of 4 slots used
+  // on average <= 2 of 4 slots used.  (Twice the buckets -- <= 1 of 4 -- halves the second probes, yet
+  // measured no faster on c2, 4.75 against 4.71 ms, and 9.3 against 6.3 ms on c5, whose table then
+  // misses L2.)
+  while ((size_t(1) << bits) * 2 < n_deep) bits++;
   t->dfa_bits = bits;
   const uint32_t mask = (1u << bits) - 1u, shift = 32u - bits;
   t->dfa_buckets.assign((size_t(1) << bits) * 8, 0);
