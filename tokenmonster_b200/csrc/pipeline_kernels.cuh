@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(kPipeBlock) table_kernel(const TokenizeArgs A)
 // (Five CTAs per SM instead of four was measured: the 51-register budget spills and the kernel is
 // 0.3 ms slower on c2, 0.7 ms on c3.)
 template <bool STORE>
-__global__ void __launch_bounds__(kPipeBlock) chain_kernel(const TokenizeArgs A) {
+__global__ void __launch_bounds__(kPipeBlock, 4) chain_kernel(const TokenizeArgs A) {
   constexpr unsigned FULL = 0xFFFFFFFFu;
   ChainTables T;
   T.crec = A.v.dfa.crec;
@@ -448,6 +448,19 @@ __global__ void __launch_bounds__(kPipeBlock) chain_kernel(const TokenizeArgs A)
   uint32_t* counter = A.pipe_counters + 3;
   const bool two_ids = STORE || A.scores != nullptr;
   const int lane = threadIdx.x & 31;
+  // Ids leave in whole 32-byte sectors: the id with slab index g waits at word g & 15 of the lane's
+  // shared-memory row (two sectors: a step emits up to two ids and may finish one sector and begin
+  // the next) and a finished, aligned group of eight goes out with one STG.256 after the step (a
+  // 4-byte store per id and lane was 20 of the ~100 L1 wavefronts of a step).  The ends of a string
+  // that do not fill a sector go out one by one.
+  constexpr uint32_t kRowBytes = 80;   // 16 words + 16: an odd number of 16-byte units
+  __shared__ __align__(16) uint8_t s_rows[STORE ? kPipeBlock * kRowBytes : 16];
+  const uint32_t row_b = pipe_smem_u32(s_rows) + (STORE ? uint32_t(threadIdx.x) * kRowBytes : 0u);
+  auto row_word = [&](uint32_t g) -> uint32_t {
+    uint32_t w;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(row_b + (g & 15u) * 4u) : "memory");
+    return w;
+  };
 
   for (;;) {
     uint32_t g = 0;
@@ -484,9 +497,19 @@ __global__ void __launch_bounds__(kPipeBlock) chain_kernel(const TokenizeArgs A)
         active = true;
       }
     }
+    const uint32_t base_lo = uint32_t(slab_base) & 7u;
+    auto put = [&](uint32_t id, uint32_t& stored) {
+      if (STORE && stored < cap)
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(row_b + ((base_lo + stored) & 15u) * 4u), "r"(id) : "memory");
+      stored++;
+    };
     while (__any_sync(FULL, active)) {
       if (!active) continue;
       if (z.i >= S.len) {
+        if (STORE) {   // the ids behind the last complete group of eight
+          const uint32_t cntc = min(z.cnt, cap), rem = (base_lo + cntc) & 7u;
+          for (uint32_t k = cntc > rem ? cntc - rem : 0u; k < cntc; k++) A.slab[slab_base + k] = row_word(base_lo + k);
+        }
         A.counts[s] = STORE ? min(z.cnt, cap) : z.cnt;
         A.need[s] = z.cnt;
         A.missing[s] = z.miss;
@@ -496,12 +519,12 @@ __global__ void __launch_bounds__(kPipeBlock) chain_kernel(const TokenizeArgs A)
         continue;
       }
       uint32_t stored = z.cnt;   // ids stored so far follow the lane's own count
+      const uint32_t g_before = base_lo + min(stored, cap);
       chain_step(
           T, S, z, two_ids, [&](const uint4* tab, uint32_t idx, uint4* a, uint4* b) { pipe_load32(tab + 2 * idx, a, b); },
           [&](uint32_t id, uint32_t, uint32_t adv) {
             if (!STORE && A.scores) atomicAdd(&A.scores[id], static_cast<unsigned long long>(adv));
-            if (STORE && stored < cap) A.slab[slab_base + stored] = id;
-            stored++;
+            put(id, stored);
           },
           [&](int pos) -> uint32_t {
             if (!STORE && A.scores) {   // trainvocab.go:1164-1171: counted, never scored
@@ -509,12 +532,28 @@ __global__ void __launch_bounds__(kPipeBlock) chain_kernel(const TokenizeArgs A)
               return 1u;
             }
             if (A.v.unk != 0xFFFFFFu) {
-              if (STORE && stored < cap) A.slab[slab_base + stored] = A.v.unk;
-              stored++;
+              put(A.v.unk, stored);
               return 1u;
             }
             return 0u;
           });
+      if (STORE) {
+        // did this step finish a group of eight?  (at most one: a step stages at most two ids)
+        const uint32_t g_after = base_lo + min(stored, cap);
+        const uint32_t m = g_after >> 3;                       // groups 0 .. m-1 are complete now
+        const bool done = m != (g_before >> 3);
+        const bool whole = done & ((m > 1u) | (base_lo == 0u));   // group m-1 starts inside this string's ids
+        asm volatile(
+            "{\n\t.reg .pred q;\n\t.reg .b32 t0, t1, t2, t3, t4, t5, t6, t7;\n\t"
+            "setp.ne.u32 q, %1, 0;\n\t"
+            "@q ld.shared.v4.u32 {t0, t1, t2, t3}, [%2];\n\t"
+            "@q ld.shared.v4.u32 {t4, t5, t6, t7}, [%2+16];\n\t"
+            "@q st.global.v8.u32 [%0], {t0, t1, t2, t3, t4, t5, t6, t7};\n\t}" ::"l"(A.slab + (slab_base - base_lo + 8u * (m - 1u))),
+            "r"(uint32_t(whole)), "r"(row_b + ((m - 1u) & 1u) * 32u)
+            : "memory");
+        if (done && !whole)   // the string's first ids end a sector they do not fill (once per string)
+          for (uint32_t k = 0; k < 8u - base_lo; k++) A.slab[slab_base + k] = row_word(base_lo + k);
+      }
     }
   }
 }
