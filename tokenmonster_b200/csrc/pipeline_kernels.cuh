@@ -497,7 +497,9 @@ __global__ void __launch_bounds__(kPipeBlock, 4) chain_kernel(const TokenizeArgs
         active = true;
       }
     }
-    const uint32_t base_lo = uint32_t(slab_base) & 7u;
+    // position of the string's first id inside its 32-byte sector (the slab pointer of a chunk launch
+    // is itself only 4-byte aligned, so this comes from the address, not from the index)
+    const uint32_t base_lo = uint32_t(reinterpret_cast<uintptr_t>(A.slab + slab_base) >> 2) & 7u;
     auto put = [&](uint32_t id, uint32_t& stored) {
       if (STORE && stored < cap)
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(row_b + ((base_lo + stored) & 15u) * 4u), "r"(id) : "memory");
