@@ -196,3 +196,27 @@ def test_capcode_decode_scan_equals_oracle(sim):
             got, gst = run(bytes([b]), 0, st)
             assert got == want and gst == wst, (b, st)
     assert run(b"abc\xc3\xa9", 3, 0) == (None, None)   # non-ASCII text is left to the per-code-point kernel
+
+
+def test_committed_capdec_tables_match_their_generator():
+    """csrc/capdec_tables.inc (compiled into the decode kernel) is what gen_capdec_tables.py produces:
+    44 monoid elements, composition / application / step tables entry by entry."""
+    import importlib.util
+    import re
+    src = os.path.join(ROOT, "tokenmonster_b200", "csrc")
+    spec = importlib.util.spec_from_file_location("gen_capdec_tables", os.path.join(src, "gen_capdec_tables.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    n, comp, mul, apply_, stp = gen.tables()
+    text = open(os.path.join(src, "capdec_tables.inc")).read()
+    assert int(re.search(r"#define TM_CAPDEC_ELEMS (\d+)", text).group(1)) == n == 44
+    for name, want in (("kCapdecComp", comp), ("kCapdecMul", mul), ("kCapdecApply", apply_), ("kCapdecStep", stp)):
+        body = re.search(name + r"\[\d+\] = \{([^}]*)\}", text).group(1)
+        got = [int(x) for x in body.replace("\n", " ").split(",") if x.strip()]
+        assert got == want, name
+    # the monoid really is closed and the identity is element 0
+    assert all(mul[0 * 64 + b] == b and mul[b * 64 + 0] == b for b in range(n))
+    for a in range(n):
+        for b in range(n):
+            ab = mul[a * 64 + b]
+            assert all(apply_[ab * 16 + s] == apply_[b * 16 + apply_[a * 16 + s]] for s in range(16))
