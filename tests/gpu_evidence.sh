@@ -31,7 +31,7 @@ head -c 600 gpurun_out/${TAG}_bench_c2_n1.json; echo
 python tests/gpu_bench_decode.py > gpurun_out/${TAG}_decode.log 2>&1; tail -2 gpurun_out/${TAG}_decode.log
 for C in "c3 1000000" "c5 300000"; do python tests/gpu_profile_pipeline.py $C 4 2>&1 | tail -1; done | tee gpurun_out/${TAG}_stage_times.log
 echo "== launch list of the bench command"
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"tmgpu|DeviceScan|DeviceRadixSort" -c 400 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"kernel|DeviceScan|DeviceRadixSort" -c 400 --csv \
     --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/${TAG}_bench_under_ncu.log 2>&1
 echo "== full captures: table + chain (c2, 1M strings), decode kernels"
 ncu --set full --clock-control none --import-source on -k regex:"table_kernel|chain_kernel" -s 2 -c 2 -o gpurun_out/${TAG}_pipeline_full \
