@@ -21,8 +21,9 @@
 // every lane, so the warp executes their code almost every iteration for one or two lanes (ncu:
 // 13-20 of 32 lanes active, profiles/r02_v1_*).  With equal lengths the lanes stay in phase: they
 // start together, refill together and end together.  Per-lane loads are 16-byte vectors
-// wherever the data is a stream: with one string per lane every load instruction touches 32
-// different lines, and the L1 pipeline charges per line.
+// wherever the data is a stream, and what a lane produces (position words, ids) collects in a
+// shared-memory row and leaves as whole 32-byte sectors: with one string per lane every memory
+// instruction touches 32 different lines, and the L1 pipeline charges per line.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -160,8 +161,9 @@ __global__ void __launch_bounds__(256) select_overflowed_kernel(const uint8_t* _
 // stages 1 + 2: capcode encoder and reversed-key automaton in one right-to-left loop.
 // A warp takes 32 strings of (nearly) equal length; every iteration each lane consumes exactly one
 // normalized byte: if its byte queue is empty it first encodes the next raw character (0..4 bytes,
-// one table read decides), then the automaton takes one byte and the position word goes out (16
-// bytes at a time, right aligned in the string's slot, so the slot's start need not be known).
+// one table read decides), then the automaton takes one byte and the position word goes out (a
+// whole 32-byte sector at a time, right aligned in the string's slot, so the slot's start need
+// not be known).
 // (Splitting the loop into two phases -- encode 8 characters into a shared-memory buffer, then the
 // automaton over their bytes -- was measured slower: 6.6 against 5.6 ms.)
 // Raw text comes in through a 32-byte ring per lane in shared memory, filled 16 bytes at a time
